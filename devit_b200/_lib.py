@@ -1,0 +1,242 @@
+"""ctypes binding of ``libdevit_b200.so`` (the C ABI declared in ``include/devit_b200.h``).
+
+This module is deliberately thin: it only turns torch tensors into raw device pointers and
+forwards the current CUDA stream.  There is no fallback -- if the shared library is missing the
+import of any compute entry point raises, and on a non-sm_100 device every call returns
+``DEVIT_ERR_DEVICE`` which is re-raised here as ``DevitError``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import torch
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "lib" / "libdevit_b200.so"
+
+DEVIT_BF16, DEVIT_FP32 = 0, 1
+OUT_BF16, OUT_F32, OUT_F32_SPLIT = 0, 1, 2
+ACT_NONE, ACT_GELU_ERF = 0, 1
+
+
+class DevitError(RuntimeError):
+    pass
+
+
+class GemmSeg(C.Structure):
+    _fields_ = [("a_row_off", C.c_int32), ("a_k_off", C.c_int32), ("b_k_off", C.c_int32),
+                ("k_len", C.c_int32)]
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [
+        ("precision", C.c_int32), ("m", C.c_int32), ("n", C.c_int32),
+        ("a", C.c_void_p), ("a_rows", C.c_int32), ("a_cols", C.c_int32), ("lda", C.c_int64),
+        ("a_plane_stride", C.c_int64),
+        ("b", C.c_void_p), ("b_rows", C.c_int32), ("b_cols", C.c_int32), ("ldb", C.c_int64),
+        ("b_plane_stride", C.c_int64),
+        ("num_segs", C.c_int32), ("segs", GemmSeg * 8),
+        ("out", C.c_void_p), ("ldo", C.c_int64), ("out_kind", C.c_int32),
+        ("out_plane_stride", C.c_int64),
+        ("bias", C.c_void_p), ("resid", C.c_void_p), ("ldr", C.c_int64),
+        ("rowbias", C.c_void_p), ("ld_rowbias", C.c_int64),
+        ("act", C.c_int32), ("alpha", C.c_float),
+        ("rowmap_period", C.c_int32), ("rowmap_stride", C.c_int32), ("rowmap_off", C.c_int32),
+        ("block_n", C.c_int32),
+    ]
+
+
+class LayerDesc(C.Structure):
+    _fields_ = [
+        ("heads", C.c_int32), ("hidden", C.c_int32), ("hidden_ld", C.c_int32),
+        ("ln1_g", C.c_void_p), ("ln1_b", C.c_void_p),
+        ("w_qkv", C.c_void_p), ("b_qkv", C.c_void_p),
+        ("w_proj", C.c_void_p), ("b_proj", C.c_void_p),
+        ("ln2_g", C.c_void_p), ("ln2_b", C.c_void_p),
+        ("w_fc1", C.c_void_p), ("b_fc1", C.c_void_p),
+        ("w_fc2", C.c_void_p), ("b_fc2", C.c_void_p),
+    ]
+
+
+class VitDesc(C.Structure):
+    _fields_ = [
+        ("precision", C.c_int32), ("dim", C.c_int32), ("depth", C.c_int32),
+        ("img", C.c_int32), ("chans", C.c_int32), ("num_prefix", C.c_int32),
+        ("ln_eps", C.c_float),
+        ("w_patch", C.c_void_p), ("b_patch", C.c_void_p),
+        ("prefix", C.c_void_p), ("pos", C.c_void_p),
+        ("norm_g", C.c_void_p), ("norm_b", C.c_void_p),
+        ("layers", C.POINTER(LayerDesc)),
+        ("w_plane_stride_unused", C.c_int64),
+    ]
+
+
+# name -> (restype, argtypes); this table is also what tests/test_abi.py checks against the header
+_SIGS = {
+    "devit_abi_version": (C.c_int, []),
+    "devit_last_error": (C.c_char_p, []),
+    "devit_device_check": (C.c_int, []),
+    "devit_launch_count": (C.c_longlong, []),
+    "devit_gemm": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
+    "devit_layernorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                  C.c_int32, C.c_float, C.c_int32, C.c_int64, C.c_void_p]),
+    "devit_attention": (C.c_int, [C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                  C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p]),
+    "devit_im2col_patch16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                       C.c_int32, C.c_int64, C.c_void_p]),
+    "devit_token_prefix": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                     C.c_int32, C.c_int32, C.c_void_p]),
+    "devit_gather_ln": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                  C.c_int32, C.c_float, C.c_void_p]),
+    "devit_vit_workspace_bytes": (C.c_size_t, [C.POINTER(VitDesc), C.c_int32]),
+    "devit_vit_forward": (C.c_int, [C.POINTER(VitDesc), C.c_void_p, C.c_int32, C.c_void_p,
+                                    C.c_size_t, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                    C.c_int32, C.c_void_p]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the shared library (once).  Raises DevitError with build instructions if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = Path(os.environ.get("DEVIT_B200_LIB", LIB_PATH))
+    if not path.exists():
+        raise DevitError(
+            f"{path} not found: build it with `python -c 'import __graft_entry__ as g; "
+            f"g.build()'` or `make -C devit_b200/csrc`. devit_b200 has no CPU/PyTorch fallback.")
+    lib = C.CDLL(str(path))
+    for name, (res, args) in _SIGS.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.devit_abi_version() != 1:
+        raise DevitError("libdevit_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def exported_symbols() -> list[str]:
+    return list(_SIGS)
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = load().devit_last_error().decode(errors="replace")
+        raise DevitError(f"devit_b200 error {rc}: {msg}")
+
+
+def ptr(t: torch.Tensor | None) -> int | None:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise DevitError("devit_b200 kernels need CUDA tensors (there is no CPU fallback)")
+    return t.data_ptr()
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+# ------------------------------------------------------------------------------------------
+# Convenience wrappers used by the modules and the tests.  Operand tensors:
+#   DEVIT_BF16: torch.bfloat16 [rows, cols]
+#   DEVIT_FP32: torch.float32  [2, rows, cols]   (hi plane, lo plane)
+# ------------------------------------------------------------------------------------------
+def split_tf32(t: torch.Tensor) -> torch.Tensor:
+    """fp32 [..] -> [2, ..] (hi exactly representable in tf32, hi + lo == t)."""
+    t = t.contiguous().float()
+    bits = t.view(torch.int32)
+    hi = ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
+    return torch.stack([hi, t - hi], 0).contiguous()
+
+
+def to_operand(t: torch.Tensor, precision: int) -> torch.Tensor:
+    if precision == DEVIT_BF16:
+        return t.to(torch.bfloat16).contiguous()
+    return split_tf32(t)
+
+
+def operand_to_f32(t: torch.Tensor, precision: int) -> torch.Tensor:
+    if precision == DEVIT_BF16:
+        return t.float()
+    return t[0] + t[1]
+
+
+def gemm(a, b, *, precision=DEVIT_BF16, m=None, n=None, segs=None, out=None,
+         out_kind=OUT_BF16, bias=None, resid=None, rowbias=None, act=ACT_NONE, alpha=1.0,
+         rowmap=(0, 0, 0), block_n=0, out_rows=None):
+    """out = epilogue(sum_s A_s B_s^T); see include/devit_b200.h (devit_gemm)."""
+    lib = load()
+    planes = 1 if precision == DEVIT_BF16 else 2
+    a2 = a if planes == 1 else a[0]
+    b2 = b if planes == 1 else b[0]
+    a_rows, a_cols = a2.shape
+    b_rows, b_cols = b2.shape
+    if segs is None:
+        segs = [(0, 0, 0, a_cols)]
+    m = a_rows if m is None else m
+    n = b_rows if n is None else n
+    if out is None:
+        rows = m if out_rows is None else out_rows
+        if out_kind == OUT_BF16:
+            out = torch.empty(rows, n, device=a.device, dtype=torch.bfloat16)
+        elif out_kind == OUT_F32:
+            out = torch.empty(rows, n, device=a.device, dtype=torch.float32)
+        else:
+            out = torch.empty(2, rows, n, device=a.device, dtype=torch.float32)
+    o2 = out[0] if out_kind == OUT_F32_SPLIT else out
+    g = GemmArgs()
+    g.precision, g.m, g.n = precision, m, n
+    g.a, g.a_rows, g.a_cols, g.lda = ptr(a), a_rows, a_cols, a2.stride(0)
+    g.a_plane_stride = a.stride(0) if planes == 2 else 0
+    g.b, g.b_rows, g.b_cols, g.ldb = ptr(b), b_rows, b_cols, b2.stride(0)
+    g.b_plane_stride = b.stride(0) if planes == 2 else 0
+    g.num_segs = len(segs)
+    for i, s in enumerate(segs):
+        g.segs[i] = GemmSeg(*s)
+    g.out, g.ldo, g.out_kind = ptr(out), o2.stride(0), out_kind
+    g.out_plane_stride = out.stride(0) if out_kind == OUT_F32_SPLIT else 0
+    g.bias = ptr(bias)
+    g.resid = ptr(resid)
+    g.ldr = resid.stride(0) if resid is not None else 0
+    g.rowbias = ptr(rowbias)
+    g.ld_rowbias = rowbias.stride(0) if rowbias is not None else 0
+    g.act, g.alpha = act, alpha
+    g.rowmap_period, g.rowmap_stride, g.rowmap_off = rowmap
+    g.block_n = block_n
+    check(lib.devit_gemm(C.byref(g), stream_ptr()))
+    return out
+
+
+def layernorm(x, gamma, beta, eps, out_kind=OUT_BF16):
+    lib = load()
+    rows, dim = x.shape
+    if out_kind == OUT_BF16:
+        y = torch.empty(rows, dim, device=x.device, dtype=torch.bfloat16)
+    elif out_kind == OUT_F32:
+        y = torch.empty(rows, dim, device=x.device, dtype=torch.float32)
+    else:
+        y = torch.empty(2, rows, dim, device=x.device, dtype=torch.float32)
+    check(lib.devit_layernorm(ptr(x), ptr(gamma), ptr(beta), ptr(y), rows, dim, eps, out_kind,
+                              rows * dim, stream_ptr()))
+    return y
+
+
+def attention(qkv, batch, tokens, heads, scale, precision=DEVIT_BF16):
+    lib = load()
+    rows = batch * tokens
+    if precision == DEVIT_BF16:
+        out = torch.empty(rows, heads * 64, device=qkv.device, dtype=torch.bfloat16)
+        check(lib.devit_attention(precision, ptr(qkv), 0, ptr(out), 0, batch, tokens, heads,
+                                  scale, stream_ptr()))
+    else:
+        out = torch.empty(2, rows, heads * 64, device=qkv.device, dtype=torch.float32)
+        check(lib.devit_attention(precision, ptr(qkv), qkv.stride(0), ptr(out), out.stride(0),
+                                  batch, tokens, heads, scale, stream_ptr()))
+    return out

@@ -1,0 +1,403 @@
+// Fused multi-head attention for ViT-sized sequences (tokens <= 256, head_dim 64), see
+// include/devit_b200.h devit_attention.  Replaces models/de_vit.py:70-74.
+//
+// bf16 path (attn_bf16_kernel): one CTA per (query tile of 128 rows, kept head, image).
+//   TMA pulls the Q tile and the head's whole K and V straight out of the QKV-GEMM output
+//   (3-D tensor map [image][token][3*h*64]; rows past `tokens` are zero-filled), so no
+//   head-major copy exists anywhere.  S = Q K^T is ONE accumulation chain of 4 UMMAs into
+//   TMEM (128 x KVP fp32); because every key of the head fits in that tile the softmax is
+//   single pass (no online rescale): 128 threads each own one TMEM lane = one query row,
+//   read it twice (max, then exp2/sum), and write P as bf16 into shared memory in the
+//   K-major 128B-swizzled layout the tensor core expects.  O = P V runs as KVP/16 UMMAs with
+//   V consumed in place as an MN-major operand, accumulating over the dead S columns.
+//   The epilogue scales by 1/rowsum and stores 128 contiguous bytes per row into
+//   out[token, head*64 ..], which is exactly the A operand of the proj GEMM.
+//   ~92 KB smem and 256 TMEM columns per CTA -> two CTAs per SM, so one CTA's softmax
+//   overlaps the other's loads and MMAs.
+// fp32 path (attn_f32_kernel): CUDA-core fp32 for the parity mode.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace devit {
+
+constexpr int kAttnThreads = 160;  // 4 softmax warps + 1 control warp
+
+template <int KVP>
+struct AttnCfg {
+  static constexpr int kAtoms = (KVP + 63) / 64;
+  static constexpr int kQBytes = 128 * 128;
+  static constexpr int kKVBytes = KVP * 128;
+  static constexpr int kPBytes = kAtoms * 16384;
+  static constexpr int kOffK = kQBytes;
+  static constexpr int kQKEnd = kQBytes + kKVBytes;
+  static constexpr int kOffV = ((kQKEnd > kPBytes ? kQKEnd : kPBytes) + 1023) / 1024 * 1024;
+  static constexpr int kOffBar = kOffV + kKVBytes;
+  static constexpr int kSmemBytes = kOffBar + 64 + 1024;
+  static constexpr int kTmemCols = KVP <= 64 ? 64 : (KVP <= 128 ? 128 : 256);
+};
+
+template <int KVP>
+__global__ void __launch_bounds__(kAttnThreads, 2)
+attn_bf16_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                 __nv_bfloat16* __restrict__ out, int tokens, int heads, float scale_log2e) {
+  using Cfg = AttnCfg<KVP>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + Cfg::kOffK;
+  uint8_t* sP = smem;  // overlays Q and K once S has been computed
+  uint8_t* sV = smem + Cfg::kOffV;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBar);
+  uint64_t* bar_qk = bars + 0;
+  uint64_t* bar_v = bars + 1;
+  uint64_t* bar_s = bars + 2;
+  uint64_t* bar_p = bars + 3;
+  uint64_t* bar_o = bars + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int mtile = blockIdx.x;
+  const int head = blockIdx.y;
+  const int img = blockIdx.z;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmQ);
+      tma_prefetch_desc(&tmKV);
+      mbar_init(bar_qk, 1);
+      mbar_init(bar_v, 1);
+      mbar_init(bar_s, 1);
+      mbar_init(bar_p, 128);
+      mbar_init(bar_o, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      // ---- loads
+      mbar_expect_tx(bar_qk, Cfg::kQBytes + Cfg::kKVBytes);
+      tma_load_3d(sQ, &tmQ, bar_qk, head * 64, mtile * 128, img);
+      tma_load_3d(sK, &tmKV, bar_qk, (heads + head) * 64, 0, img);
+      mbar_expect_tx(bar_v, Cfg::kKVBytes);
+      tma_load_3d(sV, &tmKV, bar_v, (2 * heads + head) * 64, 0, img);
+      // ---- S = Q K^T   (M=128, N=KVP, K=64: 4 UMMAs of K=16)
+      mbar_wait(bar_qk, 0);
+      tc_fence_after();
+      {
+        const uint32_t idesc = make_idesc(kFmtBF16, 128, KVP, 0, 0);
+        const uint64_t dq = make_sw128_desc(smem_u32(sQ), 1024, 16);
+        const uint64_t dk = make_sw128_desc(smem_u32(sK), 1024, 16);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, dq + 2 * k, dk + 2 * k, idesc, k > 0);
+        umma_commit(bar_s);
+      }
+      // ---- O = P V     (M=128, N=64, K=KVP: KVP/16 UMMAs; V is MN-major, 16 keys = 2 KB)
+      mbar_wait(bar_p, 0);
+      tc_fence_after();
+      mbar_wait(bar_v, 0);
+      tc_fence_after();
+      {
+        const uint32_t idesc = make_idesc(kFmtBF16, 128, 64, 0, 1);
+        const uint32_t p0 = smem_u32(sP);
+        const uint32_t v0 = smem_u32(sV);
+#pragma unroll
+        for (int k = 0; k < KVP / 16; ++k) {
+          const uint64_t dp = make_sw128_desc(p0 + (k >> 2) * 16384 + (k & 3) * 32, 1024, 16);
+          const uint64_t dv = make_sw128_desc(v0 + k * 2048, 1024, 1024);
+          umma_bf16(tmem_base, dp, dv, idesc, k > 0);
+        }
+        umma_commit(bar_o);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ softmax + epilogue warps
+    const int row_in_tile = warp * 32 + lane;
+    const int row = mtile * 128 + row_in_tile;
+    const bool warp_live = (mtile * 128 + warp * 32) < tokens;  // any valid row in this warp
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    constexpr int kFull = KVP / 32;
+    constexpr int kTail = KVP % 32;  // 0 or 16
+
+    mbar_wait(bar_s, 0);
+    tc_fence_after();
+    float inv_sum = 0.f;
+    if (warp_live) {
+      // pass 1: row max over the valid keys
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < kFull; ++c) {
+        uint32_t r[32];
+        tmem_ld_x32(t_row + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (c * 32 + j < tokens) mx = fmaxf(mx, __uint_as_float(r[j]));
+      }
+      if (kTail) {
+        uint32_t r[16];
+        tmem_ld_x16(t_row + kFull * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (kFull * 32 + j < tokens) mx = fmaxf(mx, __uint_as_float(r[j]));
+      }
+      const float moff = mx * scale_log2e;
+      // pass 2: p = exp2(s*c - max*c), row sum, P -> smem (bf16, K-major, 128B swizzle)
+      float sum = 0.f;
+      uint8_t* prow = sP + row_in_tile * 128;
+      const int sw = row_in_tile & 7;
+#pragma unroll 1
+      for (int c = 0; c < kFull; ++c) {
+        uint32_t r[32];
+        tmem_ld_x32(t_row + c * 32, r);
+        tmem_ld_wait();
+        float pv[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float e = fast_exp2(fmaf(__uint_as_float(r[j]), scale_log2e, -moff));
+          e = (c * 32 + j < tokens) ? e : 0.f;
+          sum += e;
+          pv[j] = e;
+        }
+        uint8_t* atom = prow + (c >> 1) * 16384;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 t;
+          t.x = pack_bf16x2(pv[8 * g], pv[8 * g + 1]);
+          t.y = pack_bf16x2(pv[8 * g + 2], pv[8 * g + 3]);
+          t.z = pack_bf16x2(pv[8 * g + 4], pv[8 * g + 5]);
+          t.w = pack_bf16x2(pv[8 * g + 6], pv[8 * g + 7]);
+          const int chunk = (c & 1) * 4 + g;
+          *reinterpret_cast<uint4*>(atom + ((chunk ^ sw) << 4)) = t;
+        }
+      }
+      if (kTail) {
+        uint32_t r[16];
+        tmem_ld_x16(t_row + kFull * 32, r);
+        tmem_ld_wait();
+        float pv[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float e = fast_exp2(fmaf(__uint_as_float(r[j]), scale_log2e, -moff));
+          e = (kFull * 32 + j < tokens) ? e : 0.f;
+          sum += e;
+          pv[j] = e;
+        }
+        uint8_t* atom = prow + (kFull >> 1) * 16384;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          uint4 t;
+          t.x = pack_bf16x2(pv[8 * g], pv[8 * g + 1]);
+          t.y = pack_bf16x2(pv[8 * g + 2], pv[8 * g + 3]);
+          t.z = pack_bf16x2(pv[8 * g + 4], pv[8 * g + 5]);
+          t.w = pack_bf16x2(pv[8 * g + 6], pv[8 * g + 7]);
+          const int chunk = (kFull & 1) * 4 + g;
+          *reinterpret_cast<uint4*>(atom + ((chunk ^ sw) << 4)) = t;
+        }
+      }
+      inv_sum = 1.0f / sum;
+    }
+    // P (generic-proxy writes) must be visible to the tensor core (async proxy); S reads done.
+    fence_proxy_async_smem();
+    tc_fence_before();
+    mbar_arrive(bar_p);
+
+    mbar_wait(bar_o, 0);
+    tc_fence_after();
+    if (warp_live) {
+      uint32_t r0[32], r1[32];
+      tmem_ld_x32(t_row, r0);
+      tmem_ld_x32(t_row + 32, r1);
+      tmem_ld_wait();
+      if (row < tokens) {
+        __nv_bfloat16* o =
+            out + (static_cast<long long>(img) * tokens + row) * (heads * 64) + head * 64;
+        uint4* o4 = reinterpret_cast<uint4*>(o);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 t;
+          t.x = pack_bf16x2(__uint_as_float(r0[8 * g]) * inv_sum, __uint_as_float(r0[8 * g + 1]) * inv_sum);
+          t.y = pack_bf16x2(__uint_as_float(r0[8 * g + 2]) * inv_sum, __uint_as_float(r0[8 * g + 3]) * inv_sum);
+          t.z = pack_bf16x2(__uint_as_float(r0[8 * g + 4]) * inv_sum, __uint_as_float(r0[8 * g + 5]) * inv_sum);
+          t.w = pack_bf16x2(__uint_as_float(r0[8 * g + 6]) * inv_sum, __uint_as_float(r0[8 * g + 7]) * inv_sum);
+          o4[g] = t;
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 t;
+          t.x = pack_bf16x2(__uint_as_float(r1[8 * g]) * inv_sum, __uint_as_float(r1[8 * g + 1]) * inv_sum);
+          t.y = pack_bf16x2(__uint_as_float(r1[8 * g + 2]) * inv_sum, __uint_as_float(r1[8 * g + 3]) * inv_sum);
+          t.z = pack_bf16x2(__uint_as_float(r1[8 * g + 4]) * inv_sum, __uint_as_float(r1[8 * g + 5]) * inv_sum);
+          t.w = pack_bf16x2(__uint_as_float(r1[8 * g + 6]) * inv_sum, __uint_as_float(r1[8 * g + 7]) * inv_sum);
+          o4[4 + g] = t;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------- fp32 parity path
+// One CTA per (head, image); K (padded rows, conflict-free) and V live in shared memory as
+// fp32; each warp owns query rows round-robin.
+constexpr int kF32Threads = 256;
+
+__global__ void __launch_bounds__(kF32Threads)
+attn_f32_kernel(const float* __restrict__ qkv, long long in_plane, float* __restrict__ out,
+                long long out_plane, int tokens, int heads, float scale) {
+  extern __shared__ float sm[];
+  float* sK = sm;                       // [tokens][65]
+  float* sV = sK + tokens * 65;         // [tokens][64]
+  float* sP = sV + tokens * 64;         // [8][256]
+  float* sQ = sP + 8 * 256;             // [8][64]
+  const int head = blockIdx.x, img = blockIdx.y;
+  const int ld = 3 * heads * 64;
+  const float* base = qkv + static_cast<long long>(img) * tokens * ld;
+  for (int i = threadIdx.x; i < tokens * 64; i += kF32Threads) {
+    const int t = i >> 6, d = i & 63;
+    const long long ko = static_cast<long long>(t) * ld + (heads + head) * 64 + d;
+    const long long vo = static_cast<long long>(t) * ld + (2 * heads + head) * 64 + d;
+    sK[t * 65 + d] = base[ko] + base[ko + in_plane];
+    sV[t * 64 + d] = base[vo] + base[vo + in_plane];
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* myP = sP + warp * 256;
+  float* myQ = sQ + warp * 64;
+  for (int row = warp; row < tokens; row += 8) {
+    const long long qo = static_cast<long long>(row) * ld + head * 64;
+    myQ[lane] = base[qo + lane] + base[qo + lane + in_plane];
+    myQ[lane + 32] = base[qo + lane + 32] + base[qo + lane + 32 + in_plane];
+    __syncwarp();
+    float s[8];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int j = lane + 32 * i;
+      float acc = 0.f;
+      if (j < tokens) {
+        const float* kr = sK + j * 65;
+#pragma unroll 16
+        for (int d = 0; d < 64; ++d) acc = fmaf(myQ[d], kr[d], acc);
+        acc *= scale;
+        mx = fmaxf(mx, acc);
+      }
+      s[i] = acc;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int j = lane + 32 * i;
+      if (j < tokens) {
+        const float e = expf(s[i] - mx);
+        sum += e;
+        myP[j] = e;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    __syncwarp();
+    float o0 = 0.f, o1 = 0.f;
+    for (int j = 0; j < tokens; ++j) {
+      const float pj = myP[j];
+      o0 = fmaf(pj, sV[j * 64 + lane], o0);
+      o1 = fmaf(pj, sV[j * 64 + lane + 32], o1);
+    }
+    const float inv = 1.0f / sum;
+    o0 *= inv;
+    o1 *= inv;
+    float* orow = out + (static_cast<long long>(img) * tokens + row) * (heads * 64) + head * 64;
+    const float h0 = tf32_hi(o0), h1 = tf32_hi(o1);
+    orow[lane] = h0;
+    orow[lane + 32] = h1;
+    orow[lane + out_plane] = o0 - h0;
+    orow[lane + 32 + out_plane] = o1 - h1;
+    __syncwarp();
+  }
+}
+
+template <int KVP>
+static int launch_attn_bf16(const void* qkv, void* out, int batch, int tokens, int heads,
+                            float scale, cudaStream_t stream) {
+  using Cfg = AttnCfg<KVP>;
+  static bool attr_done[64] = {};
+  int dev = 0;
+  DEVIT_CUDA_OK(cudaGetDevice(&dev));
+  if (!attr_done[dev & 63]) {
+    DEVIT_CUDA_OK(cudaFuncSetAttribute(attn_bf16_kernel<KVP>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Cfg::kSmemBytes));
+    attr_done[dev & 63] = true;
+  }
+  const uint64_t ld = 3ull * heads * 64;
+  CUtensorMap tq, tkv;
+  int rc = encode_tmap_3d(&tq, qkv, 2, ld, tokens, batch, ld, ld * tokens, 64, 128, 1);
+  if (rc) return rc;
+  rc = encode_tmap_3d(&tkv, qkv, 2, ld, tokens, batch, ld, ld * tokens, 64, KVP, 1);
+  if (rc) return rc;
+  dim3 grid((tokens + 127) / 128, heads, batch);
+  attn_bf16_kernel<KVP><<<grid, kAttnThreads, Cfg::kSmemBytes, stream>>>(
+      tq, tkv, static_cast<__nv_bfloat16*>(out), tokens, heads,
+      scale * 1.4426950408889634f);
+  DEVIT_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return DEVIT_OK;
+}
+
+}  // namespace devit
+
+extern "C" int devit_attention(int32_t precision, const void* qkv, int64_t qkv_plane_stride,
+                               void* out, int64_t out_plane_stride, int32_t batch,
+                               int32_t tokens, int32_t heads, float scale, void* stream_v) {
+  using namespace devit;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  int rc = check_device();
+  if (rc) return rc;
+  DEVIT_REQUIRE(qkv && out, "devit_attention: null pointer");
+  DEVIT_REQUIRE(batch > 0 && heads > 0 && tokens > 0 && tokens <= 256,
+                "devit_attention: need batch>0, heads>0, 0<tokens<=256 (got %d,%d,%d)", batch,
+                heads, tokens);
+  if (precision == DEVIT_BF16) {
+    const int kvp = (tokens + 15) & ~15;
+    if (kvp <= 64) return launch_attn_bf16<64>(qkv, out, batch, tokens, heads, scale, stream);
+    if (kvp <= 208) return launch_attn_bf16<208>(qkv, out, batch, tokens, heads, scale, stream);
+    return launch_attn_bf16<256>(qkv, out, batch, tokens, heads, scale, stream);
+  }
+  DEVIT_REQUIRE(precision == DEVIT_FP32, "devit_attention: bad precision %d", precision);
+  DEVIT_REQUIRE(qkv_plane_stride > 0 && out_plane_stride > 0,
+                "devit_attention: DEVIT_FP32 needs plane strides");
+  const size_t smem = static_cast<size_t>(tokens) * (65 + 64) * 4 + 8 * 256 * 4 + 8 * 64 * 4;
+  static bool attr_done[64] = {};
+  int dev = 0;
+  DEVIT_CUDA_OK(cudaGetDevice(&dev));
+  if (!attr_done[dev & 63]) {
+    DEVIT_CUDA_OK(cudaFuncSetAttribute(attn_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       256 * (65 + 64) * 4 + 8 * 256 * 4 + 8 * 64 * 4));
+    attr_done[dev & 63] = true;
+  }
+  dim3 grid(heads, batch);
+  attn_f32_kernel<<<grid, kF32Threads, smem, stream>>>(
+      static_cast<const float*>(qkv), qkv_plane_stride, static_cast<float*>(out),
+      out_plane_stride, tokens, heads, scale);
+  DEVIT_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return DEVIT_OK;
+}

@@ -1,0 +1,144 @@
+#include "common.cuh"
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <mutex>
+
+namespace devit {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+struct DevInfo {
+  int major = -1, minor = -1, sms = 0;
+};
+static DevInfo g_dev[64];
+static std::mutex g_dev_mu;
+
+static int device_info(DevInfo* out) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess)
+    return set_error(DEVIT_ERR_DEVICE, "no CUDA device: %s", cudaGetErrorString(e));
+  if (dev < 0 || dev >= 64) return set_error(DEVIT_ERR_DEVICE, "device index %d unsupported", dev);
+  std::lock_guard<std::mutex> lk(g_dev_mu);
+  if (g_dev[dev].major < 0) {
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, dev);
+    if (e != cudaSuccess)
+      return set_error(DEVIT_ERR_DEVICE, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    g_dev[dev].major = prop.major;
+    g_dev[dev].minor = prop.minor;
+    g_dev[dev].sms = prop.multiProcessorCount;
+  }
+  *out = g_dev[dev];
+  return DEVIT_OK;
+}
+
+int check_device() {
+  DevInfo d;
+  int rc = device_info(&d);
+  if (rc) return rc;
+  if (d.major != 10)
+    return set_error(DEVIT_ERR_DEVICE,
+                     "devit_b200 needs an sm_100 (B200) device, found sm_%d%d; there is no "
+                     "fallback path",
+                     d.major, d.minor);
+  return DEVIT_OK;
+}
+
+int num_sms() {
+  DevInfo d;
+  if (device_info(&d)) return 1;
+  return d.sms > 0 ? d.sms : 1;
+}
+
+// ------------------------------------------------------------------ tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) ==
+            cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+static int encode(CUtensorMap* map, const void* base, int elem_bytes, int rank,
+                  const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                  const cuuint32_t* box, bool weight_like) {
+  EncodeTiledFn fn = get_encode();
+  if (!fn) return set_error(DEVIT_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0)
+    return set_error(DEVIT_ERR_ARG, "TMA base pointer %p is not 16-byte aligned", base);
+  for (int i = 0; i < rank - 1; ++i)
+    if (strides_bytes[i] % 16 != 0)
+      return set_error(DEVIT_ERR_ARG, "TMA stride %llu bytes is not a multiple of 16",
+                       (unsigned long long)strides_bytes[i]);
+  if (box[0] * (cuuint32_t)elem_bytes != 128)
+    return set_error(DEVIT_ERR_ARG, "TMA inner box must be 128 bytes for SWIZZLE_128B");
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUtensorMapDataType dt =
+      elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  CUresult r = fn(map, dt, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  weight_like ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                              : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(DEVIT_ERR_CUDA,
+                     "cuTensorMapEncodeTiled failed (CUresult %d; rank %d dims %llu,%llu box "
+                     "%u,%u)",
+                     (int)r, rank, (unsigned long long)dims[0], (unsigned long long)dims[1],
+                     box[0], box[1]);
+  return DEVIT_OK;
+}
+
+int encode_tmap_2d(CUtensorMap* map, const void* base, int elem_bytes, uint64_t cols,
+                   uint64_t rows, uint64_t ld, uint32_t box_cols, uint32_t box_rows,
+                   bool weight_like) {
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * (uint64_t)elem_bytes};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  return encode(map, base, elem_bytes, 2, dims, strides, box, weight_like);
+}
+
+int encode_tmap_3d(CUtensorMap* map, const void* base, int elem_bytes, uint64_t d0, uint64_t d1,
+                   uint64_t d2, uint64_t stride1, uint64_t stride2, uint32_t box0,
+                   uint32_t box1, uint32_t box2) {
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {stride1 * (uint64_t)elem_bytes, stride2 * (uint64_t)elem_bytes};
+  cuuint32_t box[3] = {box0, box1, box2};
+  return encode(map, base, elem_bytes, 3, dims, strides, box, false);
+}
+
+}  // namespace devit
+
+extern "C" {
+
+int devit_abi_version(void) { return DEVIT_ABI_VERSION; }
+const char* devit_last_error(void) { return devit::g_err; }
+int devit_device_check(void) { return devit::check_device(); }
+long long devit_launch_count(void) { return devit::g_launches.load(); }
+
+}  // extern "C"

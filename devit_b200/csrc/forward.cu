@@ -1,0 +1,206 @@
+// Whole-sub-model forward (VisionTransformer.forward_features, models/de_vit.py:242-292) as one
+// C call that enqueues every kernel on the caller's stream: im2col -> patch GEMM (+bias +pos,
+// row-remapped into the token matrix) -> cls/dist rows -> depth x [LN, QKV GEMM, attention,
+// proj GEMM (+residual), LN, fc1 GEMM (+GELU), fc2 GEMM (+residual)] -> final LN on the
+// cls/dist rows only.  Gated heads / neurons never appear: the host packs compacted weights.
+#include <cstring>
+
+#include "common.cuh"
+
+namespace devit {
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct VitLayout {
+  int tokens, grid, max_heads, max_hidden_ld, planes, esz;
+  long long M;
+  size_t off_x, off_y, off_qkv, off_o, off_hid, total;
+};
+
+static int plan_layout(const devit_vit_desc* d, int batch, VitLayout* L) {
+  DEVIT_REQUIRE(d && d->layers, "devit_vit: null descriptor");
+  DEVIT_REQUIRE(d->precision == DEVIT_BF16 || d->precision == DEVIT_FP32,
+                "devit_vit: bad precision %d", d->precision);
+  DEVIT_REQUIRE(d->dim == 256 || d->dim == 384 || d->dim == 768,
+                "devit_vit: dim %d not in {256,384,768}", d->dim);
+  DEVIT_REQUIRE(d->depth > 0 && d->img > 0 && d->img % 16 == 0 && d->chans > 0 && batch > 0,
+                "devit_vit: bad geometry");
+  DEVIT_REQUIRE(d->num_prefix == 1 || d->num_prefix == 2, "devit_vit: num_prefix must be 1 or 2");
+  L->grid = d->img / 16;
+  L->tokens = L->grid * L->grid + d->num_prefix;
+  DEVIT_REQUIRE(L->tokens <= 256, "devit_vit: %d tokens exceed the attention kernel's 256",
+                L->tokens);
+  L->M = static_cast<long long>(batch) * L->tokens;
+  L->planes = d->precision == DEVIT_BF16 ? 1 : 2;
+  L->esz = d->precision == DEVIT_BF16 ? 2 : 4;
+  L->max_heads = 0;
+  L->max_hidden_ld = 0;
+  for (int l = 0; l < d->depth; ++l) {
+    const devit_layer_desc& y = d->layers[l];
+    DEVIT_REQUIRE(y.heads >= 1 && y.heads * 64 <= d->dim, "devit_vit: layer %d heads %d", l,
+                  y.heads);
+    DEVIT_REQUIRE(y.hidden >= 1 && y.hidden_ld >= y.hidden && y.hidden_ld % 16 == 0,
+                  "devit_vit: layer %d hidden %d / ld %d (ld must be a multiple of 16)", l,
+                  y.hidden, y.hidden_ld);
+    if (y.heads > L->max_heads) L->max_heads = y.heads;
+    if (y.hidden_ld > L->max_hidden_ld) L->max_hidden_ld = y.hidden_ld;
+  }
+  const size_t pe = static_cast<size_t>(L->planes) * L->esz;
+  size_t off = 0;
+  L->off_x = off;
+  off = align_up(off + static_cast<size_t>(L->M) * d->dim * 4, 256);
+  L->off_y = off;
+  off = align_up(off + static_cast<size_t>(L->M) * d->dim * pe, 256);
+  L->off_qkv = off;
+  const size_t qkv_b = static_cast<size_t>(L->M) * 3 * L->max_heads * 64 * pe;
+  const size_t patch_b = static_cast<size_t>(batch) * L->grid * L->grid * d->chans * 256 * pe;
+  off = align_up(off + (qkv_b > patch_b ? qkv_b : patch_b), 256);
+  L->off_o = off;
+  off = align_up(off + static_cast<size_t>(L->M) * L->max_heads * 64 * pe, 256);
+  L->off_hid = off;
+  off = align_up(off + static_cast<size_t>(L->M) * L->max_hidden_ld * pe, 256);
+  L->total = off;
+  return DEVIT_OK;
+}
+
+static void base_gemm(devit_gemm_args* g, int precision) {
+  std::memset(g, 0, sizeof(*g));
+  g->precision = precision;
+  g->num_segs = 1;
+  g->alpha = 1.0f;
+}
+
+}  // namespace devit
+
+using namespace devit;
+
+extern "C" size_t devit_vit_workspace_bytes(const devit_vit_desc* desc, int32_t batch) {
+  VitLayout L;
+  if (plan_layout(desc, batch, &L)) return 0;
+  return L.total;
+}
+
+extern "C" int devit_vit_forward(const devit_vit_desc* d, const float* images, int32_t batch,
+                                 void* workspace, size_t workspace_bytes, float* feats_f32,
+                                 void* feats_op, int64_t feats_op_plane_stride, float* x_out,
+                                 int32_t num_layers_run, void* stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  VitLayout L;
+  rc = plan_layout(d, batch, &L);
+  if (rc) return rc;
+  DEVIT_REQUIRE(images && workspace, "devit_vit_forward: null pointer");
+  DEVIT_REQUIRE(reinterpret_cast<uintptr_t>(workspace) % 256 == 0,
+                "devit_vit_forward: workspace must be 256-byte aligned");
+  if (workspace_bytes < L.total)
+    return set_error(DEVIT_ERR_WORKSPACE, "devit_vit_forward: workspace %zu < required %zu",
+                     workspace_bytes, L.total);
+  const int prec = d->precision;
+  const int opk = prec == DEVIT_BF16 ? DEVIT_OUT_BF16 : DEVIT_OUT_F32_SPLIT;
+  const int D = d->dim;
+  const long long M = L.M;
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  float* x = reinterpret_cast<float*>(ws + L.off_x);
+  void* y = ws + L.off_y;
+  void* qkv = ws + L.off_qkv;
+  void* o = ws + L.off_o;
+  void* hid = ws + L.off_hid;
+  const int P = L.grid * L.grid;
+  const int kp = d->chans * 256;
+  const long long Mp = static_cast<long long>(batch) * P;
+
+  // ---- patch embedding as a GEMM; the epilogue adds bias + pos_embed and scatters patch p of
+  //      image b to token row b*tokens + num_prefix + p            (models/de_vit.py:258-264)
+  rc = devit_im2col_patch16(images, qkv, batch, d->chans, d->img, opk, Mp * kp, stream);
+  if (rc) return rc;
+  devit_gemm_args g;
+  base_gemm(&g, prec);
+  g.m = static_cast<int>(Mp);
+  g.n = D;
+  g.a = qkv; g.a_rows = static_cast<int>(Mp); g.a_cols = kp; g.lda = kp; g.a_plane_stride = Mp * kp;
+  g.b = d->w_patch; g.b_rows = D; g.b_cols = kp; g.ldb = kp;
+  g.b_plane_stride = static_cast<long long>(D) * kp;
+  g.segs[0] = devit_gemm_seg{0, 0, 0, kp};
+  g.out = x; g.ldo = D; g.out_kind = DEVIT_OUT_F32;
+  g.bias = d->b_patch;
+  g.rowbias = d->pos; g.ld_rowbias = D;
+  g.rowmap_period = P; g.rowmap_stride = L.tokens; g.rowmap_off = d->num_prefix;
+  rc = devit_gemm(&g, stream);
+  if (rc) return rc;
+  rc = devit_token_prefix(x, d->prefix, d->pos, batch, L.tokens, D, d->num_prefix, stream);
+  if (rc) return rc;
+
+  const int nl = (num_layers_run < 0 || num_layers_run > d->depth) ? d->depth : num_layers_run;
+  for (int l = 0; l < nl; ++l) {
+    const devit_layer_desc& w = d->layers[l];
+    const int hd = w.heads * 64;
+    // x -> LN1 -> y                                              (models/de_vit.py:113)
+    rc = devit_layernorm(x, w.ln1_g, w.ln1_b, y, M, D, d->ln_eps, opk, M * D, stream);
+    if (rc) return rc;
+    // qkv = y Wqkv^T + b                                         (:67)
+    base_gemm(&g, prec);
+    g.m = static_cast<int>(M); g.n = 3 * hd;
+    g.a = y; g.a_rows = static_cast<int>(M); g.a_cols = D; g.lda = D; g.a_plane_stride = M * D;
+    g.b = w.w_qkv; g.b_rows = 3 * hd; g.b_cols = D; g.ldb = D;
+    g.b_plane_stride = static_cast<long long>(3 * hd) * D;
+    g.segs[0] = devit_gemm_seg{0, 0, 0, D};
+    g.out = qkv; g.ldo = 3 * hd; g.out_kind = opk; g.out_plane_stride = M * 3 * hd;
+    g.bias = w.b_qkv;
+    rc = devit_gemm(&g, stream);
+    if (rc) return rc;
+    // o = softmax(q k^T / 8) v  per kept head                    (:70-74)
+    rc = devit_attention(prec, qkv, M * 3 * hd, o, M * hd, batch, L.tokens, w.heads, 0.125f,
+                         stream);
+    if (rc) return rc;
+    // x += o Wproj^T + b                                         (:81, :114)
+    base_gemm(&g, prec);
+    g.m = static_cast<int>(M); g.n = D;
+    g.a = o; g.a_rows = static_cast<int>(M); g.a_cols = hd; g.lda = hd; g.a_plane_stride = M * hd;
+    g.b = w.w_proj; g.b_rows = D; g.b_cols = hd; g.ldb = hd;
+    g.b_plane_stride = static_cast<long long>(D) * hd;
+    g.segs[0] = devit_gemm_seg{0, 0, 0, hd};
+    g.out = x; g.ldo = D; g.out_kind = DEVIT_OUT_F32;
+    g.bias = w.b_proj; g.resid = x; g.ldr = D;
+    rc = devit_gemm(&g, stream);
+    if (rc) return rc;
+    // x -> LN2 -> y                                              (:115)
+    rc = devit_layernorm(x, w.ln2_g, w.ln2_b, y, M, D, d->ln_eps, opk, M * D, stream);
+    if (rc) return rc;
+    // hid = gelu(y W1^T + b1), kept neurons only                 (:36-37)
+    const int F = w.hidden_ld;
+    base_gemm(&g, prec);
+    g.m = static_cast<int>(M); g.n = F;
+    g.a = y; g.a_rows = static_cast<int>(M); g.a_cols = D; g.lda = D; g.a_plane_stride = M * D;
+    g.b = w.w_fc1; g.b_rows = F; g.b_cols = D; g.ldb = D;
+    g.b_plane_stride = static_cast<long long>(F) * D;
+    g.segs[0] = devit_gemm_seg{0, 0, 0, D};
+    g.out = hid; g.ldo = F; g.out_kind = opk; g.out_plane_stride = M * F;
+    g.bias = w.b_fc1; g.act = DEVIT_ACT_GELU_ERF;
+    rc = devit_gemm(&g, stream);
+    if (rc) return rc;
+    // x += hid W2^T + b2                                         (:45, :115)
+    base_gemm(&g, prec);
+    g.m = static_cast<int>(M); g.n = D;
+    g.a = hid; g.a_rows = static_cast<int>(M); g.a_cols = F; g.lda = F; g.a_plane_stride = M * F;
+    g.b = w.w_fc2; g.b_rows = D; g.b_cols = F; g.ldb = F;
+    g.b_plane_stride = static_cast<long long>(D) * F;
+    g.segs[0] = devit_gemm_seg{0, 0, 0, F};
+    g.out = x; g.ldo = D; g.out_kind = DEVIT_OUT_F32;
+    g.bias = w.b_fc2; g.resid = x; g.ldr = D;
+    rc = devit_gemm(&g, stream);
+    if (rc) return rc;
+  }
+  if (x_out) {
+    DEVIT_CUDA_OK(cudaMemcpyAsync(x_out, x, static_cast<size_t>(M) * D * 4,
+                                  cudaMemcpyDeviceToDevice,
+                                  reinterpret_cast<cudaStream_t>(stream)));
+  }
+  // final norm on the returned rows only                         (:286-288)
+  if (feats_f32 || feats_op) {
+    rc = devit_gather_ln(x, d->norm_g, d->norm_b, feats_f32, feats_op, opk,
+                         feats_op_plane_stride, batch, L.tokens, D, d->num_prefix, d->ln_eps,
+                         stream);
+    if (rc) return rc;
+  }
+  return DEVIT_OK;
+}

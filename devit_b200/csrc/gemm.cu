@@ -1,0 +1,480 @@
+// Persistent, warp-specialised tcgen05 GEMM with a fused epilogue (see include/devit_b200.h,
+// devit_gemm).  out = epilogue(sum_s A_s * B_s^T), A and B K-major, fp32 accumulation in TMEM.
+//
+// CTA = 192 threads: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM owner),
+// warps 2..5 = epilogue (TMEM -> registers -> global).  Three pipelines:
+//   smem ring   : full[s] / empty[s] mbarriers between TMA and the MMA issuer,
+//   TMEM ring   : two accumulator stages, tmem_full[2] / tmem_empty[2] between the MMA issuer
+//                 and the epilogue warps, so the epilogue of tile i overlaps the MMAs of i+1,
+//   tile loop   : static round-robin over (m_blk, n_blk), n fastest so CTAs that are resident
+//                 together share the same A rows in L2.
+// Tile = 128 x BN (BN in {128,192,256}); each k-block is one 128-byte swizzle atom along K
+// (64 bf16 or 32 tf32) = 4 UMMA instructions.  The last N tile issues a narrower UMMA
+// (N rounded up to 16) so ragged shrunk widths do not pay for a full tile.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace devit {
+
+constexpr int kBlockM = 128;
+constexpr int kGemmThreads = 192;
+constexpr int kMaxKSegs = 24;  // 8 logical segments x 3 passes in the 3xTF32 mode
+
+struct KSeg {
+  int a_row_off, a_k_off, b_k_off, k_blocks;
+  int a_plane, b_plane;
+};
+
+struct GemmKParams {
+  int M, N;
+  int num_segs;
+  KSeg segs[kMaxKSegs];
+  void* out;
+  long long ldo;
+  int out_kind;
+  long long out_plane_stride;
+  const float* bias;
+  const float* resid;
+  long long ldr;
+  const float* rowbias;
+  long long ld_rowbias;
+  int act;
+  float alpha;
+  int rowmap_period, rowmap_stride, rowmap_off;
+  int vec_ok;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kStageA = kBlockM * 128;
+  static constexpr int kStageB = BN * 128;
+  static constexpr int kStageBytes = kStageA + kStageB;
+  static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
+  static constexpr int kAccStride = BN <= 128 ? 128 : 256;
+  static constexpr int kTmemCols = 2 * kAccStride;
+  static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;
+};
+
+// Applies the epilogue to `cnt` consecutive columns held in v[] and stores them.
+// FULL = all 32 columns valid and every pointer suitably aligned -> 16-byte vector path.
+template <bool FULL>
+__device__ __forceinline__ void epilogue_store(const GemmKParams& p, float* v, int cnt,
+                                               long long row_out, int rb_row, int col0) {
+  if (p.bias) {
+    if (FULL) {
+      const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 t = __ldg(b4 + j);
+        v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+      }
+    } else {
+      for (int j = 0; j < cnt; ++j) v[j] += __ldg(p.bias + col0 + j);
+    }
+  }
+  if (p.act == DEVIT_ACT_GELU_ERF) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+  }
+  if (p.rowbias) {
+    const float* rb = p.rowbias + (long long)rb_row * p.ld_rowbias + col0;
+    if (FULL) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 t = __ldg(reinterpret_cast<const float4*>(rb) + j);
+        v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+      }
+    } else {
+      for (int j = 0; j < cnt; ++j) v[j] += __ldg(rb + j);
+    }
+  }
+  if (p.resid) {
+    const float* rs = p.resid + row_out * p.ldr + col0;
+    if (FULL) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 t = *(reinterpret_cast<const float4*>(rs) + j);
+        v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+      }
+    } else {
+      for (int j = 0; j < cnt; ++j) v[j] += rs[j];
+    }
+  }
+  if (p.alpha != 1.0f) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
+  }
+  if (p.out_kind == DEVIT_OUT_BF16) {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + row_out * p.ldo + col0;
+    if (FULL) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 t;
+        t.x = pack_bf16x2(v[8 * j], v[8 * j + 1]);
+        t.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+        t.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+        t.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+        *(reinterpret_cast<uint4*>(o) + j) = t;
+      }
+    } else {
+      for (int j = 0; j < cnt; ++j) o[j] = __float2bfloat16_rn(v[j]);
+    }
+  } else if (p.out_kind == DEVIT_OUT_F32) {
+    float* o = reinterpret_cast<float*>(p.out) + row_out * p.ldo + col0;
+    if (FULL) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *(reinterpret_cast<float4*>(o) + j) =
+            make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    } else {
+      for (int j = 0; j < cnt; ++j) o[j] = v[j];
+    }
+  } else {  // split fp32: hi plane + lo plane
+    float* o = reinterpret_cast<float*>(p.out) + row_out * p.ldo + col0;
+    float* ol = o + p.out_plane_stride;
+    if (FULL) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float h0 = tf32_hi(v[4 * j]), h1 = tf32_hi(v[4 * j + 1]), h2 = tf32_hi(v[4 * j + 2]),
+              h3 = tf32_hi(v[4 * j + 3]);
+        *(reinterpret_cast<float4*>(o) + j) = make_float4(h0, h1, h2, h3);
+        *(reinterpret_cast<float4*>(ol) + j) =
+            make_float4(v[4 * j] - h0, v[4 * j + 1] - h1, v[4 * j + 2] - h2, v[4 * j + 3] - h3);
+      }
+    } else {
+      for (int j = 0; j < cnt; ++j) {
+        float h = tf32_hi(v[j]);
+        o[j] = h;
+        ol[j] = v[j] - h;
+      }
+    }
+  }
+}
+
+template <int BN, int KIND>  // KIND: 0 = bf16 operands, 1 = fp32 operands consumed as tf32
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+            const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
+            const __grid_constant__ GemmKParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int kElem = KIND == 0 ? 2 : 4;
+  constexpr int kBlockK = 128 / kElem;  // elements per k-block (one swizzle atom)
+  constexpr int kStages = Cfg::kStages;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full = empty_bar + kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmB0);
+    if (KIND == 1) {
+      tma_prefetch_desc(&tmA1);
+      tma_prefetch_desc(&tmB1);
+    }
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_m = (p.M + kBlockM - 1) / kBlockM;
+  const int num_n = (p.N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / num_n) * kBlockM;
+        const int n0 = (tile % num_n) * BN;
+        for (int s = 0; s < p.num_segs; ++s) {
+          const KSeg sg = p.segs[s];
+          const CUtensorMap* ma = (KIND == 1 && sg.a_plane) ? &tmA1 : &tmA0;
+          const CUtensorMap* mb = (KIND == 1 && sg.b_plane) ? &tmB1 : &tmB0;
+          for (int kb = 0; kb < sg.k_blocks; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * Cfg::kStageBytes;
+            uint8_t* sb = sa + Cfg::kStageA;
+            mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            tma_load_2d(sa, ma, &full_bar[stage], sg.a_k_off + kb * kBlockK, sg.a_row_off + m0);
+            tma_load_2d(sb, mb, &full_bar[stage], sg.b_k_off + kb * kBlockK, n0);
+            if (++stage == kStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n0 = (tile % num_n) * BN;
+        int n_cur = p.N - n0;
+        n_cur = n_cur >= BN ? BN : ((n_cur + 15) & ~15);
+        const uint32_t idesc = make_idesc(KIND == 0 ? kFmtBF16 : kFmtTF32, kBlockM, n_cur, 0, 0);
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * Cfg::kAccStride;
+        uint32_t accumulate = 0;
+        for (int s = 0; s < p.num_segs; ++s) {
+          const int kbs = p.segs[s].k_blocks;
+          for (int kb = 0; kb < kbs; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+            const uint32_t sb = sa + Cfg::kStageA;
+            const uint64_t da = make_sw128_desc(sa, 1024, 16);
+            const uint64_t db = make_sw128_desc(sb, 1024, 16);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              // advance 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
+              if (KIND == 0)
+                umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, accumulate);
+              else
+                umma_tf32(d_tmem, da + 2 * k, db + 2 * k, idesc, accumulate);
+              accumulate = 1;
+            }
+            umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+            if (++stage == kStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps
+    const int quarter = warp & 3;  // TMEM lanes [32*quarter, +32)
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / num_n) * kBlockM;
+      const int n0 = (tile % num_n) * BN;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const int m = m0 + quarter * 32 + lane;
+      const bool row_ok = m < p.M;
+      long long row_out = m;
+      int rb_row = 0;
+      if (p.rowmap_period > 0) {
+        const int q = m / p.rowmap_period;
+        const int r = m - q * p.rowmap_period;
+        rb_row = p.rowmap_off + r;
+        row_out = (long long)q * p.rowmap_stride + rb_row;
+      }
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                             acc * Cfg::kAccStride;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = n0 + c * 32;
+        if (col0 >= p.N) break;
+        uint32_t r[32];
+        __syncwarp();
+        tmem_ld_x32(t_row + c * 32, r);
+        tmem_ld_wait();
+        if (row_ok) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          const int cnt = p.N - col0;
+          if (cnt >= 32 && p.vec_ok)
+            epilogue_store<true>(p, v, 32, row_out, rb_row, col0);
+          else
+            epilogue_store<false>(p, v, cnt < 32 ? cnt : 32, row_out, rb_row, col0);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <int BN, int KIND>
+static int launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b0,
+                       const CUtensorMap& b1, const GemmKParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_done[64] = {};  // per device; benign race: the attribute set is idempotent
+  int dev = 0;
+  DEVIT_CUDA_OK(cudaGetDevice(&dev));
+  if (!attr_done[dev & 63]) {
+    DEVIT_CUDA_OK(cudaFuncSetAttribute(gemm_kernel<BN, KIND>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Cfg::kSmemBytes));
+    attr_done[dev & 63] = true;
+  }
+  const int num_tiles = ((p.M + kBlockM - 1) / kBlockM) * ((p.N + BN - 1) / BN);
+  int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+  gemm_kernel<BN, KIND><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(a0, a1, b0, b1, p);
+  DEVIT_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return DEVIT_OK;
+}
+
+static int pick_block_n(int n) {
+  int best = 128, best_waste = 1 << 30;
+  const int cands[3] = {256, 192, 128};
+  for (int i = 0; i < 3; ++i) {
+    const int bn = cands[i];
+    const int waste = ((n + bn - 1) / bn) * bn - n;
+    if (waste < best_waste) {
+      best_waste = waste;
+      best = bn;
+    }
+  }
+  return best;
+}
+
+}  // namespace devit
+
+extern "C" int devit_gemm(const devit_gemm_args* a, void* stream_v) {
+  using namespace devit;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  DEVIT_REQUIRE(a != nullptr, "devit_gemm: null args");
+  int rc = check_device();
+  if (rc) return rc;
+  DEVIT_REQUIRE(a->precision == DEVIT_BF16 || a->precision == DEVIT_FP32,
+                "devit_gemm: bad precision %d", a->precision);
+  DEVIT_REQUIRE(a->m > 0 && a->n > 0, "devit_gemm: empty problem m=%d n=%d", a->m, a->n);
+  DEVIT_REQUIRE(a->a && a->b && a->out, "devit_gemm: null operand");
+  DEVIT_REQUIRE(a->num_segs >= 1 && a->num_segs <= 8, "devit_gemm: num_segs %d not in [1,8]",
+                a->num_segs);
+  DEVIT_REQUIRE(a->out_kind >= DEVIT_OUT_BF16 && a->out_kind <= DEVIT_OUT_F32_SPLIT,
+                "devit_gemm: bad out_kind %d", a->out_kind);
+  DEVIT_REQUIRE(!(a->resid && a->out_kind == DEVIT_OUT_BF16 &&
+                  static_cast<const void*>(a->resid) == a->out),
+                "devit_gemm: resid may alias out only for fp32 outputs");
+  const int kind = a->precision == DEVIT_BF16 ? 0 : 1;
+  const int elem = kind == 0 ? 2 : 4;
+  const int block_k = 128 / elem;
+
+  GemmKParams p;
+  p.M = a->m;
+  p.N = a->n;
+  p.num_segs = 0;
+  for (int s = 0; s < a->num_segs; ++s) {
+    const devit_gemm_seg& g = a->segs[s];
+    DEVIT_REQUIRE(g.k_len > 0 && g.a_k_off >= 0 && g.b_k_off >= 0 && g.a_row_off >= 0,
+                  "devit_gemm: bad segment %d", s);
+    DEVIT_REQUIRE(g.a_k_off % (16 / elem) == 0 && g.b_k_off % (16 / elem) == 0,
+                  "devit_gemm: segment %d K offsets must be 16-byte aligned", s);
+    const bool ragged = g.k_len % block_k != 0;
+    DEVIT_REQUIRE(!ragged || (g.a_k_off + g.k_len == a->a_cols && g.b_k_off + g.k_len == a->b_cols),
+                  "devit_gemm: segment %d has a ragged K (%d) that does not end at the operand "
+                  "edge",
+                  s, g.k_len);
+    const int kbs = (g.k_len + block_k - 1) / block_k;
+    if (kind == 0) {
+      p.segs[p.num_segs++] = KSeg{g.a_row_off, g.a_k_off, g.b_k_off, kbs, 0, 0};
+    } else {  // 3xTF32: small cross terms first, then hi*hi
+      p.segs[p.num_segs++] = KSeg{g.a_row_off, g.a_k_off, g.b_k_off, kbs, 1, 0};
+      p.segs[p.num_segs++] = KSeg{g.a_row_off, g.a_k_off, g.b_k_off, kbs, 0, 1};
+      p.segs[p.num_segs++] = KSeg{g.a_row_off, g.a_k_off, g.b_k_off, kbs, 0, 0};
+    }
+  }
+  p.out = a->out;
+  p.ldo = a->ldo;
+  p.out_kind = a->out_kind;
+  p.out_plane_stride = a->out_plane_stride;
+  p.bias = a->bias;
+  p.resid = a->resid;
+  p.ldr = a->ldr;
+  p.rowbias = a->rowbias;
+  p.ld_rowbias = a->ld_rowbias;
+  p.act = a->act;
+  p.alpha = a->alpha;
+  p.rowmap_period = a->rowmap_period;
+  p.rowmap_stride = a->rowmap_stride;
+  p.rowmap_off = a->rowmap_off;
+  DEVIT_REQUIRE(!(p.rowbias && p.rowmap_period <= 0),
+                "devit_gemm: rowbias needs rowmap_period > 0");
+  // 16-byte vector path requirements
+  const int out_elem = a->out_kind == DEVIT_OUT_BF16 ? 2 : 4;
+  bool vec = (reinterpret_cast<uintptr_t>(a->out) % 16 == 0) && ((a->ldo * out_elem) % 16 == 0);
+  if (a->out_kind == DEVIT_OUT_F32_SPLIT) vec = vec && ((a->out_plane_stride * 4) % 16 == 0);
+  if (a->bias) vec = vec && (reinterpret_cast<uintptr_t>(a->bias) % 16 == 0);
+  if (a->resid)
+    vec = vec && (reinterpret_cast<uintptr_t>(a->resid) % 16 == 0) && ((a->ldr * 4) % 16 == 0);
+  if (a->rowbias)
+    vec = vec && (reinterpret_cast<uintptr_t>(a->rowbias) % 16 == 0) &&
+          ((a->ld_rowbias * 4) % 16 == 0);
+  p.vec_ok = vec ? 1 : 0;
+
+  int bn = a->block_n ? a->block_n : pick_block_n(a->n);
+  DEVIT_REQUIRE(bn == 128 || bn == 192 || bn == 256, "devit_gemm: block_n %d unsupported", bn);
+
+  CUtensorMap ta0, ta1, tb0, tb1;
+  rc = encode_tmap_2d(&ta0, a->a, elem, a->a_cols, a->a_rows, a->lda, block_k, kBlockM, false);
+  if (rc) return rc;
+  rc = encode_tmap_2d(&tb0, a->b, elem, a->b_cols, a->b_rows, a->ldb, block_k, bn, true);
+  if (rc) return rc;
+  ta1 = ta0;
+  tb1 = tb0;
+  if (kind == 1) {
+    DEVIT_REQUIRE(a->a_plane_stride > 0 && a->b_plane_stride > 0,
+                  "devit_gemm: DEVIT_FP32 operands need plane strides");
+    rc = encode_tmap_2d(&ta1, static_cast<const float*>(a->a) + a->a_plane_stride, elem,
+                        a->a_cols, a->a_rows, a->lda, block_k, kBlockM, false);
+    if (rc) return rc;
+    rc = encode_tmap_2d(&tb1, static_cast<const float*>(a->b) + a->b_plane_stride, elem,
+                        a->b_cols, a->b_rows, a->ldb, block_k, bn, true);
+    if (rc) return rc;
+  }
+
+  if (kind == 0) {
+    if (bn == 128) return launch_gemm<128, 0>(ta0, ta1, tb0, tb1, p, stream);
+    if (bn == 192) return launch_gemm<192, 0>(ta0, ta1, tb0, tb1, p, stream);
+    return launch_gemm<256, 0>(ta0, ta1, tb0, tb1, p, stream);
+  } else {
+    if (bn == 128) return launch_gemm<128, 1>(ta0, ta1, tb0, tb1, p, stream);
+    if (bn == 192) return launch_gemm<192, 1>(ta0, ta1, tb0, tb1, p, stream);
+    return launch_gemm<256, 1>(ta0, ta1, tb0, tb1, p, stream);
+  }
+}

@@ -1,0 +1,221 @@
+// Memory-bound row kernels: LayerNorm (one warp per row, 128-bit loads, shuffle reductions),
+// the final-norm + cls/dist gather, cls/dist token rows, and the patch im2col + cast.
+// All are pure streaming kernels; their roofline is HBM bandwidth (DESIGN.md gives bytes/row).
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace devit {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Normalises one row held as V float4 per lane (dim = V*128) and writes it in `out_kind`.
+template <int V>
+__device__ __forceinline__ void ln_row(const float* __restrict__ xr, const float* __restrict__ g,
+                                       const float* __restrict__ b, float eps, int lane,
+                                       int out_kind, void* y_row, long long plane,
+                                       float* y_f32_row) {
+  constexpr int D = V * 128;
+  float4 v[V];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    v[i] = *(reinterpret_cast<const float4*>(xr) + lane + 32 * i);
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float mean = warp_sum(s) * (1.0f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+    q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / D) + eps);
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int e4 = lane + 32 * i;
+    const float4 gg = __ldg(reinterpret_cast<const float4*>(g) + e4);
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(b) + e4);
+    float4 o;
+    o.x = v[i].x * rstd * gg.x + bb.x;
+    o.y = v[i].y * rstd * gg.y + bb.y;
+    o.z = v[i].z * rstd * gg.z + bb.z;
+    o.w = v[i].w * rstd * gg.w + bb.w;
+    if (y_f32_row) *(reinterpret_cast<float4*>(y_f32_row) + e4) = o;
+    if (y_row) {
+      if (out_kind == DEVIT_OUT_BF16) {
+        uint2 t;
+        t.x = pack_bf16x2(o.x, o.y);
+        t.y = pack_bf16x2(o.z, o.w);
+        *(reinterpret_cast<uint2*>(y_row) + e4) = t;
+      } else if (out_kind == DEVIT_OUT_F32) {
+        *(reinterpret_cast<float4*>(y_row) + e4) = o;
+      } else {
+        float4 h = make_float4(tf32_hi(o.x), tf32_hi(o.y), tf32_hi(o.z), tf32_hi(o.w));
+        *(reinterpret_cast<float4*>(y_row) + e4) = h;
+        *(reinterpret_cast<float4*>(static_cast<float*>(y_row) + plane) + e4) =
+            make_float4(o.x - h.x, o.y - h.y, o.z - h.z, o.w - h.w);
+      }
+    }
+  }
+}
+
+template <int V>
+__global__ void __launch_bounds__(256)
+ln_kernel(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ b,
+          void* __restrict__ y, long long rows, float eps, int out_kind, long long plane) {
+  constexpr int D = V * 128;
+  const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int esz = out_kind == DEVIT_OUT_BF16 ? 2 : 4;
+  ln_row<V>(x + row * D, g, b, eps, threadIdx.x & 31, out_kind,
+            static_cast<uint8_t*>(y) + row * D * esz, plane, nullptr);
+}
+
+template <int V>
+__global__ void __launch_bounds__(256)
+gather_ln_kernel(const float* __restrict__ x, const float* __restrict__ g,
+                 const float* __restrict__ b, float* __restrict__ feats_f32,
+                 void* __restrict__ feats_op, int out_kind, long long plane, int batch, int tokens,
+                 int num_prefix, float eps) {
+  constexpr int D = V * 128;
+  const int idx = blockIdx.x * 8 + (threadIdx.x >> 5);  // = img * num_prefix + j
+  if (idx >= batch * num_prefix) return;
+  const int img = idx / num_prefix, j = idx - img * num_prefix;
+  const long long orow = static_cast<long long>(j) * batch + img;
+  const int esz = out_kind == DEVIT_OUT_BF16 ? 2 : 4;
+  ln_row<V>(x + (static_cast<long long>(img) * tokens + j) * D, g, b, eps, threadIdx.x & 31,
+            out_kind, feats_op ? static_cast<uint8_t*>(feats_op) + orow * D * esz : nullptr, plane,
+            feats_f32 ? feats_f32 + orow * D : nullptr);
+}
+
+__global__ void token_prefix_kernel(float* __restrict__ x, const float* __restrict__ prefix,
+                                    const float* __restrict__ pos, int batch, int tokens, int dim,
+                                    int num_prefix) {
+  const int per_img = num_prefix * dim;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(batch) * per_img) return;
+  const int img = static_cast<int>(i / per_img);
+  const int r = static_cast<int>(i - static_cast<long long>(img) * per_img);
+  x[static_cast<long long>(img) * tokens * dim + r] = prefix[r] + pos[r];
+}
+
+// One thread converts 4 horizontally adjacent pixels (one float4) of one channel row.
+__global__ void __launch_bounds__(256)
+im2col16_kernel(const float* __restrict__ img, void* __restrict__ a, int batch, int chans, int hw,
+                int out_kind, long long plane) {
+  const int w4 = hw >> 2;
+  const long long total = static_cast<long long>(batch) * chans * hw * w4;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int x4 = static_cast<int>(i % w4);
+  long long t = i / w4;
+  const int y = static_cast<int>(t % hw);
+  t /= hw;
+  const int c = static_cast<int>(t % chans);
+  const int b = static_cast<int>(t / chans);
+  const float4 v = __ldg(reinterpret_cast<const float4*>(img) + i);
+  const int g = hw >> 4;
+  const int x = x4 << 2;
+  const long long m = (static_cast<long long>(b) * g + (y >> 4)) * g + (x >> 4);
+  const long long k = static_cast<long long>(c) * 256 + (y & 15) * 16 + (x & 15);
+  const long long o = m * (static_cast<long long>(chans) * 256) + k;
+  if (out_kind == DEVIT_OUT_BF16) {
+    uint2 pk;
+    pk.x = pack_bf16x2(v.x, v.y);
+    pk.y = pack_bf16x2(v.z, v.w);
+    *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(a) + o) = pk;
+  } else if (out_kind == DEVIT_OUT_F32) {
+    *reinterpret_cast<float4*>(static_cast<float*>(a) + o) = v;
+  } else {
+    const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+    *reinterpret_cast<float4*>(static_cast<float*>(a) + o) = h;
+    *reinterpret_cast<float4*>(static_cast<float*>(a) + o + plane) =
+        make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+  }
+}
+
+}  // namespace devit
+
+using namespace devit;
+
+extern "C" int devit_layernorm(const float* x, const float* gamma, const float* beta, void* y,
+                               int64_t rows, int32_t dim, float eps, int32_t out_kind,
+                               int64_t out_plane_stride, void* stream_v) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  int rc = check_device();
+  if (rc) return rc;
+  DEVIT_REQUIRE(x && gamma && beta && y, "devit_layernorm: null pointer");
+  DEVIT_REQUIRE(rows > 0, "devit_layernorm: rows must be > 0");
+  DEVIT_REQUIRE(out_kind >= 0 && out_kind <= 2, "devit_layernorm: bad out_kind %d", out_kind);
+  const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
+  switch (dim) {
+    case 256: ln_kernel<2><<<grid, 256, 0, stream>>>(x, gamma, beta, y, rows, eps, out_kind, out_plane_stride); break;
+    case 384: ln_kernel<3><<<grid, 256, 0, stream>>>(x, gamma, beta, y, rows, eps, out_kind, out_plane_stride); break;
+    case 768: ln_kernel<6><<<grid, 256, 0, stream>>>(x, gamma, beta, y, rows, eps, out_kind, out_plane_stride); break;
+    default: return set_error(DEVIT_ERR_ARG, "devit_layernorm: dim %d not in {256,384,768}", dim);
+  }
+  DEVIT_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return DEVIT_OK;
+}
+
+extern "C" int devit_gather_ln(const float* x, const float* gamma, const float* beta,
+                               float* feats_f32, void* feats_op, int32_t out_kind,
+                               int64_t out_plane_stride, int32_t batch, int32_t tokens,
+                               int32_t dim, int32_t num_prefix, float eps, void* stream_v) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  int rc = check_device();
+  if (rc) return rc;
+  DEVIT_REQUIRE(x && gamma && beta && (feats_f32 || feats_op), "devit_gather_ln: null pointer");
+  DEVIT_REQUIRE(batch > 0 && num_prefix > 0 && num_prefix <= tokens, "devit_gather_ln: bad shape");
+  const unsigned grid = static_cast<unsigned>((batch * num_prefix + 7) / 8);
+  switch (dim) {
+    case 256: gather_ln_kernel<2><<<grid, 256, 0, stream>>>(x, gamma, beta, feats_f32, feats_op, out_kind, out_plane_stride, batch, tokens, num_prefix, eps); break;
+    case 384: gather_ln_kernel<3><<<grid, 256, 0, stream>>>(x, gamma, beta, feats_f32, feats_op, out_kind, out_plane_stride, batch, tokens, num_prefix, eps); break;
+    case 768: gather_ln_kernel<6><<<grid, 256, 0, stream>>>(x, gamma, beta, feats_f32, feats_op, out_kind, out_plane_stride, batch, tokens, num_prefix, eps); break;
+    default: return set_error(DEVIT_ERR_ARG, "devit_gather_ln: dim %d not in {256,384,768}", dim);
+  }
+  DEVIT_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return DEVIT_OK;
+}
+
+extern "C" int devit_token_prefix(float* x, const float* prefix, const float* pos, int32_t batch,
+                                  int32_t tokens, int32_t dim, int32_t num_prefix,
+                                  void* stream_v) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  int rc = check_device();
+  if (rc) return rc;
+  DEVIT_REQUIRE(x && prefix && pos, "devit_token_prefix: null pointer");
+  DEVIT_REQUIRE(batch > 0 && num_prefix > 0 && num_prefix <= tokens && dim > 0,
+                "devit_token_prefix: bad shape");
+  const long long total = static_cast<long long>(batch) * num_prefix * dim;
+  token_prefix_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+      x, prefix, pos, batch, tokens, dim, num_prefix);
+  DEVIT_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return DEVIT_OK;
+}
+
+extern "C" int devit_im2col_patch16(const float* images, void* a, int32_t batch, int32_t chans,
+                                    int32_t hw, int32_t out_kind, int64_t out_plane_stride,
+                                    void* stream_v) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  int rc = check_device();
+  if (rc) return rc;
+  DEVIT_REQUIRE(images && a, "devit_im2col_patch16: null pointer");
+  DEVIT_REQUIRE(batch > 0 && chans > 0 && hw > 0 && hw % 16 == 0,
+                "devit_im2col_patch16: image side %d must be a positive multiple of 16", hw);
+  DEVIT_REQUIRE(reinterpret_cast<uintptr_t>(images) % 16 == 0,
+                "devit_im2col_patch16: images must be 16-byte aligned");
+  const long long total = static_cast<long long>(batch) * chans * hw * (hw / 4);
+  im2col16_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+      images, a, batch, chans, hw, out_kind, out_plane_stride);
+  DEVIT_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return DEVIT_OK;
+}

@@ -1,0 +1,232 @@
+/*
+ * devit_b200 -- C ABI of the B200-native DeViT collaborative-inference hot path.
+ *
+ * The reference (falcon-xu/DeViT) has no FFI layer: its "plugin boundary" for this path is
+ * the set of nn.Module forwards in models/de_vit.py and models/ensemble_models.py.  Each entry
+ * point below replaces the torch ops one of those forwards dispatches (file:line given per
+ * function); the Python host (devit_b200/models.py) binds them with ctypes, see INTEGRATION.md.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless stated; the caller owns all memory;
+ *  - all work is enqueued on `stream` (a cudaStream_t passed as void*), no hidden syncs,
+ *    safe to capture in a CUDA graph;
+ *  - return value 0 = ok, otherwise a DEVIT_ERR_* code; devit_last_error() gives the text;
+ *  - there is no CPU fallback: on a device that is not sm_100 every launch returns
+ *    DEVIT_ERR_DEVICE.
+ *
+ * Precision modes (`precision` fields)
+ *  - DEVIT_BF16 : GEMM/attention operands are bf16 row-major arrays, fp32 accumulation in
+ *                 TMEM, fp32 residual stream / LayerNorm statistics / softmax.
+ *  - DEVIT_FP32 : operands are fp32 "split" arrays: two planes [hi | lo] with hi exactly
+ *                 representable in tf32 and hi+lo == value; GEMMs run as 3xTF32 on tcgen05
+ *                 (hi*hi + lo*hi + hi*lo), attention runs in plain fp32.  Matches the fp32
+ *                 reference to ~1e-6 relative per op.
+ */
+#ifndef DEVIT_B200_H_
+#define DEVIT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DEVIT_ABI_VERSION 1
+
+enum {
+  DEVIT_OK = 0,
+  DEVIT_ERR_ARG = 1,     /* invalid argument (shape / alignment / null pointer) */
+  DEVIT_ERR_DEVICE = 2,  /* current device is not compute capability 10.0 */
+  DEVIT_ERR_CUDA = 3,    /* a CUDA runtime / driver call failed */
+  DEVIT_ERR_WORKSPACE = 4 /* workspace too small */
+};
+
+enum { DEVIT_BF16 = 0, DEVIT_FP32 = 1 };
+
+/* element kinds for outputs of the row-wise kernels and the GEMM epilogue */
+enum {
+  DEVIT_OUT_BF16 = 0,      /* bf16 [rows, ld] */
+  DEVIT_OUT_F32 = 1,       /* fp32 [rows, ld] */
+  DEVIT_OUT_F32_SPLIT = 2  /* fp32 hi plane at out, lo plane at out + plane_stride */
+};
+
+enum { DEVIT_ACT_NONE = 0, DEVIT_ACT_GELU_ERF = 1 };
+
+int devit_abi_version(void);
+const char* devit_last_error(void);
+/* 0 when the CURRENT cuda device is sm_100 (B200); DEVIT_ERR_DEVICE otherwise. */
+int devit_device_check(void);
+/* number of kernels this library has launched in the calling process (all threads) */
+long long devit_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------
+ * devit_gemm: out = epilogue( sum_s A_s[M, K_s] * B_s[N, K_s]^T )  on tcgen05/TMEM via TMA.
+ *
+ * Replaces nn.Linear (addmm) call sites: qkv  models/de_vit.py:67, proj :81, fc1 :36,
+ * fc2 :45, head/head_dist :317, patch-embed conv-as-GEMM (timm PatchEmbed, called :258),
+ * EnsMLP cls_mlp/dist_mlp/cls_classifier/dist_classifier models/ensemble_models.py:79-85.
+ *
+ * A and B are both "K-major" (row-major with K contiguous): A is [a_rows, a_cols] with row
+ * stride lda, B (an nn.Linear weight) is [b_rows, b_cols] with row stride ldb.  Up to 8
+ * K-segments are accumulated: segment s multiplies A rows [a_row_off + m] cols
+ * [a_k_off, a_k_off + k_len) with B cols [b_k_off, b_k_off + k_len)  (this is how the fusion
+ * head consumes the all-gathered [n_sub, B, D] feature slabs without a stack/transpose).
+ * Reads outside [a_rows, a_cols] / [b_rows, b_cols] are zero-filled by TMA, so M, N and the
+ * last K block may be ragged.
+ *
+ * Epilogue, per output element (m, n), all in fp32:
+ *   v = acc + bias[n]; v = act(v); v += rowbias[(rowmap_off + m % period) * ld_rowbias + n];
+ *   v += resid[row_out * ldr + n]; v *= alpha; out[row_out, n] = v
+ *   row_out = period ? (m / period) * rowmap_stride + rowmap_off + m % period : m
+ * (each term is skipped when its pointer is NULL; resid may alias out when out is fp32).
+ * ------------------------------------------------------------------------------------- */
+typedef struct devit_gemm_seg {
+  int32_t a_row_off;
+  int32_t a_k_off;
+  int32_t b_k_off;
+  int32_t k_len;
+} devit_gemm_seg;
+
+typedef struct devit_gemm_args {
+  int32_t precision; /* DEVIT_BF16 | DEVIT_FP32 (operand format) */
+  int32_t m, n;
+  const void* a;
+  int32_t a_rows, a_cols;
+  int64_t lda;
+  int64_t a_plane_stride; /* elements between hi and lo plane (DEVIT_FP32 only) */
+  const void* b;
+  int32_t b_rows, b_cols;
+  int64_t ldb;
+  int64_t b_plane_stride;
+  int32_t num_segs;
+  devit_gemm_seg segs[8];
+  void* out;
+  int64_t ldo;
+  int32_t out_kind; /* DEVIT_OUT_* */
+  int64_t out_plane_stride;
+  const float* bias;
+  const float* resid;
+  int64_t ldr;
+  const float* rowbias;
+  int64_t ld_rowbias;
+  int32_t act;
+  float alpha;
+  int32_t rowmap_period, rowmap_stride, rowmap_off;
+  int32_t block_n; /* 0 = choose automatically from {128, 192, 256} */
+} devit_gemm_args;
+
+int devit_gemm(const devit_gemm_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * devit_layernorm: y[r, :] = (x[r, :] - mean) * rstd * gamma + beta, biased variance,
+ * one warp per row, fp32 statistics.   Replaces nn.LayerNorm (norm1/norm2)
+ * models/de_vit.py:113,115.  x fp32 [rows, dim] (the residual stream), dim in {256,384,768}.
+ * ------------------------------------------------------------------------------------- */
+int devit_layernorm(const float* x, const float* gamma, const float* beta, void* y,
+                    int64_t rows, int32_t dim, float eps, int32_t out_kind,
+                    int64_t out_plane_stride, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * devit_attention: out[b, t, h*64:(h+1)*64] = softmax(q k^T * scale) v   per (b, h).
+ * Replaces models/de_vit.py:70-74 (two bmm + scale + softmax + transpose).
+ *
+ * qkv is the natural output of the QKV Linear: [batch*tokens, 3*heads*64] with column
+ * (which*heads + h)*64 + d  (the reference's reshape(B,N,3,H,hd), models/de_vit.py:67);
+ * out is [batch*tokens, heads*64] -- exactly the A operand of the proj GEMM, so the
+ * reference's transpose(1,2).reshape copies vanish.  `heads` is the number of KEPT heads
+ * (gated heads are compacted away by the host).  head_dim is fixed at 64, tokens <= 256.
+ * DEVIT_BF16: bf16 in/out, QK^T and PV on tcgen05, fp32 softmax.
+ * DEVIT_FP32: split-fp32 in (hi+lo summed on load) and split-fp32 out, fp32 CUDA-core math.
+ * ------------------------------------------------------------------------------------- */
+int devit_attention(int32_t precision, const void* qkv, int64_t qkv_plane_stride, void* out,
+                    int64_t out_plane_stride, int32_t batch, int32_t tokens, int32_t heads,
+                    float scale, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * devit_im2col_patch16: images fp32 NCHW [batch, chans, hw, hw] -> patch matrix
+ * A[batch*(hw/16)^2, chans*256] with K order (c, py, px) and patch index gy*(hw/16)+gx, i.e.
+ * the operand that turns timm PatchEmbed's Conv2d(k=16, s=16) + flatten(2).transpose(1,2)
+ * (called at models/de_vit.py:258) into a GEMM against proj.weight.view(D, chans*256).
+ * ------------------------------------------------------------------------------------- */
+int devit_im2col_patch16(const float* images, void* a, int32_t batch, int32_t chans,
+                         int32_t hw, int32_t out_kind, int64_t out_plane_stride, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * devit_token_prefix: x[b, j, :] = prefix[j, :] + pos[j, :] for j < num_prefix
+ * (cls / dist tokens; models/de_vit.py:259-264).  x fp32 [batch, tokens, dim].
+ * ------------------------------------------------------------------------------------- */
+int devit_token_prefix(float* x, const float* prefix, const float* pos, int32_t batch,
+                       int32_t tokens, int32_t dim, int32_t num_prefix, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * devit_gather_ln: feats[j, b, :] = LayerNorm(x[b, j, :]) for j < num_prefix -- the final
+ * norm restricted to the rows the model actually returns (models/de_vit.py:286-288).
+ * feats_f32 (optional) fp32 [num_prefix, batch, dim]; feats_op (optional) the same values in
+ * the GEMM operand format selected by out_kind (bf16 or split fp32) for the fusion head.
+ * ------------------------------------------------------------------------------------- */
+int devit_gather_ln(const float* x, const float* gamma, const float* beta, float* feats_f32,
+                    void* feats_op, int32_t out_kind, int64_t out_plane_stride, int32_t batch,
+                    int32_t tokens, int32_t dim, int32_t num_prefix, float eps, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * devit_vit_forward: the whole VisionTransformer.forward_features of one (compacted)
+ * sub-model, models/de_vit.py:242-292: patch embed -> tokens -> depth x Block -> final norm on
+ * the cls/dist rows.  One call enqueues every kernel on `stream`.
+ *
+ * Weights are the host-packed, gate-compacted operands (devit_b200/packing.py): per layer the
+ * kept heads' qkv rows / proj columns and the kept neurons' fc1 rows / fc2 columns.
+ * ------------------------------------------------------------------------------------- */
+typedef struct devit_layer_desc {
+  int32_t heads;     /* kept heads h_l (>= 1)                                  */
+  int32_t hidden;    /* kept neurons f_l                                        */
+  int32_t hidden_ld; /* f_l rounded up to a multiple of 16 (row stride of fc2 / hidden)*/
+  const float* ln1_g;
+  const float* ln1_b;
+  const void* w_qkv; /* [3*h_l*64, dim]   */
+  const float* b_qkv;
+  const void* w_proj; /* [dim, h_l*64]     */
+  const float* b_proj;
+  const float* ln2_g;
+  const float* ln2_b;
+  const void* w_fc1; /* [hidden_ld, dim] (rows >= hidden are zero) */
+  const float* b_fc1; /* [hidden_ld]       */
+  const void* w_fc2; /* [dim, hidden_ld] (cols >= hidden are zero) */
+  const float* b_fc2;
+} devit_layer_desc;
+
+typedef struct devit_vit_desc {
+  int32_t precision; /* DEVIT_BF16 | DEVIT_FP32 */
+  int32_t dim;       /* 384 (dedeit) or 768 (teacher); head_dim = 64 */
+  int32_t depth;
+  int32_t img, chans;  /* 224, 3 ; patch size fixed at 16 */
+  int32_t num_prefix;  /* 2 = cls + dist (distilled), 1 = cls only */
+  float ln_eps;
+  const void* w_patch; /* [dim, chans*256] */
+  const float* b_patch;
+  const float* prefix; /* [num_prefix, dim] = cls_token (, dist_token) */
+  const float* pos;    /* [num_prefix + (img/16)^2, dim] */
+  const float* norm_g;
+  const float* norm_b;
+  const devit_layer_desc* layers; /* HOST pointer to depth entries */
+  int64_t w_plane_stride_unused;  /* reserved, must be 0 */
+} devit_vit_desc;
+
+size_t devit_vit_workspace_bytes(const devit_vit_desc* desc, int32_t batch);
+
+/* feats_f32: fp32 [num_prefix, batch, dim]; feats_op: GEMM-operand copy (bf16, or split fp32
+ * with the given plane stride) or NULL.  x_out (optional): fp32 [batch, tokens, dim] copy of
+ * the residual stream after the last block that ran; num_layers_run < 0 runs all `depth`
+ * blocks, otherwise only the first num_layers_run (parity checks of intermediate state). */
+int devit_vit_forward(const devit_vit_desc* desc, const float* images, int32_t batch,
+                      void* workspace, size_t workspace_bytes, float* feats_f32, void* feats_op,
+                      int64_t feats_op_plane_stride, float* x_out, int32_t num_layers_run,
+                      void* stream);
+
+/* In DEVIT_FP32 every weight matrix pointer in the descriptors addresses the hi plane and the
+ * lo plane follows at + rows*cols elements (plane stride = rows * ld). */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEVIT_B200_H_ */

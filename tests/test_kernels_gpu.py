@@ -1,0 +1,131 @@
+"""Per-kernel parity on the GPU: each C-ABI entry point against a plain PyTorch fp32 statement of
+the same op (bf16 mode: inputs rounded to bf16 first, so only accumulation order / output
+rounding differ; fp32 mode: 3xTF32 vs fp32)."""
+import math
+
+import pytest
+import torch
+
+from devit_b200 import _lib as L
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    return ((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-30)).item()
+
+
+def _mk(shape, seed, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).cuda()
+
+
+@pytest.mark.parametrize("m,n,k", [(128, 128, 64), (256, 192, 384), (1000, 384, 1536),
+                                   (396, 1152, 384), (50, 100, 768), (333, 864, 384),
+                                   (777, 384, 864), (4096, 1536, 384)])
+@pytest.mark.parametrize("bn", [0, 128, 192, 256])
+def test_gemm_bf16_plain(m, n, k, bn):
+    a = _mk((m, k), 1).bfloat16()
+    w = _mk((n, k), 2, 0.05).bfloat16()
+    bias = _mk((n,), 3)
+    out = L.gemm(a, w, bias=bias, out_kind=L.OUT_F32, block_n=bn)
+    ref = a.float() @ w.float().t() + bias
+    assert rel(out, ref) < 2e-5, (m, n, k, bn, rel(out, ref))
+    out16 = L.gemm(a, w, bias=bias, out_kind=L.OUT_BF16, block_n=bn)
+    assert rel(out16, ref) < 6e-3
+
+
+@pytest.mark.parametrize("m,n,k", [(256, 192, 384), (1000, 384, 1536), (333, 864, 384),
+                                   (777, 384, 864), (50, 100, 768)])
+def test_gemm_fp32_3xtf32(m, n, k):
+    a = _mk((m, k), 1)
+    w = _mk((n, k), 2, 0.05)
+    bias = _mk((n,), 3)
+    out = L.gemm(L.split_tf32(a), L.split_tf32(w), precision=L.DEVIT_FP32, bias=bias,
+                 out_kind=L.OUT_F32)
+    ref = (a.double() @ w.double().t() + bias.double()).float()
+    assert rel(out, ref) < 1e-5, rel(out, ref)
+    outs = L.gemm(L.split_tf32(a), L.split_tf32(w), precision=L.DEVIT_FP32, bias=bias,
+                  out_kind=L.OUT_F32_SPLIT)
+    assert rel(outs[0] + outs[1], ref) < 1e-5
+    # hi plane must be tf32-exact
+    assert (outs[0].view(torch.int32) & 0x1FFF).abs().max().item() == 0
+
+
+def test_gemm_epilogue_gelu_resid_alpha():
+    m, n, k = 520, 384, 384
+    a = _mk((m, k), 1).bfloat16()
+    w = _mk((n, k), 2, 0.05).bfloat16()
+    bias = _mk((n,), 3)
+    res = _mk((m, n), 4)
+    out = L.gemm(a, w, bias=bias, act=L.ACT_GELU_ERF, out_kind=L.OUT_F32)
+    ref = torch.nn.functional.gelu(a.float() @ w.float().t() + bias)
+    assert rel(out, ref) < 2e-5
+    x = res.clone()
+    L.gemm(a, w, bias=bias, resid=x, out=x, out_kind=L.OUT_F32, alpha=0.5)
+    ref = (a.float() @ w.float().t() + bias + res) * 0.5
+    assert rel(x, ref) < 2e-5
+
+
+def test_gemm_rowmap_rowbias():
+    # the patch-embed epilogue: row m -> (m // P) * T + off + m % P, + pos[off + m % P]
+    bsz, P, T, off, n, k = 5, 196, 198, 2, 384, 768
+    a = _mk((bsz * P, k), 1).bfloat16()
+    w = _mk((n, k), 2, 0.05).bfloat16()
+    bias = _mk((n,), 3)
+    pos = _mk((T, n), 4)
+    x = torch.zeros(bsz * T, n, device="cuda")
+    L.gemm(a, w, bias=bias, rowbias=pos, rowmap=(P, T, off), out=x, out_kind=L.OUT_F32)
+    ref = torch.zeros(bsz, T, n, device="cuda")
+    ref[:, off:] = (a.float() @ w.float().t() + bias).view(bsz, P, n) + pos[off:]
+    assert rel(x.view(bsz, T, n), ref) < 2e-5
+    assert x.view(bsz, T, n)[:, :off].abs().max().item() == 0.0
+
+
+def test_gemm_ksegments_fusion_layout():
+    # A = n_sub stacked slabs [n_sub*B, D]; B weight [N, n_sub*D]: the EnsMLP K-split
+    nsub, bsz, d, n = 4, 37, 384, 768
+    slabs = _mk((nsub * bsz, d), 1).bfloat16()
+    w = _mk((n, nsub * d), 2, 0.05).bfloat16()
+    segs = [(r * bsz, 0, r * d, d) for r in range(nsub)]
+    out = L.gemm(slabs, w, m=bsz, segs=segs, out_kind=L.OUT_F32)
+    x = slabs.float().view(nsub, bsz, d).permute(1, 0, 2).reshape(bsz, nsub * d)
+    ref = x @ w.float().t()
+    assert rel(out, ref) < 2e-5
+
+
+@pytest.mark.parametrize("rows,dim", [(8, 384), (1001, 384), (300, 768), (77, 256)])
+def test_layernorm(rows, dim):
+    x = _mk((rows, dim), 1) * 3 + 0.5
+    g = 1 + 0.1 * _mk((dim,), 2)
+    b = 0.1 * _mk((dim,), 3)
+    ref = torch.nn.functional.layer_norm(x.double(), (dim,), g.double(), b.double(), 1e-6).float()
+    y = L.layernorm(x, g, b, 1e-6, L.OUT_F32)
+    assert rel(y, ref) < 2e-6
+    y16 = L.layernorm(x, g, b, 1e-6, L.OUT_BF16)
+    assert rel(y16, ref) < 5e-3
+    ys = L.layernorm(x, g, b, 1e-6, L.OUT_F32_SPLIT)
+    assert rel(ys[0] + ys[1], ref) < 2e-6
+
+
+def _attn_ref(qkv, batch, tokens, heads, scale):
+    q, k, v = qkv.double().view(batch, tokens, 3, heads, 64).permute(2, 0, 3, 1, 4).unbind(0)
+    p = ((q @ k.transpose(-2, -1)) * scale).softmax(-1)
+    return (p @ v).transpose(1, 2).reshape(batch * tokens, heads * 64).float()
+
+
+@pytest.mark.parametrize("batch,tokens,heads", [(2, 198, 6), (3, 197, 3), (1, 198, 1),
+                                                (2, 64, 4), (2, 256, 4), (5, 100, 2)])
+def test_attention_bf16(batch, tokens, heads):
+    qkv = _mk((batch * tokens, 3 * heads * 64), 7).bfloat16()
+    out = L.attention(qkv, batch, tokens, heads, 0.125)
+    ref = _attn_ref(qkv.float(), batch, tokens, heads, 0.125)
+    assert rel(out, ref) < 1.5e-2, rel(out, ref)
+
+
+@pytest.mark.parametrize("batch,tokens,heads", [(2, 198, 6), (1, 197, 5), (2, 64, 4)])
+def test_attention_fp32(batch, tokens, heads):
+    qkv = _mk((batch * tokens, 3 * heads * 64), 7)
+    out = L.attention(L.split_tf32(qkv), batch, tokens, heads, 0.125, precision=L.DEVIT_FP32)
+    ref = _attn_ref(qkv, batch, tokens, heads, 0.125)
+    assert rel(out[0] + out[1], ref) < 3e-6

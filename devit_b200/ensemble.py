@@ -1,0 +1,206 @@
+"""Ensemble wrappers: MultiViT (N decomposed sub-models) and the EnsMLP feature-fusion head,
+drop-in for models/ensemble_models.py:13-90.
+
+Data layout.  The reference builds ``torch.stack(list, 1).view(B, -1)`` (sub-model-major within
+a sample) and feeds two Linears (models/ensemble_models.py:76-85).  Here every sub-model's
+final-norm kernel writes its cls / dist rows straight into one slab
+
+        feats[s, j, b, :]      s = sub-model, j = 0 (cls) | 1 (dist), b = image
+
+and the first fusion GEMM walks the slab as K-segments: sub-model s contributes
+A = feats[s, j] ([B, D]) against weight columns [s*D, (s+1)*D) -- the same sum as the stacked
+matmul, without the stack/transpose copies.  With one sub-model per GPU the slab is exactly what
+an all-gather of the per-rank [2, B, D] blocks produces (devit_b200/parallel.py).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from . import models  # noqa: F401  (registers the entrypoints)
+from .models import _PREC, default_precision
+from .registry import create_model
+
+
+class FeatureList(list):
+    """A plain list of [B, D] tensors (what the reference's MultiViT returns) that remembers
+    the slab its entries are views of, so EnsMLP can skip the stack."""
+    slab_f32 = None   # [n_sub, n_kind, B, D] fp32
+    slab_op = None    # same in GEMM-operand format (bf16, or [2, n_sub, n_kind, B, D] split)
+    kind = 0          # 0 = cls, 1 = dist
+
+
+class MultiViT(nn.Module):
+    """models/ensemble_models.py:13-40."""
+
+    def __init__(self, model='dedevit', drop=0, drop_path=0.1, num_classes_list=[25, 25, 25, 25],
+                 num_div=4):
+        super().__init__()
+        self.model = model
+        assert len(num_classes_list) == num_div, 'num of classes is not match num of sub-models'
+        self.backbones = nn.ModuleList([])
+        for i, num_class in enumerate(num_classes_list):
+            self.backbones.append(create_model(model_name=self.model, num_classes=int(num_class),
+                                               drop_rate=drop, drop_path_rate=drop_path,
+                                               drop_block_rate=None))
+            del self.backbones[i].head
+            if 'deit' in self.model:
+                del self.backbones[i].head_dist
+        self.precision = default_precision()
+
+    def set_precision(self, precision: str):
+        self.precision = precision
+        for b in self.backbones:
+            b.set_precision(precision)
+        return self
+
+    @torch.no_grad()
+    def forward_slab(self, x, subs=None):
+        """Runs the sub-models in `subs` (default: all) and returns (slab_f32, slab_op) with
+        shape [len(subs), n_kind, B, D] (slab_op: bf16, or [2, ...] split planes in fp32 mode)."""
+        subs = list(range(len(self.backbones))) if subs is None else list(subs)
+        bb0 = self.backbones[subs[0]]
+        prec = _PREC[self.precision]
+        B, D, T = x.shape[0], bb0.embed_dim, bb0.num_tokens
+        f32 = torch.empty(len(subs), T, B, D, device=x.device)
+        if prec == L.DEVIT_BF16:
+            op = torch.empty(len(subs), T, B, D, device=x.device, dtype=torch.bfloat16)
+        else:
+            op = torch.empty(2, len(subs), T, B, D, device=x.device)
+        for i, s in enumerate(subs):
+            bb = self.backbones[s]
+            if bb.precision != self.precision:
+                bb.set_precision(self.precision)
+            bb.features_into(x, feats_f32=f32[i],
+                             feats_op=op[i] if prec == L.DEVIT_BF16 else op[:, i])
+        return f32, op
+
+    def forward(self, x):
+        f32, op = self.forward_slab(x)
+        n = f32.shape[0]
+        if 'vit' in self.model:  # e.g. 'devit' (note: 'vit' is not a substring of 'dedeit')
+            out = FeatureList(f32[s, 0] for s in range(n))
+            out.slab_f32, out.slab_op, out.kind = f32, op, 0
+            return out
+        cls = FeatureList(f32[s, 0] for s in range(n))
+        dist = FeatureList(f32[s, 1] for s in range(n))
+        cls.slab_f32, cls.slab_op, cls.kind = f32, op, 0
+        dist.slab_f32, dist.slab_op, dist.kind = f32, op, 1
+        return cls, dist
+
+
+class EnsMLP(nn.Module):
+    """models/ensemble_models.py:43-90: per token kind, Linear(n*sub_size -> teacher_size) then
+    Linear(teacher_size -> num_class) (no activation between them), logits = (cls + dist) / 2."""
+
+    def __init__(self, model='dedevit', num_class=100, sub_size=192,
+                 num_classes_list=[25, 25, 25, 25], teacher_size=None):
+        super().__init__()
+        self.model = model
+        self.sub_size = sub_size
+        self.teacher_size = teacher_size
+        self.num_classes = num_class
+        self.num_sub = len(num_classes_list)
+        self.sum_feature_dim = self.sub_size * self.num_sub
+        if self.teacher_size is None:
+            self.cls_classifier = nn.Linear(self.sum_feature_dim, self.num_classes)
+            if 'deit' in self.model:
+                self.dist_classifier = nn.Linear(self.sum_feature_dim, self.num_classes)
+        else:
+            self.cls_mlp = nn.Linear(self.sum_feature_dim, self.teacher_size)
+            self.cls_classifier = nn.Linear(self.teacher_size, self.num_classes)
+            if 'deit' in self.model:
+                self.dist_mlp = nn.Linear(self.sum_feature_dim, self.teacher_size)
+                self.dist_classifier = nn.Linear(self.teacher_size, self.num_classes)
+        self.precision = default_precision()
+        self._packs = None
+
+    def set_precision(self, precision: str):
+        self.precision = precision
+        return self
+
+    # ------------------------------------------------------------------ packed weights
+    def _packed(self, device):
+        from . import packing
+        ver = (self.precision, str(device), packing.module_version(self))
+        if self._packs is None or self._packs[0] != ver:
+            prec = _PREC[self.precision]
+            pk = {name: packing.PackedLinear(m, prec, device)
+                  for name, m in self.named_children() if isinstance(m, nn.Linear)}
+            self._packs = (ver, pk)
+        return self._packs[1]
+
+    def _slab_of(self, lst, device):
+        """Operand slab [n, kinds, B, D] for a list of [B, D] tensors (+ which kind to read)."""
+        prec = _PREC[self.precision]
+        if isinstance(lst, FeatureList) and lst.slab_op is not None:
+            return lst.slab_op, lst.kind
+        if not lst[0].is_cuda:
+            raise L.DevitError("EnsMLP runs on CUDA (sm_100) tensors only; no CPU fallback")
+        stacked = torch.stack([t.float() for t in lst], 0).unsqueeze(1).contiguous()  # [n,1,B,D]
+        if prec == L.DEVIT_BF16:
+            return stacked.to(torch.bfloat16), 0
+        return L.split_tf32(stacked), 0
+
+    def _fuse(self, slab, kind, first: str, out_kind, **epi):
+        """GEMM over the slab with one K-segment per sub-model (weight = Linear `first`)."""
+        prec = _PREC[self.precision]
+        pk = self._packed(slab.device)[first]
+        s4 = slab if prec == L.DEVIT_BF16 else slab[0]
+        n, kinds, B, D = s4.shape
+        if n * D != pk.in_features:
+            raise L.DevitError(f"EnsMLP: {n} sub-models x {D} features != Linear in_features "
+                               f"{pk.in_features} (reference passes sub_size from a stale table, "
+                               f"ensemble.py:224; use sub_size={D})")
+        if n > 8:
+            raise L.DevitError("EnsMLP: at most 8 sub-models per fusion GEMM")
+        a = slab.view(n * kinds * B, D) if prec == L.DEVIT_BF16 else slab.view(2, n * kinds * B, D)
+        segs = [((s * kinds + kind) * B, 0, s * D, D) for s in range(n)]
+        return L.gemm(a, pk.w, precision=prec, m=B, segs=segs, bias=pk.b, out_kind=out_kind, **epi)
+
+    def _lin(self, name, a, out_kind, **epi):
+        prec = _PREC[self.precision]
+        pk = self._packed(a.device)[name]
+        return L.gemm(a, pk.w, precision=prec, bias=pk.b, out_kind=out_kind, **epi)
+
+    @torch.no_grad()
+    def forward(self, x, distill=False):
+        prec = _PREC[self.precision]
+        opk = L.OUT_BF16 if prec == L.DEVIT_BF16 else L.OUT_F32_SPLIT
+        want_tokens = distill and self.training and self.teacher_size is not None
+        if 'vit' in self.model:
+            slab, kind = self._slab_of(x, x[0].device)
+            if self.teacher_size is not None:
+                h = self._fuse(slab, kind, 'cls_mlp', L.OUT_F32 if want_tokens else opk)
+                ens_token = h
+                logits = self._lin('cls_classifier', L.to_operand(h, prec) if want_tokens else h,
+                                   L.OUT_F32)
+            else:
+                ens_token = None
+                logits = self._fuse(slab, kind, 'cls_classifier', L.OUT_F32)
+        elif 'deit' in self.model:
+            cls_list, dist_list = x
+            cslab, ckind = self._slab_of(cls_list, cls_list[0].device)
+            dslab, dkind = self._slab_of(dist_list, dist_list[0].device)
+            if self.teacher_size is not None:
+                hk = L.OUT_F32 if want_tokens else opk
+                hc = self._fuse(cslab, ckind, 'cls_mlp', hk)
+                hd = self._fuse(dslab, dkind, 'dist_mlp', hk)
+                ens_token = (hc, hd)
+                ac = L.to_operand(hc, prec) if want_tokens else hc
+                ad = L.to_operand(hd, prec) if want_tokens else hd
+                cls_logits = self._lin('cls_classifier', ac, L.OUT_F32)
+                # (cls_logits + dist_logits) / 2 in the last GEMM's epilogue
+                logits = self._lin('dist_classifier', ad, L.OUT_F32, resid=cls_logits, alpha=0.5)
+            else:
+                ens_token = None
+                cls_logits = self._fuse(cslab, ckind, 'cls_classifier', L.OUT_F32)
+                logits = self._fuse(dslab, dkind, 'dist_classifier', L.OUT_F32, resid=cls_logits,
+                                    alpha=0.5)
+        else:
+            raise L.DevitError(f"EnsMLP: model name {self.model!r} contains neither 'vit' nor "
+                               f"'deit' (models/ensemble_models.py:66,73)")
+        if want_tokens:
+            return ens_token, logits
+        return logits

@@ -1,0 +1,162 @@
+"""Gate-aware weight packing: nn.Parameters (fp32 masters) -> compacted GEMM operands.
+
+The reference computes every head / neuron densely and multiplies the result by a 0/1 gate
+(models/de_vit.py:41-43, :77-79).  Dropping a gated unit is numerically identical, so the pack
+physically removes it:
+  * kept heads  (gate != 0, ascending index) select rows of qkv.weight/bias and columns of
+    proj.weight (scaled by the gate value, so non-binary gates stay exact);
+  * kept neurons select rows of fc1.weight/bias and columns of fc2.weight (scaled likewise);
+    the kept count is zero-padded to a multiple of 16 (padded neurons give gelu(0) = 0).
+The kept-index lists are integer work and are exposed (``kept_heads`` / ``kept_neurons``) so the
+tests can compare them bit-exactly with the oracle's.
+
+Operand formats follow include/devit_b200.h: bf16 arrays, or fp32 hi/lo split planes for the
+3xTF32 parity mode.  Everything here is one-off host/plumbing work done with torch ops when a
+gate or a parameter changes; it is not on the per-batch path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+
+def kept_indices(gate: torch.Tensor) -> torch.Tensor:
+    """Ascending indices of the units whose gate is non-zero (int64, CPU)."""
+    return torch.nonzero(gate.detach().float().cpu() != 0, as_tuple=False).flatten()
+
+
+class PackedVit:
+    """Device-resident packed weights + the ctypes descriptor passed to devit_vit_forward."""
+
+    def __init__(self, model, precision: int, device: torch.device):
+        self.precision = precision
+        self.device = device
+        self._keep = []  # tensors referenced by raw pointers in the descriptors
+        self.kept_heads = []
+        self.kept_neurons = []
+        dim = model.embed_dim
+        depth = len(model.blocks)
+        self.layers = (L.LayerDesc * depth)()
+
+        def op(t):  # GEMM operand in the mode's format
+            t = L.to_operand(t.detach().to(device=device, dtype=torch.float32), precision)
+            self._keep.append(t)
+            return t.data_ptr()
+
+        def f32(t):
+            t = t.detach().to(device=device, dtype=torch.float32).contiguous()
+            self._keep.append(t)
+            return t.data_ptr()
+
+        for i, blk in enumerate(model.blocks):
+            attn, mlp = blk.attn, blk.mlp
+            nh = attn.num_heads
+            hg = attn.gate.detach().float().cpu()
+            hk = kept_indices(hg)
+            hscale = hg[hk]
+            if hk.numel() == 0:  # every head gated off: keep one, with zeroed proj columns
+                hk, hscale = torch.tensor([0]), torch.tensor([0.0])
+            self.kept_heads.append(hk.clone())
+            hd = dim // nh
+            if hd != 64:
+                raise L.DevitError(f"head_dim {hd} unsupported (the attention kernel is built "
+                                   f"for head_dim 64)")
+            cols = (hk[:, None] * hd + torch.arange(hd)[None, :]).flatten()  # kept q/k/v columns
+            rows = torch.cat([cols + w * dim for w in range(3)])
+            wq = attn.qkv.weight.detach().float().cpu()
+            bq = attn.qkv.bias.detach().float().cpu() if attn.qkv.bias is not None \
+                else torch.zeros(3 * dim)
+            wp = attn.proj.weight.detach().float().cpu()[:, cols] * \
+                hscale.repeat_interleave(hd)[None, :]
+
+            ng = mlp.gate.detach().float().cpu()
+            nk = kept_indices(ng)
+            nscale = ng[nk]
+            self.kept_neurons.append(nk.clone())
+            f = int(nk.numel())
+            f_ld = max(16, (f + 15) // 16 * 16)
+            w1 = torch.zeros(f_ld, dim)
+            b1 = torch.zeros(f_ld)
+            w2 = torch.zeros(dim, f_ld)
+            if f:
+                w1[:f] = mlp.fc1.weight.detach().float().cpu()[nk]
+                b1[:f] = mlp.fc1.bias.detach().float().cpu()[nk]
+                w2[:, :f] = mlp.fc2.weight.detach().float().cpu()[:, nk] * nscale[None, :]
+
+            d = self.layers[i]
+            d.heads, d.hidden, d.hidden_ld = int(hk.numel()), max(f, 1), f_ld
+            d.ln1_g, d.ln1_b = f32(blk.norm1.weight), f32(blk.norm1.bias)
+            d.w_qkv, d.b_qkv = op(wq[rows]), f32(bq[rows])
+            d.w_proj, d.b_proj = op(wp), f32(attn.proj.bias)
+            d.ln2_g, d.ln2_b = f32(blk.norm2.weight), f32(blk.norm2.bias)
+            d.w_fc1, d.b_fc1 = op(w1), f32(b1)
+            d.w_fc2, d.b_fc2 = op(w2), f32(mlp.fc2.bias)
+
+        pe = model.patch_embed
+        desc = L.VitDesc()
+        desc.precision, desc.dim, desc.depth = precision, dim, depth
+        desc.img, desc.chans = int(pe.img_size[0]), int(pe.proj.weight.shape[1])
+        desc.num_prefix = model.num_tokens
+        desc.ln_eps = float(model.norm.eps)
+        desc.w_patch = op(pe.proj.weight.detach().float().reshape(dim, -1))
+        desc.b_patch = f32(pe.proj.bias)
+        prefix = [model.cls_token.detach().reshape(1, dim)]
+        if model.dist_token is not None:
+            prefix.append(model.dist_token.detach().reshape(1, dim))
+        desc.prefix = f32(torch.cat(prefix, 0))
+        desc.pos = f32(model.pos_embed.detach().reshape(-1, dim))
+        desc.norm_g, desc.norm_b = f32(model.norm.weight), f32(model.norm.bias)
+        desc.layers = C.cast(self.layers, C.POINTER(L.LayerDesc))
+        desc.w_plane_stride_unused = 0
+        self.desc = desc
+        self.tokens = (desc.img // 16) ** 2 + desc.num_prefix
+        self.dim = dim
+
+    def workspace_bytes(self, batch: int) -> int:
+        n = L.load().devit_vit_workspace_bytes(C.byref(self.desc), batch)
+        if n == 0:
+            L.check(1)
+        return n
+
+
+class PackedLinear:
+    """One nn.Linear as a GEMM B operand (+ fp32 bias)."""
+
+    def __init__(self, linear, precision: int, device: torch.device):
+        self.w = L.to_operand(linear.weight.detach().to(device=device, dtype=torch.float32),
+                              precision)
+        self.b = None if linear.bias is None else \
+            linear.bias.detach().to(device=device, dtype=torch.float32).contiguous()
+        self.out_features, self.in_features = linear.weight.shape
+
+
+_WORKSPACES = {}
+
+
+def workspace(device: torch.device, nbytes: int) -> torch.Tensor:
+    """Per-(device, stream) scratch buffer, grown on demand and reused across calls."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    buf = _WORKSPACES.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(nbytes, device=device, dtype=torch.uint8)
+        _WORKSPACES[key] = buf
+    return buf
+
+
+def module_version(module) -> tuple:
+    """Cheap fingerprint of everything a pack depends on: parameter storage + in-place version
+    counters + the gate epochs.  A changed fingerprint invalidates the pack."""
+    v = []
+    for p in module.parameters():
+        v.append(p.data_ptr())
+        v.append(p._version)
+    for m in module.modules():
+        e = getattr(m, '_gate_epoch', None)
+        if e is not None:
+            v.append(e)
+            g = m._gate
+            v.append(g._version)
+    return tuple(v)

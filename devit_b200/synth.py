@@ -1,0 +1,128 @@
+"""Deterministic synthetic weights, inputs and gates.
+
+There are no datasets or checkpoints in the build environment, so every test / bench / golden
+fixture regenerates the same tensors from seeds with the CPU generator (bit-stable for a given
+torch version).  State dicts use the reference's key names AND order (models/de_vit.py state_dict:
+155 entries for `dedeit`), because ensemble.py:228-238 loads sub-checkpoints by position.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import shrink
+
+
+def vit_keys(depth=12, distilled=True, with_heads=True):
+    keys = ['cls_token'] + (['dist_token'] if distilled else []) + \
+        ['pos_embed', 'patch_embed.proj.weight', 'patch_embed.proj.bias']
+    for i in range(depth):
+        for sub in ('norm1', 'attn.qkv', 'attn.proj', 'norm2', 'mlp.fc1', 'mlp.fc2'):
+            keys += [f'blocks.{i}.{sub}.weight', f'blocks.{i}.{sub}.bias']
+    keys += ['norm.weight', 'norm.bias']
+    if with_heads:
+        keys += ['head.weight', 'head.bias']
+        if distilled:
+            keys += ['head_dist.weight', 'head_dist.bias']
+    return keys
+
+
+def vit_shapes(dim=384, depth=12, mlp_ratio=4, num_classes=100, img=224, patch=16, chans=3,
+               distilled=True, with_heads=True):
+    tokens = (img // patch) ** 2 + (2 if distilled else 1)
+    hidden = int(dim * mlp_ratio)
+    shp = OrderedDict()
+    for k in vit_keys(depth, distilled, with_heads):
+        if k in ('cls_token', 'dist_token'):
+            shp[k] = (1, 1, dim)
+        elif k == 'pos_embed':
+            shp[k] = (1, tokens, dim)
+        elif k == 'patch_embed.proj.weight':
+            shp[k] = (dim, chans, patch, patch)
+        elif k.endswith('attn.qkv.weight'):
+            shp[k] = (3 * dim, dim)
+        elif k.endswith('attn.qkv.bias'):
+            shp[k] = (3 * dim,)
+        elif k.endswith('mlp.fc1.weight'):
+            shp[k] = (hidden, dim)
+        elif k.endswith('mlp.fc1.bias'):
+            shp[k] = (hidden,)
+        elif k.endswith('mlp.fc2.weight'):
+            shp[k] = (dim, hidden)
+        elif k.startswith('head') and k.endswith('weight'):
+            shp[k] = (num_classes, dim)
+        elif k.startswith('head') and k.endswith('bias'):
+            shp[k] = (num_classes,)
+        elif k.endswith('attn.proj.weight'):
+            shp[k] = (dim, dim)
+        else:  # every remaining bias / LayerNorm vector
+            shp[k] = (dim,)
+    return shp
+
+
+def _fill(key, shape, gen, qkv_gain=1.0):
+    t = torch.randn(*shape, generator=gen)
+    is_norm = '.norm' in key or key.startswith('norm.')
+    if is_norm and key.endswith('weight'):
+        return 1.0 + 0.1 * t
+    if is_norm:
+        return 0.1 * t
+    if key.endswith('attn.qkv.weight'):
+        return 0.02 * qkv_gain * t
+    return 0.02 * t
+
+
+def vit_state_dict(seed, qkv_gain=1.0, **shape_kw):
+    """Every parameter non-trivial (biases, LayerNorm affine, cls/dist/pos all random) so that
+    every code path is live.  qkv_gain > 1 sharpens the softmax (stress variant for tests)."""
+    gen = torch.Generator().manual_seed(seed)
+    return OrderedDict((k, _fill(k, s, gen, qkv_gain)) for k, s in vit_shapes(**shape_kw).items())
+
+
+def dedeit_state_dict(sub_idx, num_classes=25, qkv_gain=1.0, with_heads=True):
+    return vit_state_dict(1000 + sub_idx, qkv_gain, dim=384, depth=12, num_classes=num_classes,
+                          with_heads=with_heads)
+
+
+def teacher_state_dict(num_classes=100):
+    return vit_state_dict(3000, dim=768, depth=12, num_classes=num_classes)
+
+
+def ensmlp_state_dict(n_sub=4, sub_size=384, teacher_size=768, num_class=100, seed=2000,
+                      classifier_gain=8.0, distilled=True):
+    """Key order of models/ensemble_models.py:44-63.  Classifier weights are scaled so that the
+    logits are separated enough for the argmax comparison to be meaningful."""
+    gen = torch.Generator().manual_seed(seed)
+    k_in = n_sub * sub_size
+    sd = OrderedDict()
+    kinds = ['cls'] + (['dist'] if distilled else [])
+    for kind in kinds:
+        if teacher_size is not None:
+            sd[f'{kind}_mlp.weight'] = 0.02 * torch.randn(teacher_size, k_in, generator=gen)
+            sd[f'{kind}_mlp.bias'] = 0.02 * torch.randn(teacher_size, generator=gen)
+            c_in = teacher_size
+        else:
+            c_in = k_in
+        sd[f'{kind}_classifier.weight'] = 0.02 * classifier_gain * torch.randn(num_class, c_in,
+                                                                              generator=gen)
+        sd[f'{kind}_classifier.bias'] = 0.02 * torch.randn(num_class, generator=gen)
+    return sd
+
+
+def images(batch, seed=1234, img=224, chans=3):
+    gen = torch.Generator().manual_seed(seed)
+    return torch.randn(batch, chans, img, img, generator=gen)
+
+
+def shrink_gates(sub_idx, hidden=1536, heads=6, layer=12, shrink_ratio=0.3):
+    """Sampled shrink_ratio-0.3 policy + random importance ranks -> (neuron_masks, head_masks),
+    each a list of `layer` fp32 0/1 tensors, via the reference's index-selection rule."""
+    rng = np.random.RandomState(4321 + sub_idx)
+    n_ratio, h_ratio = shrink.sample_policy(rng, shrink_ratio=shrink_ratio, layer=layer)
+    n_rank = [rng.permutation(hidden) for _ in range(layer)]
+    h_rank = [rng.permutation(heads) for _ in range(layer)]
+    n_masks = [shrink.keep_mask(hidden, n_ratio[i], n_rank[i]) for i in range(layer)]
+    h_masks = [shrink.keep_mask(heads, h_ratio[i], h_rank[i]) for i in range(layer)]
+    return n_masks, h_masks

@@ -1,0 +1,129 @@
+"""Host-side logic that needs no GPU: C-ABI export surface, registry / constructor / state_dict
+compatibility, the gate protocol, gate-aware packing (integer index selection), and the
+loud-failure rule (no CPU fallback)."""
+import ctypes
+import os
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from devit_b200 import _lib as L
+from devit_b200 import ensemble, models, packing, shrink, synth
+from devit_b200.registry import create_model, is_model
+from oracle import devit_oracle as O
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def test_abi_exports_every_declared_symbol():
+    header = (ROOT / 'include' / 'devit_b200.h').read_text()
+    declared = set(re.findall(r'\b(devit_[a-z0-9_]+)\s*\(', header))
+    assert declared, "no prototypes found in include/devit_b200.h"
+    lib = ctypes.CDLL(str(L.LIB_PATH))
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert declared == set(L.exported_symbols()), "ctypes table and header disagree"
+    assert L.load().devit_abi_version() == 1
+
+
+def test_no_cpu_fallback():
+    m = create_model('dedeit', num_classes=10).eval()
+    with pytest.raises(L.DevitError):
+        m(torch.zeros(1, 3, 224, 224))
+    if not torch.cuda.is_available():
+        assert L.load().devit_device_check() != 0
+    fuse = ensemble.EnsMLP(model='dedeit', num_class=10, sub_size=384, num_classes_list=[5, 5],
+                           teacher_size=768)
+    with pytest.raises(L.DevitError):
+        fuse(([torch.zeros(2, 384)] * 2, [torch.zeros(2, 384)] * 2))
+
+
+def test_registry_and_none_kwarg_filtering():
+    assert is_model('dedeit') and is_model('devit') and is_model('deit_base_distilled_patch16_224')
+    m = create_model('dedeit', num_classes=25, drop_rate=0, drop_path_rate=0.1,
+                     drop_block_rate=None)  # models/ensemble_models.py:23-27
+    assert m.embed_dim == 384 and m.num_tokens == 2 and len(m.blocks) == 12
+    t = create_model('deit_base_distilled_patch16_224', num_classes=100)
+    assert t.embed_dim == 768 and t.blocks[0].attn.num_heads == 12 and t.tuple_api
+
+
+def test_state_dict_names_and_order_match_reference_layout():
+    m = create_model('dedeit', num_classes=25)
+    keys = list(m.state_dict())
+    assert len(keys) == 155
+    assert keys == synth.vit_keys(12, True, True)
+    for k, shape in synth.vit_shapes(num_classes=25).items():
+        assert tuple(m.state_dict()[k].shape) == shape, k
+    m.load_state_dict(synth.dedeit_state_dict(0, num_classes=25))  # strict
+    v = create_model('devit', num_classes=10)
+    assert list(v.state_dict()) == synth.vit_keys(12, False, True)
+    mv = ensemble.MultiViT(model='dedeit', num_classes_list=[25] * 4, num_div=4)
+    assert len(mv.state_dict()) == 4 * 151  # heads deleted (ensemble.py:233-237 skips 4 keys)
+    e = ensemble.EnsMLP(model='dedeit', num_class=100, sub_size=384, num_classes_list=[25] * 4,
+                        teacher_size=768)
+    assert list(e.state_dict()) == list(synth.ensmlp_state_dict(4))
+
+
+def test_gate_protocol_with_mirror_functions():
+    m = create_model('dedeit', num_classes=25)
+    mlps = [x for x in m.modules() if shrink._is_mlp(x)]
+    attns = [x for x in m.modules() if shrink._is_attn(x)]
+    assert len(mlps) == 12 and len(attns) == 12  # Block / model contain both names -> skipped
+    assert all(x.hidden_features == 1536 and x.gate.shape == (1536,) for x in mlps)
+    assert all(x.num_heads == 6 and x.gate.shape == (6,) for x in attns)
+    ng, hg = synth.shrink_gates(0)
+    v0 = packing.module_version(m)
+    shrink.mlp_neuron_shrink(m, ng)
+    shrink.attn_head_shrink(m, hg)
+    assert packing.module_version(m) != v0  # packs are invalidated by a gate assignment
+    assert shrink.check_head_sparsity(m) == [(6 - g.sum().item()) / 6 for g in hg]
+    shrink.mlp_neuron_restore(m)
+    shrink.attn_head_restore(m)
+    assert all(x.gate.sum().item() == 1536 for x in mlps)
+    v1 = packing.module_version(m)
+    mlps[0].gate[3] = 0  # in-place edits are noticed too
+    assert packing.module_version(m) != v1
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/core'), reason="reference not mounted")
+def test_gate_protocol_with_the_reference_functions_unchanged():
+    """The reference's own core/imp_rank.py functions must find and set gates on our modules."""
+    from oracle import ref_shim
+    ref_shim.install()
+    from core import imp_rank
+    m = create_model('dedeit', num_classes=25)
+    rng = np.random.RandomState(0)
+    ratio = [0.3] * 12
+    n_rank = [rng.permutation(1536) for _ in range(12)]
+    h_rank = [rng.permutation(6) for _ in range(12)]
+    nm = imp_rank.mlp_neuron_mask(m, ratio, n_rank)
+    hm = imp_rank.attn_head_mask(m, ratio, h_rank)
+    assert len(nm) == 12 and len(hm) == 12
+    imp_rank.mlp_neuron_shrink(m, nm)
+    imp_rank.attn_head_shrink(m, hm)
+    assert imp_rank.check_head_sparsity(m) == [2 / 6] * 12
+    ours = shrink.mlp_neuron_mask(m, ratio, n_rank)
+    assert all(torch.equal(a, b) for a, b in zip(nm, ours))
+    imp_rank.mlp_neuron_restore(m)
+    imp_rank.attn_head_restore(m)
+    assert imp_rank.check_neuron_sparsity(m) == [0.0] * 12
+
+
+def test_packing_kept_indices_match_oracle():
+    ng, hg = synth.shrink_gates(1)
+    for i in range(12):
+        assert np.array_equal(packing.kept_indices(ng[i]).numpy(), O.kept_indices(ng[i].numpy()))
+        assert np.array_equal(packing.kept_indices(hg[i]).numpy(), O.kept_indices(hg[i].numpy()))
+    g = torch.tensor([0., 2., 0., 0.5, 0., 1.])
+    assert packing.kept_indices(g).tolist() == [1, 3, 5]
+
+
+def test_split_tf32_is_exact():
+    t = torch.randn(1000) * torch.logspace(-6, 6, 1000)
+    s = L.split_tf32(t)
+    assert torch.equal(s[0] + s[1], t)
+    assert (s[0].view(torch.int32) & 0x1FFF).abs().max().item() == 0
+    assert ((s[1].abs() <= t.abs() * 2 ** -11 * 1.0001) | (t == 0)).all()

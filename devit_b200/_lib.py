@@ -44,7 +44,7 @@ class GemmArgs(C.Structure):
         ("rowbias", C.c_void_p), ("ld_rowbias", C.c_int64),
         ("act", C.c_int32), ("alpha", C.c_float),
         ("rowmap_period", C.c_int32), ("rowmap_stride", C.c_int32), ("rowmap_off", C.c_int32),
-        ("block_n", C.c_int32),
+        ("block_n", C.c_int32), ("profile_tag", C.c_int32),
     ]
 
 
@@ -79,6 +79,8 @@ _SIGS = {
     "devit_last_error": (C.c_char_p, []),
     "devit_device_check": (C.c_int, []),
     "devit_launch_count": (C.c_longlong, []),
+    "devit_profile_enable": (C.c_int, [C.c_int]),
+    "devit_profile_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "devit_gemm": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
     "devit_layernorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                   C.c_int32, C.c_float, C.c_int32, C.c_int64, C.c_void_p]),
@@ -170,7 +172,7 @@ def operand_to_f32(t: torch.Tensor, precision: int) -> torch.Tensor:
 
 def gemm(a, b, *, precision=DEVIT_BF16, m=None, n=None, segs=None, out=None,
          out_kind=OUT_BF16, bias=None, resid=None, rowbias=None, act=ACT_NONE, alpha=1.0,
-         rowmap=(0, 0, 0), block_n=0, out_rows=None):
+         rowmap=(0, 0, 0), block_n=0, out_rows=None, tag=0):
     """out = epilogue(sum_s A_s B_s^T); see include/devit_b200.h (devit_gemm)."""
     lib = load()
     planes = 1 if precision == DEVIT_BF16 else 2
@@ -210,8 +212,26 @@ def gemm(a, b, *, precision=DEVIT_BF16, m=None, n=None, segs=None, out=None,
     g.act, g.alpha = act, alpha
     g.rowmap_period, g.rowmap_stride, g.rowmap_off = rowmap
     g.block_n = block_n
+    g.profile_tag = tag
     check(lib.devit_gemm(C.byref(g), stream_ptr()))
     return out
+
+
+TAGS = ["gemm_other", "gemm_patch", "gemm_qkv", "gemm_proj", "gemm_fc1", "gemm_fc2",
+        "gemm_fusion", "gemm_head", "attention", "layernorm", "gather_ln", "im2col",
+        "token_prefix"]
+
+
+def profile_enable(on: bool) -> None:
+    check(load().devit_profile_enable(1 if on else 0))
+
+
+def profile_collect() -> dict:
+    """{tag: (milliseconds, launches)} accumulated since profile_enable(True)."""
+    ms = (C.c_double * 16)()
+    cnt = (C.c_longlong * 16)()
+    check(load().devit_profile_collect(ms, cnt))
+    return {TAGS[i]: (ms[i], cnt[i]) for i in range(len(TAGS)) if cnt[i]}
 
 
 def layernorm(x, gamma, beta, eps, out_kind=OUT_BF16):

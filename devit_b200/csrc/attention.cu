@@ -354,9 +354,11 @@ static int launch_attn_bf16(const void* qkv, void* out, int batch, int tokens, i
   rc = encode_tmap_3d(&tkv, qkv, 2, ld, tokens, batch, ld, ld * tokens, 64, KVP, 1);
   if (rc) return rc;
   dim3 grid((tokens + 127) / 128, heads, batch);
-  attn_bf16_kernel<KVP><<<grid, kAttnThreads, Cfg::kSmemBytes, stream>>>(
-      tq, tkv, static_cast<__nv_bfloat16*>(out), tokens, heads,
-      scale * 1.4426950408889634f);
+  {
+    ProfScope ps(kTagAttention, stream);
+    attn_bf16_kernel<KVP><<<grid, kAttnThreads, Cfg::kSmemBytes, stream>>>(
+        tq, tkv, static_cast<__nv_bfloat16*>(out), tokens, heads, scale * 1.4426950408889634f);
+  }
   DEVIT_CUDA_OK(cudaGetLastError());
   count_launch();
   return DEVIT_OK;
@@ -394,9 +396,12 @@ extern "C" int devit_attention(int32_t precision, const void* qkv, int64_t qkv_p
     attr_done[dev & 63] = true;
   }
   dim3 grid(heads, batch);
-  attn_f32_kernel<<<grid, kF32Threads, smem, stream>>>(
-      static_cast<const float*>(qkv), qkv_plane_stride, static_cast<float*>(out),
-      out_plane_stride, tokens, heads, scale);
+  {
+    ProfScope ps(kTagAttention, stream);
+    attn_f32_kernel<<<grid, kF32Threads, smem, stream>>>(
+        static_cast<const float*>(qkv), qkv_plane_stride, static_cast<float*>(out),
+        out_plane_stride, tokens, heads, scale);
+  }
   DEVIT_CUDA_OK(cudaGetLastError());
   count_launch();
   return DEVIT_OK;

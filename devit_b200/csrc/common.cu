@@ -4,6 +4,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <mutex>
+#include <vector>
 
 namespace devit {
 
@@ -19,6 +20,32 @@ int set_error(int code, const char* fmt, ...) {
 }
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+struct ProfRec {
+  cudaEvent_t a, b;
+  int tag;
+};
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static std::mutex g_prof_mu;
+
+ProfScope::ProfScope(int tag, cudaStream_t s) : stream(s), on(g_prof_on) {
+  if (!on) return;
+  ProfRec r;
+  r.tag = tag;
+  if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) {
+    on = false;
+    return;
+  }
+  cudaEventRecord(r.a, stream);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof.push_back(r);
+}
+ProfScope::~ProfScope() {
+  if (!on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  cudaEventRecord(g_prof.back().b, stream);
+}
 
 struct DevInfo {
   int major = -1, minor = -1, sms = 0;
@@ -140,5 +167,38 @@ int devit_abi_version(void) { return DEVIT_ABI_VERSION; }
 const char* devit_last_error(void) { return devit::g_err; }
 int devit_device_check(void) { return devit::check_device(); }
 long long devit_launch_count(void) { return devit::g_launches.load(); }
+
+int devit_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(devit::g_prof_mu);
+  for (auto& r : devit::g_prof) {
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  devit::g_prof.clear();
+  devit::g_prof_on = on != 0;
+  return DEVIT_OK;
+}
+
+int devit_profile_collect(double* ms_by_tag, long long* count_by_tag) {
+  if (!ms_by_tag || !count_by_tag) return devit::set_error(DEVIT_ERR_ARG, "null output");
+  std::lock_guard<std::mutex> lk(devit::g_prof_mu);
+  for (int i = 0; i < devit::kNumProfTags; ++i) {
+    ms_by_tag[i] = 0.0;
+    count_by_tag[i] = 0;
+  }
+  for (auto& r : devit::g_prof) {
+    float ms = 0.f;
+    cudaError_t e = cudaEventSynchronize(r.b);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, r.a, r.b);
+    if (e != cudaSuccess)
+      return devit::set_error(DEVIT_ERR_CUDA, "profile event: %s", cudaGetErrorString(e));
+    ms_by_tag[r.tag] += ms;
+    count_by_tag[r.tag] += 1;
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  devit::g_prof.clear();
+  return DEVIT_OK;
+}
 
 }  // extern "C"

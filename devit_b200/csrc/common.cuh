@@ -14,6 +14,20 @@ int check_device();  // DEVIT_OK iff current device is sm_100
 int num_sms();
 void count_launch(int n = 1);
 
+// Optional per-launch device timing (devit_profile_enable): when on, each launcher brackets
+// its kernel with two CUDA events on the launch stream, tagged by kernel family.
+enum ProfTag {
+  kTagGemmOther = 0, kTagGemmPatch = 1, kTagGemmQkv = 2, kTagGemmProj = 3, kTagGemmFc1 = 4,
+  kTagGemmFc2 = 5, kTagGemmFusion = 6, kTagGemmHead = 7, kTagAttention = 8, kTagLayerNorm = 9,
+  kTagGatherLn = 10, kTagIm2col = 11, kTagPrefix = 12, kNumProfTags = 16
+};
+struct ProfScope {
+  cudaStream_t stream;
+  bool on;
+  ProfScope(int tag, cudaStream_t s);
+  ~ProfScope();
+};
+
 #define DEVIT_CUDA_OK(expr)                                                              \
   do {                                                                                   \
     cudaError_t _e = (expr);                                                             \

@@ -75,7 +75,7 @@ static void base_gemm(devit_gemm_args* g, int precision) {
 using namespace devit;
 
 extern "C" size_t devit_vit_workspace_bytes(const devit_vit_desc* desc, int32_t batch) {
-  VitLayout L;
+  VitLayout L{};
   if (plan_layout(desc, batch, &L)) return 0;
   return L.total;
 }
@@ -86,7 +86,7 @@ extern "C" int devit_vit_forward(const devit_vit_desc* d, const float* images, i
                                  int32_t num_layers_run, void* stream) {
   int rc = check_device();
   if (rc) return rc;
-  VitLayout L;
+  VitLayout L{};
   rc = plan_layout(d, batch, &L);
   if (rc) return rc;
   DEVIT_REQUIRE(images && workspace, "devit_vit_forward: null pointer");
@@ -125,6 +125,7 @@ extern "C" int devit_vit_forward(const devit_vit_desc* d, const float* images, i
   g.bias = d->b_patch;
   g.rowbias = d->pos; g.ld_rowbias = D;
   g.rowmap_period = P; g.rowmap_stride = L.tokens; g.rowmap_off = d->num_prefix;
+  g.profile_tag = DEVIT_TAG_GEMM_PATCH;
   rc = devit_gemm(&g, stream);
   if (rc) return rc;
   rc = devit_token_prefix(x, d->prefix, d->pos, batch, L.tokens, D, d->num_prefix, stream);
@@ -146,6 +147,7 @@ extern "C" int devit_vit_forward(const devit_vit_desc* d, const float* images, i
     g.segs[0] = devit_gemm_seg{0, 0, 0, D};
     g.out = qkv; g.ldo = 3 * hd; g.out_kind = opk; g.out_plane_stride = M * 3 * hd;
     g.bias = w.b_qkv;
+    g.profile_tag = DEVIT_TAG_GEMM_QKV;
     rc = devit_gemm(&g, stream);
     if (rc) return rc;
     // o = softmax(q k^T / 8) v  per kept head                    (:70-74)
@@ -161,6 +163,7 @@ extern "C" int devit_vit_forward(const devit_vit_desc* d, const float* images, i
     g.segs[0] = devit_gemm_seg{0, 0, 0, hd};
     g.out = x; g.ldo = D; g.out_kind = DEVIT_OUT_F32;
     g.bias = w.b_proj; g.resid = x; g.ldr = D;
+    g.profile_tag = DEVIT_TAG_GEMM_PROJ;
     rc = devit_gemm(&g, stream);
     if (rc) return rc;
     // x -> LN2 -> y                                              (:115)
@@ -176,6 +179,7 @@ extern "C" int devit_vit_forward(const devit_vit_desc* d, const float* images, i
     g.segs[0] = devit_gemm_seg{0, 0, 0, D};
     g.out = hid; g.ldo = F; g.out_kind = opk; g.out_plane_stride = M * F;
     g.bias = w.b_fc1; g.act = DEVIT_ACT_GELU_ERF;
+    g.profile_tag = DEVIT_TAG_GEMM_FC1;
     rc = devit_gemm(&g, stream);
     if (rc) return rc;
     // x += hid W2^T + b2                                         (:45, :115)
@@ -187,6 +191,7 @@ extern "C" int devit_vit_forward(const devit_vit_desc* d, const float* images, i
     g.segs[0] = devit_gemm_seg{0, 0, 0, F};
     g.out = x; g.ldo = D; g.out_kind = DEVIT_OUT_F32;
     g.bias = w.b_fc2; g.resid = x; g.ldr = D;
+    g.profile_tag = DEVIT_TAG_GEMM_FC2;
     rc = devit_gemm(&g, stream);
     if (rc) return rc;
   }

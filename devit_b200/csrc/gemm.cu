@@ -339,7 +339,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
 
 template <int BN, int KIND>
 static int launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b0,
-                       const CUtensorMap& b1, const GemmKParams& p, cudaStream_t stream) {
+                       const CUtensorMap& b1, const GemmKParams& p, cudaStream_t stream,
+                       int tag) {
   using Cfg = GemmCfg<BN>;
   static bool attr_done[64] = {};  // per device; benign race: the attribute set is idempotent
   int dev = 0;
@@ -352,7 +353,10 @@ static int launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUten
   }
   const int num_tiles = ((p.M + kBlockM - 1) / kBlockM) * ((p.N + BN - 1) / BN);
   int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-  gemm_kernel<BN, KIND><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(a0, a1, b0, b1, p);
+  {
+    ProfScope ps(tag, stream);
+    gemm_kernel<BN, KIND><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(a0, a1, b0, b1, p);
+  }
   DEVIT_CUDA_OK(cudaGetLastError());
   count_launch();
   return DEVIT_OK;
@@ -447,6 +451,7 @@ extern "C" int devit_gemm(const devit_gemm_args* a, void* stream_v) {
           ((a->ld_rowbias * 4) % 16 == 0);
   p.vec_ok = vec ? 1 : 0;
 
+  const int tag = (a->profile_tag >= 0 && a->profile_tag < 8) ? a->profile_tag : 0;
   int bn = a->block_n ? a->block_n : pick_block_n(a->n);
   DEVIT_REQUIRE(bn == 128 || bn == 192 || bn == 256, "devit_gemm: block_n %d unsupported", bn);
 
@@ -469,12 +474,12 @@ extern "C" int devit_gemm(const devit_gemm_args* a, void* stream_v) {
   }
 
   if (kind == 0) {
-    if (bn == 128) return launch_gemm<128, 0>(ta0, ta1, tb0, tb1, p, stream);
-    if (bn == 192) return launch_gemm<192, 0>(ta0, ta1, tb0, tb1, p, stream);
-    return launch_gemm<256, 0>(ta0, ta1, tb0, tb1, p, stream);
+    if (bn == 128) return launch_gemm<128, 0>(ta0, ta1, tb0, tb1, p, stream, tag);
+    if (bn == 192) return launch_gemm<192, 0>(ta0, ta1, tb0, tb1, p, stream, tag);
+    return launch_gemm<256, 0>(ta0, ta1, tb0, tb1, p, stream, tag);
   } else {
-    if (bn == 128) return launch_gemm<128, 1>(ta0, ta1, tb0, tb1, p, stream);
-    if (bn == 192) return launch_gemm<192, 1>(ta0, ta1, tb0, tb1, p, stream);
-    return launch_gemm<256, 1>(ta0, ta1, tb0, tb1, p, stream);
+    if (bn == 128) return launch_gemm<128, 1>(ta0, ta1, tb0, tb1, p, stream, tag);
+    if (bn == 192) return launch_gemm<192, 1>(ta0, ta1, tb0, tb1, p, stream, tag);
+    return launch_gemm<256, 1>(ta0, ta1, tb0, tb1, p, stream, tag);
   }
 }

@@ -152,6 +152,7 @@ extern "C" int devit_layernorm(const float* x, const float* gamma, const float* 
   DEVIT_REQUIRE(rows > 0, "devit_layernorm: rows must be > 0");
   DEVIT_REQUIRE(out_kind >= 0 && out_kind <= 2, "devit_layernorm: bad out_kind %d", out_kind);
   const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
+  ProfScope ps(kTagLayerNorm, stream);
   switch (dim) {
     case 256: ln_kernel<2><<<grid, 256, 0, stream>>>(x, gamma, beta, y, rows, eps, out_kind, out_plane_stride); break;
     case 384: ln_kernel<3><<<grid, 256, 0, stream>>>(x, gamma, beta, y, rows, eps, out_kind, out_plane_stride); break;
@@ -173,6 +174,7 @@ extern "C" int devit_gather_ln(const float* x, const float* gamma, const float* 
   DEVIT_REQUIRE(x && gamma && beta && (feats_f32 || feats_op), "devit_gather_ln: null pointer");
   DEVIT_REQUIRE(batch > 0 && num_prefix > 0 && num_prefix <= tokens, "devit_gather_ln: bad shape");
   const unsigned grid = static_cast<unsigned>((batch * num_prefix + 7) / 8);
+  ProfScope ps(kTagGatherLn, stream);
   switch (dim) {
     case 256: gather_ln_kernel<2><<<grid, 256, 0, stream>>>(x, gamma, beta, feats_f32, feats_op, out_kind, out_plane_stride, batch, tokens, num_prefix, eps); break;
     case 384: gather_ln_kernel<3><<<grid, 256, 0, stream>>>(x, gamma, beta, feats_f32, feats_op, out_kind, out_plane_stride, batch, tokens, num_prefix, eps); break;
@@ -194,8 +196,11 @@ extern "C" int devit_token_prefix(float* x, const float* prefix, const float* po
   DEVIT_REQUIRE(batch > 0 && num_prefix > 0 && num_prefix <= tokens && dim > 0,
                 "devit_token_prefix: bad shape");
   const long long total = static_cast<long long>(batch) * num_prefix * dim;
-  token_prefix_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
-      x, prefix, pos, batch, tokens, dim, num_prefix);
+  {
+    ProfScope ps(kTagPrefix, stream);
+    token_prefix_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+        x, prefix, pos, batch, tokens, dim, num_prefix);
+  }
   DEVIT_CUDA_OK(cudaGetLastError());
   count_launch();
   return DEVIT_OK;
@@ -213,8 +218,11 @@ extern "C" int devit_im2col_patch16(const float* images, void* a, int32_t batch,
   DEVIT_REQUIRE(reinterpret_cast<uintptr_t>(images) % 16 == 0,
                 "devit_im2col_patch16: images must be 16-byte aligned");
   const long long total = static_cast<long long>(batch) * chans * hw * (hw / 4);
-  im2col16_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
-      images, a, batch, chans, hw, out_kind, out_plane_stride);
+  {
+    ProfScope ps(kTagIm2col, stream);
+    im2col16_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+        images, a, batch, chans, hw, out_kind, out_plane_stride);
+  }
   DEVIT_CUDA_OK(cudaGetLastError());
   count_launch();
   return DEVIT_OK;

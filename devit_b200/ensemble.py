@@ -143,12 +143,16 @@ class EnsMLP(nn.Module):
             return stacked.to(torch.bfloat16), 0
         return L.split_tf32(stacked), 0
 
-    def _fuse(self, slab, kind, first: str, out_kind, **epi):
-        """GEMM over the slab with one K-segment per sub-model (weight = Linear `first`)."""
+    def _fuse(self, slab, kind, first: str, out_kind, order=None, **epi):
+        """GEMM over the slab with one K-segment per sub-model (weight = Linear `first`).
+        order[j] = sub-model id held by slab entry j (identity when None)."""
         prec = _PREC[self.precision]
         pk = self._packed(slab.device)[first]
         s4 = slab if prec == L.DEVIT_BF16 else slab[0]
         n, kinds, B, D = s4.shape
+        order = list(range(n)) if order is None else list(order)
+        if sorted(order) != list(range(n)):
+            raise L.DevitError(f"EnsMLP: slab order {order} is not a permutation of 0..{n - 1}")
         if n * D != pk.in_features:
             raise L.DevitError(f"EnsMLP: {n} sub-models x {D} features != Linear in_features "
                                f"{pk.in_features} (reference passes sub_size from a stale table, "
@@ -156,13 +160,30 @@ class EnsMLP(nn.Module):
         if n > 8:
             raise L.DevitError("EnsMLP: at most 8 sub-models per fusion GEMM")
         a = slab.view(n * kinds * B, D) if prec == L.DEVIT_BF16 else slab.view(2, n * kinds * B, D)
-        segs = [((s * kinds + kind) * B, 0, s * D, D) for s in range(n)]
-        return L.gemm(a, pk.w, precision=prec, m=B, segs=segs, bias=pk.b, out_kind=out_kind, **epi)
+        segs = [((j * kinds + kind) * B, 0, order[j] * D, D) for j in range(n)]
+        return L.gemm(a, pk.w, precision=prec, m=B, segs=segs, bias=pk.b, out_kind=out_kind,
+                      tag=6, **epi)
 
     def _lin(self, name, a, out_kind, **epi):
         prec = _PREC[self.precision]
         pk = self._packed(a.device)[name]
-        return L.gemm(a, pk.w, precision=prec, bias=pk.b, out_kind=out_kind, **epi)
+        return L.gemm(a, pk.w, precision=prec, bias=pk.b, out_kind=out_kind, tag=6, **epi)
+
+    @torch.no_grad()
+    def forward_gathered(self, slab, order=None):
+        """Fusion head straight from a gathered operand slab [n, 2, B, D] (bf16; or
+        [2, n, 2, B, D] split planes in fp32 mode) whose entry j holds sub-model order[j] --
+        the layout an all-gather of the per-rank [2, B, D] blocks produces.  'deit' models."""
+        prec = _PREC[self.precision]
+        opk = L.OUT_BF16 if prec == L.DEVIT_BF16 else L.OUT_F32_SPLIT
+        if self.teacher_size is not None:
+            hc = self._fuse(slab, 0, 'cls_mlp', opk, order)
+            hd = self._fuse(slab, 1, 'dist_mlp', opk, order)
+            cls_logits = self._lin('cls_classifier', hc, L.OUT_F32)
+            return self._lin('dist_classifier', hd, L.OUT_F32, resid=cls_logits, alpha=0.5)
+        cls_logits = self._fuse(slab, 0, 'cls_classifier', L.OUT_F32, order)
+        return self._fuse(slab, 1, 'dist_classifier', L.OUT_F32, order, resid=cls_logits,
+                          alpha=0.5)
 
     @torch.no_grad()
     def forward(self, x, distill=False):

@@ -1,0 +1,111 @@
+"""Multi-GPU execution of the ensemble: one process per GPU (torchrun), sub-models sharded
+across ranks, ONE exchange step -- an all-gather of each rank's LayerNormed cls/dist block into
+the slab the fusion head reads (new in this build, the reference runs all
+sub-models sequentially on one device, models/ensemble_models.py:33).
+
+Partitioning (n_sub sub-models, W ranks): model-parallel groups of G = min(W, n_sub) ranks;
+rank r of a group owns sub-models {s : s % G == r}; with W > n_sub the W / G groups are
+data-parallel replicas that each take an equal slice of the batch (no cross-group traffic).
+After the gather every rank of a group holds the group's logits.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import torch
+import torch.distributed as dist
+
+
+@dataclass
+class ShardPlan:
+    world: int
+    rank: int
+    n_sub: int
+    batch: int
+    group_size: int = 1
+    num_groups: int = 1
+    group_id: int = 0
+    model_rank: int = 0
+    subs: list = field(default_factory=list)
+    batch_lo: int = 0
+    batch_hi: int = 0
+    group_ranks: list = field(default_factory=list)
+
+    @property
+    def n_local(self) -> int:
+        return len(self.subs)
+
+    @property
+    def group_batch(self) -> int:
+        return self.batch_hi - self.batch_lo
+
+    def gathered_order(self) -> list:
+        """Sub-model id of entry j of the gathered slab [G * n_local, ...] (rank-major)."""
+        return [i * self.group_size + r for r in range(self.group_size)
+                for i in range(self.n_local)]
+
+
+def shard_plan(world: int, rank: int, n_sub: int, batch: int) -> ShardPlan:
+    if not 0 <= rank < world:
+        raise ValueError(f"rank {rank} outside world {world}")
+    g = min(world, n_sub)
+    if world % g or n_sub % g:
+        raise ValueError(f"world {world} and n_sub {n_sub} must nest (G={g})")
+    groups = world // g
+    if batch % groups:
+        raise ValueError(f"batch {batch} is not divisible by the {groups} data-parallel groups")
+    gid, mr = rank // g, rank % g
+    per = batch // groups
+    return ShardPlan(world=world, rank=rank, n_sub=n_sub, batch=batch, group_size=g,
+                     num_groups=groups, group_id=gid, model_rank=mr,
+                     subs=[s for s in range(n_sub) if s % g == mr],
+                     batch_lo=gid * per, batch_hi=(gid + 1) * per,
+                     group_ranks=list(range(gid * g, (gid + 1) * g)))
+
+
+def make_groups(plan: ShardPlan):
+    """Creates every model-parallel process group (collective over all ranks) and returns the
+    one this rank belongs to (None when a group is a single rank)."""
+    mine = None
+    if plan.group_size == 1:
+        return None
+    for gid in range(plan.num_groups):
+        ranks = list(range(gid * plan.group_size, (gid + 1) * plan.group_size))
+        pg = dist.new_group(ranks=ranks)
+        if gid == plan.group_id:
+            mine = pg
+    return mine
+
+
+def gather_blocks(local: torch.Tensor, plan: ShardPlan, group) -> torch.Tensor:
+    """all-gather of equally shaped per-rank blocks -> [G, *local.shape] (rank-major)."""
+    if plan.group_size == 1:
+        return local.unsqueeze(0)
+    local = local.contiguous()
+    out = torch.empty((plan.group_size * local.shape[0],) + tuple(local.shape[1:]),
+                      dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, local, group=group)
+    return out.view((plan.group_size,) + tuple(local.shape))
+
+
+class ShardedEnsemble:
+    """MultiViT + EnsMLP across the ranks of a ShardPlan.  `multi` holds (at least) this rank's
+    sub-models; `fuse` is replicated on every rank."""
+
+    def __init__(self, multi, fuse, plan: ShardPlan, group=None):
+        self.multi, self.fuse, self.plan, self.group = multi, fuse, plan, group
+        self.order = plan.gathered_order()
+
+    @torch.no_grad()
+    def __call__(self, x_group: torch.Tensor) -> torch.Tensor:
+        """x_group: this rank's copy of its group's batch slice [Bg, 3, H, W] on the local GPU.
+        Returns the group's logits [Bg, num_class]."""
+        from . import _lib as L
+        from .models import _PREC
+        _, op = self.multi.forward_slab(x_group, subs=self.plan.subs)
+        g = gather_blocks(op, self.plan, self.group)
+        if _PREC[self.multi.precision] == L.DEVIT_BF16:
+            slab = g.view((-1,) + tuple(op.shape[1:]))           # [G*n_local, 2, Bg, D]
+        else:                                                     # [G, 2, n_local, 2, Bg, D]
+            slab = g.transpose(0, 1).reshape((2, -1) + tuple(op.shape[2:])).contiguous()
+        return self.fuse.forward_gathered(slab, self.order)

@@ -60,6 +60,20 @@ int devit_device_check(void);
 /* number of kernels this library has launched in the calling process (all threads) */
 long long devit_launch_count(void);
 
+/* Per-launch device timing for benchmarks.  devit_profile_enable(1) makes every launcher
+ * bracket its kernel with two CUDA events on the launch stream (do not use while capturing a
+ * CUDA graph); devit_profile_collect synchronises them and returns, per kernel family tag
+ * (DEVIT_TAG_*, 16 slots), the summed milliseconds and the launch count, then clears the log. */
+enum {
+  DEVIT_TAG_GEMM_OTHER = 0, DEVIT_TAG_GEMM_PATCH = 1, DEVIT_TAG_GEMM_QKV = 2,
+  DEVIT_TAG_GEMM_PROJ = 3, DEVIT_TAG_GEMM_FC1 = 4, DEVIT_TAG_GEMM_FC2 = 5,
+  DEVIT_TAG_GEMM_FUSION = 6, DEVIT_TAG_GEMM_HEAD = 7, DEVIT_TAG_ATTENTION = 8,
+  DEVIT_TAG_LAYERNORM = 9, DEVIT_TAG_GATHER_LN = 10, DEVIT_TAG_IM2COL = 11,
+  DEVIT_TAG_PREFIX = 12, DEVIT_NUM_TAGS = 16
+};
+int devit_profile_enable(int on);
+int devit_profile_collect(double* ms_by_tag, long long* count_by_tag);
+
 /* ---------------------------------------------------------------------------------------
  * devit_gemm: out = epilogue( sum_s A_s[M, K_s] * B_s[N, K_s]^T )  on tcgen05/TMEM via TMA.
  *
@@ -114,6 +128,7 @@ typedef struct devit_gemm_args {
   float alpha;
   int32_t rowmap_period, rowmap_stride, rowmap_off;
   int32_t block_n; /* 0 = choose automatically from {128, 192, 256} */
+  int32_t profile_tag; /* DEVIT_TAG_GEMM_* bucket used by devit_profile_collect */
 } devit_gemm_args;
 
 int devit_gemm(const devit_gemm_args* args, void* stream);

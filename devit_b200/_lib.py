@@ -44,7 +44,7 @@ class GemmArgs(C.Structure):
         ("rowbias", C.c_void_p), ("ld_rowbias", C.c_int64),
         ("act", C.c_int32), ("alpha", C.c_float),
         ("rowmap_period", C.c_int32), ("rowmap_stride", C.c_int32), ("rowmap_off", C.c_int32),
-        ("block_n", C.c_int32), ("profile_tag", C.c_int32),
+        ("block_n", C.c_int32), ("profile_tag", C.c_int32), ("cluster_m", C.c_int32),
     ]
 
 
@@ -172,7 +172,7 @@ def operand_to_f32(t: torch.Tensor, precision: int) -> torch.Tensor:
 
 def gemm(a, b, *, precision=DEVIT_BF16, m=None, n=None, segs=None, out=None,
          out_kind=OUT_BF16, bias=None, resid=None, rowbias=None, act=ACT_NONE, alpha=1.0,
-         rowmap=(0, 0, 0), block_n=0, out_rows=None, tag=0):
+         rowmap=(0, 0, 0), block_n=0, out_rows=None, tag=0, cluster_m=0):
     """out = epilogue(sum_s A_s B_s^T); see include/devit_b200.h (devit_gemm)."""
     lib = load()
     planes = 1 if precision == DEVIT_BF16 else 2
@@ -213,6 +213,7 @@ def gemm(a, b, *, precision=DEVIT_BF16, m=None, n=None, segs=None, out=None,
     g.rowmap_period, g.rowmap_stride, g.rowmap_off = rowmap
     g.block_n = block_n
     g.profile_tag = tag
+    g.cluster_m = cluster_m
     check(lib.devit_gemm(C.byref(g), stream_ptr()))
     return out
 

@@ -11,6 +11,8 @@
 // Tile = 128 x BN (BN in {128,192,256}); each k-block is one 128-byte swizzle atom along K
 // (64 bf16 or 32 tf32) = 4 UMMA instructions.  The last N tile issues a narrower UMMA
 // (N rounded up to 16) so ragged shrunk widths do not pay for a full tile.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -42,19 +44,48 @@ struct GemmKParams {
   float alpha;
   int rowmap_period, rowmap_stride, rowmap_off;
   int vec_ok;
+  int tma_epi;  // 1: stage the tile through shared memory, TMA-store it (and TMA-load resid)
 };
 
-template <int BN>
+template <int BN, int CL>
 struct GemmCfg {
   static constexpr int kStageA = kBlockM * 128;
-  static constexpr int kStageB = BN * 128;
+  static constexpr int kStageB = (BN / CL) * 128;  // a CTA pair splits B's rows half / half
   static constexpr int kStageBytes = kStageA + kStageB;
-  static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
+  // epilogue staging: 4 warps x 2 buffers x (32 rows x 128 B), 128B-swizzled like the TMA box
+  static constexpr int kEpiBytes = 4 * 2 * 4096;
+  static constexpr int kStages =
+      (192 * 1024) / kStageBytes > 8 ? 8 : (192 * 1024) / kStageBytes;
   static constexpr int kAccStride = BN <= 128 ? 128 : 256;
   static constexpr int kTmemCols = 2 * kAccStride;
-  static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;
+  static constexpr int kBarBytes = (2 * kStages + 4 + 8) * 8 + 16;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + kBarBytes + 1024;
 };
+
+// byte offset of 16-byte chunk j of row r inside a [32 x 128 B] 128B-swizzled staging buffer
+__device__ __forceinline__ int stg_off(int r, int j) { return r * 128 + ((j ^ (r & 7)) << 4); }
+
+// bias (+ GELU) on 32 consecutive accumulator columns starting at col0 (columns >= N untouched)
+__device__ __forceinline__ void bias_act32(const GemmKParams& p, float* v, int col0) {
+  if (p.bias) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (col0 + 4 * j + 3 < p.N) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);
+        v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+      }
+    }
+  }
+  if (p.act == DEVIT_ACT_GELU_ERF) {
+    if (p.out_kind == DEVIT_OUT_BF16) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(v[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+    }
+  }
+}
 
 // Applies the epilogue to `cnt` consecutive columns held in v[] and stores them.
 // FULL = all 32 columns valid and every pointer suitably aligned -> 16-byte vector path.
@@ -152,12 +183,21 @@ __device__ __forceinline__ void epilogue_store(const GemmKParams& p, float* v, i
   }
 }
 
-template <int BN, int KIND>  // KIND: 0 = bf16 operands, 1 = fp32 operands consumed as tf32
+// KIND: 0 = bf16 operands, 1 = fp32 operands consumed as tf32.
+// CL = 1: one CTA per 128 x BN tile (cta_group::1).
+// CL = 2: a CTA pair (cluster of 2, cta_group::2) computes a 256 x BN tile with ONE MMA stream
+//   issued by the leader: each CTA stages its own 128 A rows and HALF of the B rows, so the
+//   bytes every SM pulls through the L2 fabric per FLOP drop by ~1.5x -- these GEMMs are bound
+//   by that fabric (~6.3 KB/clk chip-wide), not by the tensor pipe.  All TMA loads of the pair
+//   complete on the leader's `full` barrier; tcgen05.commit multicasts `empty` / `tmem_full`
+//   to both CTAs; the peer's epilogue threads arrive remotely on the leader's `tmem_empty`.
+template <int BN, int KIND, int CL>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
             const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
-            const __grid_constant__ GemmKParams p) {
-  using Cfg = GemmCfg<BN>;
+            const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1,
+            const __grid_constant__ CUtensorMap tmR, const __grid_constant__ GemmKParams p) {
+  using Cfg = GemmCfg<BN, CL>;
   constexpr int kElem = KIND == 0 ? 2 : 4;
   constexpr int kBlockK = 128 / kElem;  // elements per k-block (one swizzle atom)
   constexpr int kStages = Cfg::kStages;
@@ -165,14 +205,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint8_t* epi_smem = smem + kStages * Cfg::kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + Cfg::kEpiBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full = empty_bar + kStages;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* res_bar = tmem_empty + 2;  // [4 warps][2 buffers]: residual chunk landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 8);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int cta_rank = CL > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int cluster_id = blockIdx.x / CL;
+  const int num_clusters = gridDim.x / CL;
+  const bool leader = cta_rank == 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);
@@ -187,31 +233,44 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 128);
+      mbar_init(&tmem_empty[s], 128 * CL);  // every epilogue thread of the pair
+    }
+    for (int s = 0; s < 8; ++s) mbar_init(&res_bar[s], 1);
+    if (p.tma_epi) {
+      tma_prefetch_desc(&tmO0);
+      if (p.resid) tma_prefetch_desc(&tmR);
     }
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, Cfg::kTmemCols);
-    tmem_relinquish();
+    if (CL == 1) {
+      tmem_alloc(tmem_slot, Cfg::kTmemCols);
+      tmem_relinquish();
+    } else {
+      tmem_alloc_cg2(tmem_slot, Cfg::kTmemCols);
+      tmem_relinquish_cg2();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // the peer's barriers exist before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   const int num_m = (p.M + kBlockM - 1) / kBlockM;
   const int num_n = (p.N + BN - 1) / BN;
-  const int num_tiles = num_m * num_n;
+  const int num_units = ((num_m + CL - 1) / CL) * num_n;  // unit = CL m-blocks x one n-tile
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / num_n) * kBlockM;
-        const int n0 = (tile % num_n) * BN;
+      for (int unit = cluster_id; unit < num_units; unit += num_clusters) {
+        const int m0 = ((unit / num_n) * CL + cta_rank) * kBlockM;
+        const int n0 = (unit % num_n) * BN;
+        int n_cur = p.N - n0;
+        n_cur = n_cur >= BN ? BN : ((n_cur + 16 * CL - 1) & ~(16 * CL - 1));
         for (int s = 0; s < p.num_segs; ++s) {
           const KSeg sg = p.segs[s];
           const CUtensorMap* ma = (KIND == 1 && sg.a_plane) ? &tmA1 : &tmA0;
@@ -220,9 +279,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * Cfg::kStageBytes;
             uint8_t* sb = sa + Cfg::kStageA;
-            mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-            tma_load_2d(sa, ma, &full_bar[stage], sg.a_k_off + kb * kBlockK, sg.a_row_off + m0);
-            tma_load_2d(sb, mb, &full_bar[stage], sg.b_k_off + kb * kBlockK, n0);
+            if (CL == 1) {
+              mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+              tma_load_2d(sa, ma, &full_bar[stage], sg.a_k_off + kb * kBlockK,
+                          sg.a_row_off + m0);
+              tma_load_2d(sb, mb, &full_bar[stage], sg.b_k_off + kb * kBlockK, n0);
+            } else {
+              // both CTAs' bytes complete on the LEADER's barrier (it issues the MMAs)
+              const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
+              if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+              tma_load_2d_cg2(sa, ma, full_leader, sg.a_k_off + kb * kBlockK, sg.a_row_off + m0);
+              tma_load_2d_cg2(sb, mb, full_leader, sg.b_k_off + kb * kBlockK,
+                              n0 + cta_rank * (n_cur / 2));
+            }
             if (++stage == kStages) {
               stage = 0;
               phase ^= 1;
@@ -233,17 +302,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (lane == 0 && leader) {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int n0 = (tile % num_n) * BN;
+      for (int unit = cluster_id; unit < num_units; unit += num_clusters) {
+        const int n0 = (unit % num_n) * BN;
         int n_cur = p.N - n0;
-        n_cur = n_cur >= BN ? BN : ((n_cur + 15) & ~15);
-        const uint32_t idesc = make_idesc(KIND == 0 ? kFmtBF16 : kFmtTF32, kBlockM, n_cur, 0, 0);
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        n_cur = n_cur >= BN ? BN : ((n_cur + 16 * CL - 1) & ~(16 * CL - 1));
+        const uint32_t idesc =
+            make_idesc(KIND == 0 ? kFmtBF16 : kFmtTF32, kBlockM * CL, n_cur, 0, 0);
+        if (CL == 1) mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        else mbar_wait_cluster(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * Cfg::kAccStride;
         uint32_t accumulate = 0;
@@ -259,20 +330,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               // advance 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
-              if (KIND == 0)
-                umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, accumulate);
-              else
-                umma_tf32(d_tmem, da + 2 * k, db + 2 * k, idesc, accumulate);
+              if (CL == 1) {
+                if (KIND == 0) umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, accumulate);
+                else umma_tf32(d_tmem, da + 2 * k, db + 2 * k, idesc, accumulate);
+              } else {
+                if (KIND == 0) umma_bf16_cg2(d_tmem, da + 2 * k, db + 2 * k, idesc, accumulate);
+                else umma_tf32_cg2(d_tmem, da + 2 * k, db + 2 * k, idesc, accumulate);
+              }
               accumulate = 1;
             }
-            umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+            // smem slot reusable (in both CTAs of a pair) once these MMAs retire
+            if (CL == 1) umma_commit(&empty_bar[stage]);
+            else umma_commit_cg2(&empty_bar[stage], 3);
             if (++stage == kStages) {
               stage = 0;
               phase ^= 1;
             }
           }
         }
-        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue warps (of both CTAs of a pair)
+        if (CL == 1) umma_commit(&tmem_full[acc]);
+        else umma_commit_cg2(&tmem_full[acc], 3);
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -284,82 +362,239 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, +32)
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / num_n) * kBlockM;
-      const int n0 = (tile % num_n) * BN;
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
-      const int m = m0 + quarter * 32 + lane;
-      const bool row_ok = m < p.M;
-      long long row_out = m;
-      int rb_row = 0;
-      if (p.rowmap_period > 0) {
-        const int q = m / p.rowmap_period;
-        const int r = m - q * p.rowmap_period;
-        rb_row = p.rowmap_off + r;
-        row_out = (long long)q * p.rowmap_stride + rb_row;
-      }
+    uint8_t* stg = epi_smem + quarter * 8192;  // two 4 KB staging buffers of this warp
+    uint64_t* rbar = res_bar + quarter * 2;
+    uint32_t rphase0 = 0, rphase1 = 0;
+    int buf = 0;
+    for (int unit = cluster_id; unit < num_units; unit += num_clusters) {
+      const int m0 = ((unit / num_n) * CL + cta_rank) * kBlockM;
+      const int n0 = (unit % num_n) * BN;
+      const int row0 = m0 + quarter * 32;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                              acc * Cfg::kAccStride;
+      const int n_valid = (p.N - n0) < BN ? (p.N - n0) : BN;
+      if (p.tma_epi) {
+        // ---- coalesced path: registers -> swizzled smem -> TMA store (rows/cols past the
+        //      edge are clipped by the tensor map); fp32 residual arrives by TMA as well
+        const bool live = row0 < p.M;  // warp-uniform
+        if (p.out_kind == DEVIT_OUT_BF16) {
+          mbar_wait(&tmem_full[acc], acc_phase);
+          tc_fence_after();
+          if (live) {
+            const int nchunk = (n_valid + 63) >> 6;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int col0 = n0 + c * 32;
-        if (col0 >= p.N) break;
-        uint32_t r[32];
-        __syncwarp();
-        tmem_ld_x32(t_row + c * 32, r);
-        tmem_ld_wait();
-        if (row_ok) {
-          float v[32];
+            for (int c = 0; c < nchunk; ++c) {
+              uint32_t r0[32], r1[32];
+              __syncwarp();
+              tmem_ld_x32(t_row + c * 64, r0);
+              tmem_ld_x32(t_row + c * 64 + 32, r1);
+              tmem_ld_wait();
+              float* v0 = reinterpret_cast<float*>(r0);
+              float* v1 = reinterpret_cast<float*>(r1);
+              bias_act32(p, v0, n0 + c * 64);
+              bias_act32(p, v1, n0 + c * 64 + 32);
+              if (p.alpha != 1.0f) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          const int cnt = p.N - col0;
-          if (cnt >= 32 && p.vec_ok)
-            epilogue_store<true>(p, v, 32, row_out, rb_row, col0);
-          else
-            epilogue_store<false>(p, v, cnt < 32 ? cnt : 32, row_out, rb_row, col0);
+                for (int j = 0; j < 32; ++j) { v0[j] *= p.alpha; v1[j] *= p.alpha; }
+              }
+              if (lane == 0) bulk_wait_read<1>();  // the store that last used `buf` has drained
+              __syncwarp();
+              uint8_t* b = stg + buf * 4096;
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                uint4 t;
+                t.x = pack_bf16x2(v0[8 * g], v0[8 * g + 1]);
+                t.y = pack_bf16x2(v0[8 * g + 2], v0[8 * g + 3]);
+                t.z = pack_bf16x2(v0[8 * g + 4], v0[8 * g + 5]);
+                t.w = pack_bf16x2(v0[8 * g + 6], v0[8 * g + 7]);
+                *reinterpret_cast<uint4*>(b + stg_off(lane, g)) = t;
+                t.x = pack_bf16x2(v1[8 * g], v1[8 * g + 1]);
+                t.y = pack_bf16x2(v1[8 * g + 2], v1[8 * g + 3]);
+                t.z = pack_bf16x2(v1[8 * g + 4], v1[8 * g + 5]);
+                t.w = pack_bf16x2(v1[8 * g + 6], v1[8 * g + 7]);
+                *reinterpret_cast<uint4*>(b + stg_off(lane, 4 + g)) = t;
+              }
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_2d(&tmO0, b, n0 + c * 64, row0);
+                bulk_commit();
+              }
+              buf ^= 1;
+            }
+          }
+        } else {
+          // fp32 (optionally split hi/lo, optionally + residual): 32 columns = 128 B per chunk
+          const bool split = p.out_kind == DEVIT_OUT_F32_SPLIT;
+          const bool has_res = p.resid != nullptr;
+          const int nchunk = (n_valid + 31) >> 5;
+          if (live && has_res && lane == 0) {  // residual chunk 0 can fly before the MMAs end
+            bulk_wait_read<0>();
+            mbar_expect_tx(&rbar[buf], 4096);
+            tma_load_2d(stg + buf * 4096, &tmR, &rbar[buf], n0, row0);
+          }
+          mbar_wait(&tmem_full[acc], acc_phase);
+          tc_fence_after();
+          if (live) {
+#pragma unroll 1
+            for (int c = 0; c < nchunk; ++c) {
+              uint32_t r[32];
+              __syncwarp();
+              tmem_ld_x32(t_row + c * 32, r);
+              if (lane == 0) {
+                if (has_res || split) bulk_wait_read<0>(); else bulk_wait_read<1>();
+                if (has_res && c + 1 < nchunk) {  // prefetch the next residual chunk
+                  mbar_expect_tx(&rbar[buf ^ 1], 4096);
+                  tma_load_2d(stg + (buf ^ 1) * 4096, &tmR, &rbar[buf ^ 1], n0 + (c + 1) * 32,
+                              row0);
+                }
+              }
+              tmem_ld_wait();
+              float* v = reinterpret_cast<float*>(r);
+              bias_act32(p, v, n0 + c * 32);
+              __syncwarp();
+              uint8_t* b = stg + buf * 4096;
+              if (has_res) {
+                if (buf == 0) { mbar_wait(&rbar[0], rphase0); rphase0 ^= 1; }
+                else          { mbar_wait(&rbar[1], rphase1); rphase1 ^= 1; }
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                  const float4 t = *reinterpret_cast<const float4*>(b + stg_off(lane, g));
+                  v[4 * g] += t.x; v[4 * g + 1] += t.y; v[4 * g + 2] += t.z; v[4 * g + 3] += t.w;
+                }
+              }
+              if (p.alpha != 1.0f) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
+              }
+              if (!split) {
+#pragma unroll
+                for (int g = 0; g < 8; ++g)
+                  *reinterpret_cast<float4*>(b + stg_off(lane, g)) =
+                      make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+              } else {
+                uint8_t* bl = stg + (buf ^ 1) * 4096;
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                  const float h0 = tf32_hi(v[4 * g]), h1 = tf32_hi(v[4 * g + 1]),
+                              h2 = tf32_hi(v[4 * g + 2]), h3 = tf32_hi(v[4 * g + 3]);
+                  *reinterpret_cast<float4*>(b + stg_off(lane, g)) = make_float4(h0, h1, h2, h3);
+                  *reinterpret_cast<float4*>(bl + stg_off(lane, g)) = make_float4(
+                      v[4 * g] - h0, v[4 * g + 1] - h1, v[4 * g + 2] - h2, v[4 * g + 3] - h3);
+                }
+              }
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_2d(&tmO0, b, n0 + c * 32, row0);
+                if (split) tma_store_2d(&tmO1, stg + (buf ^ 1) * 4096, n0 + c * 32, row0);
+                bulk_commit();
+              }
+              if (!split) buf ^= 1;
+            }
+          }
+        }
+      } else {
+        // ---- direct path (row-remapped patch embedding, unaligned / tiny outputs)
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        const int m = row0 + lane;
+        const bool row_ok = m < p.M;
+        long long row_out = m;
+        int rb_row = 0;
+        if (p.rowmap_period > 0) {
+          const int q = m / p.rowmap_period;
+          const int r = m - q * p.rowmap_period;
+          rb_row = p.rowmap_off + r;
+          row_out = (long long)q * p.rowmap_stride + rb_row;
+        }
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          const int col0 = n0 + c * 32;
+          if (col0 >= p.N) break;
+          uint32_t r[32];
+          __syncwarp();
+          tmem_ld_x32(t_row + c * 32, r);
+          tmem_ld_wait();
+          if (row_ok) {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            const int cnt = p.N - col0;
+            if (cnt >= 32 && p.vec_ok)
+              epilogue_store<true>(p, v, 32, row_out, rb_row, col0);
+            else
+              epilogue_store<false>(p, v, cnt < 32 ? cnt : 32, row_out, rb_row, col0);
+          }
         }
       }
+      __syncwarp();
       tc_fence_before();
-      mbar_arrive(&tmem_empty[acc]);
+      if (CL == 1 || leader) mbar_arrive(&tmem_empty[acc]);
+      else mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
       }
     }
+    if (p.tma_epi && lane == 0) bulk_wait_all<0>();  // stores complete before the CTA retires
   }
 
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // nobody leaves while the peer may still signal / be written
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if (CL == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    else tmem_dealloc_cg2(tmem_base, Cfg::kTmemCols);
   }
 }
 
-template <int BN, int KIND>
-static int launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b0,
-                       const CUtensorMap& b1, const GemmKParams& p, cudaStream_t stream,
+template <int BN, int KIND, int CL>
+static int launch_gemm(const CUtensorMap* tm, const GemmKParams& p, cudaStream_t stream,
                        int tag) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CL>;
   static bool attr_done[64] = {};  // per device; benign race: the attribute set is idempotent
   int dev = 0;
   DEVIT_CUDA_OK(cudaGetDevice(&dev));
   if (!attr_done[dev & 63]) {
-    DEVIT_CUDA_OK(cudaFuncSetAttribute(gemm_kernel<BN, KIND>,
+    DEVIT_CUDA_OK(cudaFuncSetAttribute(gemm_kernel<BN, KIND, CL>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg::kSmemBytes));
     attr_done[dev & 63] = true;
   }
-  const int num_tiles = ((p.M + kBlockM - 1) / kBlockM) * ((p.N + BN - 1) / BN);
-  int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+  const int num_m = (p.M + kBlockM - 1) / kBlockM;
+  const int num_units = ((num_m + CL - 1) / CL) * ((p.N + BN - 1) / BN);
+  int clusters = num_sms() / CL;
+  if (clusters > num_units) clusters = num_units;
+  if (clusters < 1) clusters = 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(clusters * CL);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CL > 1 ? 1 : 0;
   {
     ProfScope ps(tag, stream);
-    gemm_kernel<BN, KIND><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(a0, a1, b0, b1, p);
+    DEVIT_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, KIND, CL>, tm[0], tm[1], tm[2], tm[3],
+                                     tm[4], tm[5], tm[6], p));
   }
   DEVIT_CUDA_OK(cudaGetLastError());
   count_launch();
   return DEVIT_OK;
+}
+
+template <int BN, int KIND>
+static int launch_gemm_cl(int cl, const CUtensorMap* tm, const GemmKParams& p,
+                          cudaStream_t stream, int tag) {
+  if (cl == 2) return launch_gemm<BN, KIND, 2>(tm, p, stream, tag);
+  return launch_gemm<BN, KIND, 1>(tm, p, stream, tag);
 }
 
 static int pick_block_n(int n) {
@@ -453,12 +688,23 @@ extern "C" int devit_gemm(const devit_gemm_args* a, void* stream_v) {
 
   const int tag = (a->profile_tag >= 0 && a->profile_tag < 8) ? a->profile_tag : 0;
   int bn = a->block_n ? a->block_n : pick_block_n(a->n);
+  if (!a->block_n) {
+    if (const char* e = getenv("DEVIT_GEMM_BN")) bn = atoi(e);
+  }
   DEVIT_REQUIRE(bn == 128 || bn == 192 || bn == 256, "devit_gemm: block_n %d unsupported", bn);
+  // CTA pairs (cta_group::2, 256-row tiles) pay off once there are enough m-blocks
+  const int num_m_blocks = (a->m + kBlockM - 1) / kBlockM;
+  int cl = a->cluster_m;
+  if (cl == 0) {
+    cl = num_m_blocks >= 4 * num_sms() / 2 ? 2 : 1;
+    if (const char* e = getenv("DEVIT_GEMM_CLUSTER")) cl = atoi(e);
+  }
+  DEVIT_REQUIRE(cl == 1 || cl == 2, "devit_gemm: cluster_m %d unsupported", cl);
 
   CUtensorMap ta0, ta1, tb0, tb1;
   rc = encode_tmap_2d(&ta0, a->a, elem, a->a_cols, a->a_rows, a->lda, block_k, kBlockM, false);
   if (rc) return rc;
-  rc = encode_tmap_2d(&tb0, a->b, elem, a->b_cols, a->b_rows, a->ldb, block_k, bn, true);
+  rc = encode_tmap_2d(&tb0, a->b, elem, a->b_cols, a->b_rows, a->ldb, block_k, bn / cl, true);
   if (rc) return rc;
   ta1 = ta0;
   tb1 = tb0;
@@ -469,17 +715,48 @@ extern "C" int devit_gemm(const devit_gemm_args* a, void* stream_v) {
                         a->a_cols, a->a_rows, a->lda, block_k, kBlockM, false);
     if (rc) return rc;
     rc = encode_tmap_2d(&tb1, static_cast<const float*>(a->b) + a->b_plane_stride, elem,
-                        a->b_cols, a->b_rows, a->ldb, block_k, bn, true);
+                        a->b_cols, a->b_rows, a->ldb, block_k, bn / cl, true);
     if (rc) return rc;
   }
 
+  // ---- coalesced (TMA) epilogue eligibility
+  bool tma_epi = p.rowmap_period <= 0 && !p.rowbias && (a->n % 4 == 0) &&
+                 (reinterpret_cast<uintptr_t>(a->out) % 16 == 0) && ((a->ldo * out_elem) % 16 == 0);
+  if (a->bias) tma_epi = tma_epi && (reinterpret_cast<uintptr_t>(a->bias) % 16 == 0);
+  if (a->out_kind == DEVIT_OUT_BF16) tma_epi = tma_epi && !a->resid;
+  if (a->out_kind == DEVIT_OUT_F32_SPLIT)
+    tma_epi = tma_epi && !a->resid && ((a->out_plane_stride * 4) % 16 == 0);
+  if (a->resid)
+    tma_epi = tma_epi && (reinterpret_cast<uintptr_t>(a->resid) % 16 == 0) &&
+              ((a->ldr * 4) % 16 == 0);
+  p.tma_epi = tma_epi ? 1 : 0;
+  CUtensorMap tm[7];
+  tm[0] = ta0; tm[1] = ta1; tm[2] = tb0; tm[3] = tb1;
+  tm[4] = ta0; tm[5] = ta0; tm[6] = ta0;  // placeholders when the direct epilogue is used
+  if (tma_epi) {
+    const int box_cols = a->out_kind == DEVIT_OUT_BF16 ? 64 : 32;
+    rc = encode_tmap_2d(&tm[4], a->out, out_elem, a->n, a->m, a->ldo, box_cols, 32, false);
+    if (rc) return rc;
+    tm[5] = tm[4];
+    if (a->out_kind == DEVIT_OUT_F32_SPLIT) {
+      rc = encode_tmap_2d(&tm[5], static_cast<float*>(a->out) + a->out_plane_stride, 4, a->n,
+                          a->m, a->ldo, 32, 32, false);
+      if (rc) return rc;
+    }
+    tm[6] = tm[4];
+    if (a->resid) {
+      rc = encode_tmap_2d(&tm[6], a->resid, 4, a->n, a->m, a->ldr, 32, 32, false);
+      if (rc) return rc;
+    }
+  }
+
   if (kind == 0) {
-    if (bn == 128) return launch_gemm<128, 0>(ta0, ta1, tb0, tb1, p, stream, tag);
-    if (bn == 192) return launch_gemm<192, 0>(ta0, ta1, tb0, tb1, p, stream, tag);
-    return launch_gemm<256, 0>(ta0, ta1, tb0, tb1, p, stream, tag);
+    if (bn == 128) return launch_gemm_cl<128, 0>(cl, tm, p, stream, tag);
+    if (bn == 192) return launch_gemm_cl<192, 0>(cl, tm, p, stream, tag);
+    return launch_gemm_cl<256, 0>(cl, tm, p, stream, tag);
   } else {
-    if (bn == 128) return launch_gemm<128, 1>(ta0, ta1, tb0, tb1, p, stream, tag);
-    if (bn == 192) return launch_gemm<192, 1>(ta0, ta1, tb0, tb1, p, stream, tag);
-    return launch_gemm<256, 1>(ta0, ta1, tb0, tb1, p, stream, tag);
+    if (bn == 128) return launch_gemm_cl<128, 1>(cl, tm, p, stream, tag);
+    if (bn == 192) return launch_gemm_cl<192, 1>(cl, tm, p, stream, tag);
+    return launch_gemm_cl<256, 1>(cl, tm, p, stream, tag);
   }
 }

@@ -129,6 +129,8 @@ typedef struct devit_gemm_args {
   int32_t rowmap_period, rowmap_stride, rowmap_off;
   int32_t block_n; /* 0 = choose automatically from {128, 192, 256} */
   int32_t profile_tag; /* DEVIT_TAG_GEMM_* bucket used by devit_profile_collect */
+  int32_t cluster_m;   /* 1 = one CTA per 128-row tile; 2 = CTA pair (cta_group::2) per
+                          256-row tile, each CTA staging half of the weight tile; 0 = auto */
 } devit_gemm_args;
 
 int devit_gemm(const devit_gemm_args* args, void* stream);

@@ -67,6 +67,45 @@ def test_gemm_epilogue_gelu_resid_alpha():
     assert rel(x, ref) < 2e-5
 
 
+@pytest.mark.parametrize("cl", [1, 2])
+@pytest.mark.parametrize("bn", [128, 192, 256])
+def test_gemm_cta_pair(cl, bn):
+    """cta_group::2 CTA pairs (256-row tiles), ragged M (odd number of m-blocks) and ragged N,
+    bf16 + fp32-residual + split epilogues."""
+    m, n, k = 128 * 36 + 55, 864, 384
+    a = _mk((m, k), 21).bfloat16()
+    w = _mk((n, k), 22, 0.05).bfloat16()
+    bias = _mk((n,), 23)
+    ref = a.float() @ w.float().t() + bias
+    out = L.gemm(a, w, bias=bias, out_kind=L.OUT_BF16, block_n=bn, cluster_m=cl)
+    assert rel(out, ref) < 6e-3
+    res = _mk((m, n), 24)
+    xx = res.clone()
+    L.gemm(a, w, bias=bias, resid=xx, out=xx, out_kind=L.OUT_F32, block_n=bn, cluster_m=cl)
+    assert rel(xx, ref + res) < 2e-5
+    a32, w32 = _mk((m, k), 25), _mk((n, k), 26, 0.05)
+    o32 = L.gemm(L.split_tf32(a32), L.split_tf32(w32), precision=L.DEVIT_FP32, bias=bias,
+                 out_kind=L.OUT_F32_SPLIT, block_n=bn, cluster_m=cl)
+    ref32 = (a32.double() @ w32.double().t() + bias.double()).float()
+    assert rel(o32[0] + o32[1], ref32) < 1e-5
+
+
+def test_gemm_gelu_bf16_output_fast_path():
+    """bf16-output epilogue uses the tanh.approx-based erf-GELU fit: the result must stay within
+    bf16 rounding of the exact erf form (abs error < 2e-3 + half a bf16 ulp)."""
+    m, n, k = 1024, 1536, 384
+    a = (_mk((m, k), 11) * 1.5).bfloat16()
+    w = _mk((n, k), 12, 0.08).bfloat16()
+    bias = _mk((n,), 13)
+    out = L.gemm(a, w, bias=bias, act=L.ACT_GELU_ERF, out_kind=L.OUT_BF16).float()
+    pre = a.float() @ w.float().t() + bias
+    ref = torch.nn.functional.gelu(pre)
+    assert pre.abs().max() > 6          # the saturated range is exercised
+    err = (out - ref).abs()
+    assert (err <= 1.5e-3 + ref.abs() * 2 ** -8).all(), err.max().item()
+    assert rel(out, ref) < 6e-3
+
+
 def test_gemm_rowmap_rowbias():
     # the patch-embed epilogue: row m -> (m // P) * T + off + m % P, + pos[off + m % P]
     bsz, P, T, off, n, k = 5, 196, 198, 2, 384, 768

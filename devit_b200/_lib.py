@@ -82,6 +82,7 @@ _SIGS = {
     "devit_profile_enable": (C.c_int, [C.c_int]),
     "devit_profile_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "devit_gemm": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
+    "devit_debug_set_trace": (C.c_int, [C.c_void_p]),
     "devit_layernorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                   C.c_int32, C.c_float, C.c_int32, C.c_int64, C.c_void_p]),
     "devit_attention": (C.c_int, [C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,

@@ -3,6 +3,8 @@
 // row-remapped into the token matrix) -> cls/dist rows -> depth x [LN, QKV GEMM, attention,
 // proj GEMM (+residual), LN, fc1 GEMM (+GELU), fc2 GEMM (+residual)] -> final LN on the
 // cls/dist rows only.  Gated heads / neurons never appear: the host packs compacted weights.
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -63,6 +65,18 @@ static int plan_layout(const devit_vit_desc* d, int batch, VitLayout* L) {
   return DEVIT_OK;
 }
 
+// DEVIT_SYNC_DEBUG=1: synchronise and report after every op of the forward (debug aid)
+static int sync_debug(const char* what, int layer, void* stream) {
+  static int on = -1;
+  if (on < 0) on = getenv("DEVIT_SYNC_DEBUG") ? 1 : 0;
+  if (!on) return DEVIT_OK;
+  cudaError_t e = cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream));
+  fprintf(stderr, "[devit] layer %d %s: %s\n", layer, what, cudaGetErrorString(e));
+  fflush(stderr);
+  if (e != cudaSuccess) return set_error(DEVIT_ERR_CUDA, "%s failed: %s", what, cudaGetErrorString(e));
+  return DEVIT_OK;
+}
+
 static void base_gemm(devit_gemm_args* g, int precision) {
   std::memset(g, 0, sizeof(*g));
   g->precision = precision;
@@ -113,6 +127,7 @@ extern "C" int devit_vit_forward(const devit_vit_desc* d, const float* images, i
   //      image b to token row b*tokens + num_prefix + p            (models/de_vit.py:258-264)
   rc = devit_im2col_patch16(images, qkv, batch, d->chans, d->img, opk, Mp * kp, stream);
   if (rc) return rc;
+  if ((rc = sync_debug("im2col", -1, stream))) return rc;
   devit_gemm_args g;
   base_gemm(&g, prec);
   g.m = static_cast<int>(Mp);
@@ -128,8 +143,10 @@ extern "C" int devit_vit_forward(const devit_vit_desc* d, const float* images, i
   g.profile_tag = DEVIT_TAG_GEMM_PATCH;
   rc = devit_gemm(&g, stream);
   if (rc) return rc;
+  if ((rc = sync_debug("patch gemm", -1, stream))) return rc;
   rc = devit_token_prefix(x, d->prefix, d->pos, batch, L.tokens, D, d->num_prefix, stream);
   if (rc) return rc;
+  if ((rc = sync_debug("prefix", -1, stream))) return rc;
 
   const int nl = (num_layers_run < 0 || num_layers_run > d->depth) ? d->depth : num_layers_run;
   for (int l = 0; l < nl; ++l) {
@@ -146,14 +163,17 @@ extern "C" int devit_vit_forward(const devit_vit_desc* d, const float* images, i
     g.b_plane_stride = static_cast<long long>(3 * hd) * D;
     g.segs[0] = devit_gemm_seg{0, 0, 0, D};
     g.out = qkv; g.ldo = 3 * hd; g.out_kind = opk; g.out_plane_stride = M * 3 * hd;
+    if ((rc = sync_debug("ln1", l, stream))) return rc;
     g.bias = w.b_qkv;
     g.profile_tag = DEVIT_TAG_GEMM_QKV;
     rc = devit_gemm(&g, stream);
     if (rc) return rc;
+    if ((rc = sync_debug("qkv gemm", l, stream))) return rc;
     // o = softmax(q k^T / 8) v  per kept head                    (:70-74)
     rc = devit_attention(prec, qkv, M * 3 * hd, o, M * hd, batch, L.tokens, w.heads, 0.125f,
                          stream);
     if (rc) return rc;
+    if ((rc = sync_debug("attention", l, stream))) return rc;
     // x += o Wproj^T + b                                         (:81, :114)
     base_gemm(&g, prec);
     g.m = static_cast<int>(M); g.n = D;
@@ -166,6 +186,7 @@ extern "C" int devit_vit_forward(const devit_vit_desc* d, const float* images, i
     g.profile_tag = DEVIT_TAG_GEMM_PROJ;
     rc = devit_gemm(&g, stream);
     if (rc) return rc;
+    if ((rc = sync_debug("proj gemm", l, stream))) return rc;
     // x -> LN2 -> y                                              (:115)
     rc = devit_layernorm(x, w.ln2_g, w.ln2_b, y, M, D, d->ln_eps, opk, M * D, stream);
     if (rc) return rc;
@@ -178,10 +199,12 @@ extern "C" int devit_vit_forward(const devit_vit_desc* d, const float* images, i
     g.b_plane_stride = static_cast<long long>(F) * D;
     g.segs[0] = devit_gemm_seg{0, 0, 0, D};
     g.out = hid; g.ldo = F; g.out_kind = opk; g.out_plane_stride = M * F;
+    if ((rc = sync_debug("ln2", l, stream))) return rc;
     g.bias = w.b_fc1; g.act = DEVIT_ACT_GELU_ERF;
     g.profile_tag = DEVIT_TAG_GEMM_FC1;
     rc = devit_gemm(&g, stream);
     if (rc) return rc;
+    if ((rc = sync_debug("fc1 gemm", l, stream))) return rc;
     // x += hid W2^T + b2                                         (:45, :115)
     base_gemm(&g, prec);
     g.m = static_cast<int>(M); g.n = D;
@@ -194,6 +217,7 @@ extern "C" int devit_vit_forward(const devit_vit_desc* d, const float* images, i
     g.profile_tag = DEVIT_TAG_GEMM_FC2;
     rc = devit_gemm(&g, stream);
     if (rc) return rc;
+    if ((rc = sync_debug("fc2 gemm", l, stream))) return rc;
   }
   if (x_out) {
     DEVIT_CUDA_OK(cudaMemcpyAsync(x_out, x, static_cast<size_t>(M) * D * 4,

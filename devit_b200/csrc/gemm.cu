@@ -1,16 +1,22 @@
 // Persistent, warp-specialised tcgen05 GEMM with a fused epilogue (see include/devit_b200.h,
 // devit_gemm).  out = epilogue(sum_s A_s * B_s^T), A and B K-major, fp32 accumulation in TMEM.
 //
-// CTA = 192 threads: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM owner),
-// warps 2..5 = epilogue (TMEM -> registers -> global).  Three pipelines:
-//   smem ring   : full[s] / empty[s] mbarriers between TMA and the MMA issuer,
-//   TMEM ring   : two accumulator stages, tmem_full[2] / tmem_empty[2] between the MMA issuer
-//                 and the epilogue warps, so the epilogue of tile i overlaps the MMAs of i+1,
-//   tile loop   : static round-robin over (m_blk, n_blk), n fastest so CTAs that are resident
-//                 together share the same A rows in L2.
-// Tile = 128 x BN (BN in {128,192,256}); each k-block is one 128-byte swizzle atom along K
-// (64 bf16 or 32 tf32) = 4 UMMA instructions.  The last N tile issues a narrower UMMA
-// (N rounded up to 16) so ragged shrunk widths do not pay for a full tile.
+// CTA = 320 threads: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM owner),
+// warps 2..9 = epilogue (two warps per TMEM lane quarter, alternating column chunks).
+// Pipelines:
+//   smem ring : kStages slots of {A k-block 16 KB | B k-block}, full[s] / empty[s] mbarriers
+//               between the TMA producer and the MMA issuer.
+//   TMEM ring : two accumulator stages (tmem_full / tmem_empty) so the epilogue of tile i
+//               overlaps the MMAs of tile i+1.
+//   stores    : registers -> 128B-swizzled shared memory -> TMA store (coalesced, edge-clipped);
+//               an fp32 residual tile is TMA-prefetched chunk by chunk into the same staging
+//               buffers, summed in place and stored from there.
+//   tile loop : static round-robin, n fastest so co-resident CTAs share A rows in L2.
+// Tile = 128 x BN (BN in {128,192,256}); a k-block is one 128-byte swizzle atom along K
+// (64 bf16 or 32 tf32) = 4 UMMAs.  The last N tile issues a narrower UMMA (N rounded up to
+// 16) so ragged shrunk widths do not pay for a full tile.
+// CL = 2 (cta_group::2): a CTA pair computes a 256 x BN tile with one MMA stream issued by the
+// leader; each CTA stages its own 128 A rows and HALF of the B rows.
 #include <cstdlib>
 
 #include "common.cuh"
@@ -19,7 +25,8 @@
 namespace devit {
 
 constexpr int kBlockM = 128;
-constexpr int kGemmThreads = 192;
+constexpr int kEpiWarps = 8;
+constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
 constexpr int kMaxKSegs = 24;  // 8 logical segments x 3 passes in the 3xTF32 mode
 
 struct KSeg {
@@ -30,6 +37,7 @@ struct KSeg {
 struct GemmKParams {
   int M, N;
   int num_segs;
+  int total_kb;  // sum of k_blocks over the segments
   KSeg segs[kMaxKSegs];
   void* out;
   long long ldo;
@@ -44,51 +52,46 @@ struct GemmKParams {
   float alpha;
   int rowmap_period, rowmap_stride, rowmap_off;
   int vec_ok;
-  int tma_epi;  // 1: stage the tile through shared memory, TMA-store it (and TMA-load resid)
+  int tma_epi;  // 1: coalesced epilogue (smem staging + TMA store, residual via R-slots)
+  int dbg;      // DEVIT_GEMM_DBG bit0: no epilogue work, bit1: no TMA loads, bit2: no MMAs
+  long long* trace;  // optional clock64 trace buffer (CTA 0 only), see devit_debug_set_trace
 };
+
+static long long* g_trace = nullptr;
+
+#ifdef DEVIT_GEMM_TRACE
+#define DEVIT_TRACE(slot_, idx_)                                                  \
+  do {                                                                            \
+    if (p.trace && blockIdx.x == 0 && (idx_) < 512)                               \
+      p.trace[(slot_) * 512 + (idx_)] = clock64();                                \
+  } while (0)
+#else
+#define DEVIT_TRACE(slot_, idx_) do { (void)(idx_); } while (0)
+#endif
 
 template <int BN, int CL>
 struct GemmCfg {
   static constexpr int kStageA = kBlockM * 128;
   static constexpr int kStageB = (BN / CL) * 128;  // a CTA pair splits B's rows half / half
   static constexpr int kStageBytes = kStageA + kStageB;
-  // epilogue staging: 4 warps x 2 buffers x (32 rows x 128 B), 128B-swizzled like the TMA box
-  static constexpr int kEpiBytes = 4 * 2 * 4096;
-  static constexpr int kStages =
-      (192 * 1024) / kStageBytes > 8 ? 8 : (192 * 1024) / kStageBytes;
+  static constexpr int kEpiBytes = kEpiWarps * 4096;      // one [32 x 128 B] buffer per warp
+  static constexpr int kBiasBytes = kEpiWarps * BN * 4;   // per-warp copy of the tile's bias
+  static constexpr int kBarBytes = (3 * 8 + 4) * 8 + 16 + 32;
+  static constexpr int kBudget = 227 * 1024 - 1024 - kEpiBytes - kBiasBytes - kBarBytes;
+  static constexpr int kStages = kBudget / kStageBytes > 8 ? 8 : kBudget / kStageBytes;
   static constexpr int kAccStride = BN <= 128 ? 128 : 256;
   static constexpr int kTmemCols = 2 * kAccStride;
-  static constexpr int kBarBytes = (2 * kStages + 4 + 8) * 8 + 16;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + kBarBytes + 1024;
+  static constexpr int kSmemBytes =
+      kStages * kStageBytes + kEpiBytes + kBiasBytes + kBarBytes + 1024;
+  static_assert(kStages >= 3, "not enough shared memory for the operand ring");
 };
 
-// byte offset of 16-byte chunk j of row r inside a [32 x 128 B] 128B-swizzled staging buffer
+// byte offset of 16-byte chunk j of row r inside a [rows x 128 B] 128B-swizzled buffer
 __device__ __forceinline__ int stg_off(int r, int j) { return r * 128 + ((j ^ (r & 7)) << 4); }
 
-// bias (+ GELU) on 32 consecutive accumulator columns starting at col0 (columns >= N untouched)
-__device__ __forceinline__ void bias_act32(const GemmKParams& p, float* v, int col0) {
-  if (p.bias) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      if (col0 + 4 * j + 3 < p.N) {
-        const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);
-        v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
-      }
-    }
-  }
-  if (p.act == DEVIT_ACT_GELU_ERF) {
-    if (p.out_kind == DEVIT_OUT_BF16) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(v[j]);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-    }
-  }
-}
-
-// Applies the epilogue to `cnt` consecutive columns held in v[] and stores them.
-// FULL = all 32 columns valid and every pointer suitably aligned -> 16-byte vector path.
+// -------------------------------------------------------------------- direct (fallback) path
+// Applies the epilogue to `cnt` consecutive columns held in v[] and stores them with plain
+// global accesses (used for the row-remapped patch embedding and unaligned / tiny outputs).
 template <bool FULL>
 __device__ __forceinline__ void epilogue_store(const GemmKParams& p, float* v, int cnt,
                                                long long row_out, int rb_row, int col0) {
@@ -183,14 +186,26 @@ __device__ __forceinline__ void epilogue_store(const GemmKParams& p, float* v, i
   }
 }
 
-// KIND: 0 = bf16 operands, 1 = fp32 operands consumed as tf32.
-// CL = 1: one CTA per 128 x BN tile (cta_group::1).
-// CL = 2: a CTA pair (cluster of 2, cta_group::2) computes a 256 x BN tile with ONE MMA stream
-//   issued by the leader: each CTA stages its own 128 A rows and HALF of the B rows, so the
-//   bytes every SM pulls through the L2 fabric per FLOP drop by ~1.5x -- these GEMMs are bound
-//   by that fabric (~6.3 KB/clk chip-wide), not by the tensor pipe.  All TMA loads of the pair
-//   complete on the leader's `full` barrier; tcgen05.commit multicasts `empty` / `tmem_full`
-//   to both CTAs; the peer's epilogue threads arrive remotely on the leader's `tmem_empty`.
+// bias (from the warp's shared-memory copy) + activation on 32 accumulator columns
+__device__ __forceinline__ void bias_act32(const GemmKParams& p, float* v, const float* bias_s) {
+  if (p.bias) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 t = *reinterpret_cast<const float4*>(bias_s + 4 * j);  // warp broadcast
+      v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+    }
+  }
+  if (p.act == DEVIT_ACT_GELU_ERF) {
+    if (p.out_kind == DEVIT_OUT_BF16) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(v[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+    }
+  }
+}
+
 template <int BN, int KIND, int CL>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
@@ -206,19 +221,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* epi_smem = smem + kStages * Cfg::kStageBytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + Cfg::kEpiBytes);
-  uint64_t* empty_bar = full_bar + kStages;
-  uint64_t* tmem_full = empty_bar + kStages;
+  float* bias_smem = reinterpret_cast<float*>(epi_smem + Cfg::kEpiBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + Cfg::kEpiBytes + Cfg::kBiasBytes);
+  uint64_t* empty_bar = full_bar + 8;
+  uint64_t* rfull_bar = empty_bar + 8;  // [4 quarters][2 buffers]: residual chunk has landed
+  uint64_t* tmem_full = rfull_bar + 8;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint64_t* res_bar = tmem_empty + 2;  // [4 warps][2 buffers]: residual chunk landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 8);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
-  const int warp = threadIdx.x >> 5;
+  // Role dispatch must be WARP-UNIFORM in the compiler's eyes (shfl from lane 0): the async
+  // instructions (UTMALDG / UTCHMMA / UTCBAR / UTMASTG) take uniform-register operands, and in
+  // code the compiler considers divergent every one of them is wrapped in an elect+broadcast
+  // "waterfall" loop that costs more than the instruction itself.  So whole warps run the role
+  // loops and a single elected lane issues.
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
-  const int cta_rank = CL > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int cta_rank =
+      CL > 1 ? __shfl_sync(0xffffffffu, static_cast<int>(cluster_ctarank()), 0) : 0;
   const int cluster_id = blockIdx.x / CL;
   const int num_clusters = gridDim.x / CL;
   const bool leader = cta_rank == 0;
+  const bool has_res = p.tma_epi && p.resid != nullptr;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);
@@ -231,11 +254,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
+    for (int s = 0; s < 8; ++s) mbar_init(&rfull_bar[s], 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 128 * CL);  // every epilogue thread of the pair
+      mbar_init(&tmem_empty[s], 32 * kEpiWarps * CL);  // every epilogue thread (of the pair)
     }
-    for (int s = 0; s < 8; ++s) mbar_init(&res_bar[s], 1);
     if (p.tma_epi) {
       tma_prefetch_desc(&tmO0);
       if (p.resid) tma_prefetch_desc(&tmR);
@@ -255,7 +278,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
   __syncthreads();
   if (CL > 1) cluster_sync_all();  // the peer's barriers exist before anything signals them
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  const int total_kb = p.total_kb;
 
   const int num_m = (p.M + kBlockM - 1) / kBlockM;
   const int num_n = (p.N + BN - 1) / BN;
@@ -263,35 +287,43 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    {
       int stage = 0;
       uint32_t phase = 0;
+      int tr_p = 0;
       for (int unit = cluster_id; unit < num_units; unit += num_clusters) {
         const int m0 = ((unit / num_n) * CL + cta_rank) * kBlockM;
         const int n0 = (unit % num_n) * BN;
-        int n_cur = p.N - n0;
-        n_cur = n_cur >= BN ? BN : ((n_cur + 16 * CL - 1) & ~(16 * CL - 1));
+        const int n_valid = (p.N - n0) < BN ? (p.N - n0) : BN;
+        const int n_cur = n_valid >= BN ? BN : ((n_valid + 16 * CL - 1) & ~(16 * CL - 1));
         for (int s = 0; s < p.num_segs; ++s) {
           const KSeg sg = p.segs[s];
           const CUtensorMap* ma = (KIND == 1 && sg.a_plane) ? &tmA1 : &tmA0;
           const CUtensorMap* mb = (KIND == 1 && sg.b_plane) ? &tmB1 : &tmB0;
           for (int kb = 0; kb < sg.k_blocks; ++kb) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
+            DEVIT_TRACE(0, tr_p);
+            mbar_wait_warp(&empty_bar[stage], phase ^ 1);
+            DEVIT_TRACE(1, tr_p);
             uint8_t* sa = smem + stage * Cfg::kStageBytes;
             uint8_t* sb = sa + Cfg::kStageA;
-            if (CL == 1) {
-              mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-              tma_load_2d(sa, ma, &full_bar[stage], sg.a_k_off + kb * kBlockK,
-                          sg.a_row_off + m0);
-              tma_load_2d(sb, mb, &full_bar[stage], sg.b_k_off + kb * kBlockK, n0);
-            } else {
-              // both CTAs' bytes complete on the LEADER's barrier (it issues the MMAs)
-              const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
-              if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
-              tma_load_2d_cg2(sa, ma, full_leader, sg.a_k_off + kb * kBlockK, sg.a_row_off + m0);
-              tma_load_2d_cg2(sb, mb, full_leader, sg.b_k_off + kb * kBlockK,
-                              n0 + cta_rank * (n_cur / 2));
+            if (elect_one()) {
+              if (CL == 1) {
+                mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+                tma_load_2d(sa, ma, &full_bar[stage], sg.a_k_off + kb * kBlockK,
+                            sg.a_row_off + m0);
+                tma_load_2d(sb, mb, &full_bar[stage], sg.b_k_off + kb * kBlockK, n0);
+              } else {
+                // both CTAs' bytes complete on the LEADER's barrier (it issues the MMAs)
+                const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
+                if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+                tma_load_2d_cg2(sa, ma, full_leader, sg.a_k_off + kb * kBlockK,
+                                sg.a_row_off + m0);
+                tma_load_2d_cg2(sb, mb, full_leader, sg.b_k_off + kb * kBlockK,
+                                n0 + cta_rank * (n_cur / 2));
+              }
             }
+            DEVIT_TRACE(2, tr_p);
+            ++tr_p;
             if (++stage == kStages) {
               stage = 0;
               phase ^= 1;
@@ -302,55 +334,65 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0 && leader) {
+    if (leader) {
       int stage = 0;
-      uint32_t phase = 0;
+      uint32_t kphase_bits = 0;  // per-slot parity of full_bar: it completes on K-uses only
       int acc = 0;
       uint32_t acc_phase = 0;
+      int tr_m = 0, tr_t = 0;
       for (int unit = cluster_id; unit < num_units; unit += num_clusters) {
         const int n0 = (unit % num_n) * BN;
-        int n_cur = p.N - n0;
-        n_cur = n_cur >= BN ? BN : ((n_cur + 16 * CL - 1) & ~(16 * CL - 1));
+        const int n_valid = (p.N - n0) < BN ? (p.N - n0) : BN;
+        const int n_cur = n_valid >= BN ? BN : ((n_valid + 16 * CL - 1) & ~(16 * CL - 1));
         const uint32_t idesc =
             make_idesc(KIND == 0 ? kFmtBF16 : kFmtTF32, kBlockM * CL, n_cur, 0, 0);
+        DEVIT_TRACE(7, tr_t);
         if (CL == 1) mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         else mbar_wait_cluster(&tmem_empty[acc], acc_phase ^ 1);
+        __syncwarp();
         tc_fence_after();
+        DEVIT_TRACE(8, tr_t);
+        ++tr_t;
         const uint32_t d_tmem = tmem_base + acc * Cfg::kAccStride;
         uint32_t accumulate = 0;
-        for (int s = 0; s < p.num_segs; ++s) {
-          const int kbs = p.segs[s].k_blocks;
-          for (int kb = 0; kb < kbs; ++kb) {
-            mbar_wait(&full_bar[stage], phase);
-            tc_fence_after();
-            const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-            const uint32_t sb = sa + Cfg::kStageA;
-            const uint64_t da = make_sw128_desc(sa, 1024, 16);
-            const uint64_t db = make_sw128_desc(sb, 1024, 16);
+        for (int kb = 0; kb < total_kb; ++kb) {
+          DEVIT_TRACE(3, tr_m);
+          mbar_wait_warp(&full_bar[stage], (kphase_bits >> stage) & 1u);
+          kphase_bits ^= 1u << stage;
+          tc_fence_after();
+          DEVIT_TRACE(4, tr_m);
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t sb = sa + Cfg::kStageA;
+          const uint64_t da = make_sw128_desc(sa, 1024, 16);
+          const uint64_t db = make_sw128_desc(sb, 1024, 16);
+          if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               // advance 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
               if (CL == 1) {
-                if (KIND == 0) umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, accumulate);
-                else umma_tf32(d_tmem, da + 2 * k, db + 2 * k, idesc, accumulate);
+                if (KIND == 0) umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, accumulate | k);
+                else umma_tf32(d_tmem, da + 2 * k, db + 2 * k, idesc, accumulate | k);
               } else {
-                if (KIND == 0) umma_bf16_cg2(d_tmem, da + 2 * k, db + 2 * k, idesc, accumulate);
-                else umma_tf32_cg2(d_tmem, da + 2 * k, db + 2 * k, idesc, accumulate);
+                if (KIND == 0)
+                  umma_bf16_cg2(d_tmem, da + 2 * k, db + 2 * k, idesc, accumulate | k);
+                else
+                  umma_tf32_cg2(d_tmem, da + 2 * k, db + 2 * k, idesc, accumulate | k);
               }
-              accumulate = 1;
             }
-            // smem slot reusable (in both CTAs of a pair) once these MMAs retire
+            // slot reusable (in both CTAs of a pair) once these MMAs retire
             if (CL == 1) umma_commit(&empty_bar[stage]);
             else umma_commit_cg2(&empty_bar[stage], 3);
-            if (++stage == kStages) {
-              stage = 0;
-              phase ^= 1;
-            }
           }
+          accumulate = 1;
+          DEVIT_TRACE(6, tr_m);
+          ++tr_m;
+          if (++stage == kStages) stage = 0;
         }
         // accumulator complete -> epilogue warps (of both CTAs of a pair)
-        if (CL == 1) umma_commit(&tmem_full[acc]);
-        else umma_commit_cg2(&tmem_full[acc], 3);
+        if (elect_one()) {
+          if (CL == 1) umma_commit(&tmem_full[acc]);
+          else umma_commit_cg2(&tmem_full[acc], 3);
+        }
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -359,13 +401,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps
+    const int ew = warp - 2;       // 0..7
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, +32)
+    const int half = ew >> 2;      // this warp handles column chunks c with (c & 1) == half
     int acc = 0;
     uint32_t acc_phase = 0;
-    uint8_t* stg = epi_smem + quarter * 8192;  // two 4 KB staging buffers of this warp
-    uint64_t* rbar = res_bar + quarter * 2;
-    uint32_t rphase0 = 0, rphase1 = 0;
-    int buf = 0;
+    uint32_t rphase_bits = 0;      // parity of this warp's two residual-buffer barriers
+    uint8_t* stg = epi_smem + ew * 4096;
+    float* bias_s = bias_smem + ew * BN;
+    int tr_e = 0;
     for (int unit = cluster_id; unit < num_units; unit += num_clusters) {
       const int m0 = ((unit / num_n) * CL + cta_rank) * kBlockM;
       const int n0 = (unit % num_n) * BN;
@@ -373,33 +417,53 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                              acc * Cfg::kAccStride;
       const int n_valid = (p.N - n0) < BN ? (p.N - n0) : BN;
+      const bool live = row0 < p.M;  // warp-uniform
       if (p.tma_epi) {
-        // ---- coalesced path: registers -> swizzled smem -> TMA store (rows/cols past the
-        //      edge are clipped by the tensor map); fp32 residual arrives by TMA as well
-        const bool live = row0 < p.M;  // warp-uniform
+        // the tile's bias -> this warp's shared-memory copy (overlaps the wait for the MMAs)
+        if (p.bias) {
+#pragma unroll
+          for (int i = 0; i < BN / 32; ++i) {
+            const int col = n0 + i * 32 + lane;
+            bias_s[i * 32 + lane] = col < p.N ? __ldg(p.bias + col) : 0.f;
+          }
+        }
+        if (has_res && ew < 4 && live) {
+          // residual chunk 0 can fly while the MMAs of this tile are still running
+          if (elect_one()) {
+            bulk_wait_read<0>();
+            mbar_expect_tx(&rfull_bar[quarter * 2], 4096);
+            tma_load_2d(stg, &tmR, &rfull_bar[quarter * 2], n0, row0);
+          }
+        }
+        if (ew == 0 && lane == 0) DEVIT_TRACE(9, tr_e);
+        mbar_wait_warp(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        if (ew == 0 && lane == 0) DEVIT_TRACE(10, tr_e);
         if (p.out_kind == DEVIT_OUT_BF16) {
-          mbar_wait(&tmem_full[acc], acc_phase);
-          tc_fence_after();
-          if (live) {
-            const int nchunk = (n_valid + 63) >> 6;
+          // ---- bf16 output: 64 columns (128 B per row) per chunk
+          const int nchunk = (n_valid + 63) >> 6;
+          if (live && !(p.dbg & 1)) {
 #pragma unroll 1
-            for (int c = 0; c < nchunk; ++c) {
+            for (int c = half; c < nchunk; c += 2) {
               uint32_t r0[32], r1[32];
-              __syncwarp();
+              const bool tr = ew == 0 && lane == 0 && c == 0;
+              if (tr) DEVIT_TRACE(12, tr_e);
               tmem_ld_x32(t_row + c * 64, r0);
               tmem_ld_x32(t_row + c * 64 + 32, r1);
               tmem_ld_wait();
+              if (tr) DEVIT_TRACE(13, tr_e);
               float* v0 = reinterpret_cast<float*>(r0);
               float* v1 = reinterpret_cast<float*>(r1);
-              bias_act32(p, v0, n0 + c * 64);
-              bias_act32(p, v1, n0 + c * 64 + 32);
+              bias_act32(p, v0, bias_s + c * 64);
+              bias_act32(p, v1, bias_s + c * 64 + 32);
               if (p.alpha != 1.0f) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) { v0[j] *= p.alpha; v1[j] *= p.alpha; }
               }
-              if (lane == 0) bulk_wait_read<1>();  // the store that last used `buf` has drained
+              if (tr) DEVIT_TRACE(14, tr_e);
+              if (elect_one()) bulk_wait_read<0>();  // previous store of this warp has drained
               __syncwarp();
-              uint8_t* b = stg + buf * 4096;
+              if (tr) DEVIT_TRACE(15, tr_e);
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
                 uint4 t;
@@ -407,96 +471,134 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
                 t.y = pack_bf16x2(v0[8 * g + 2], v0[8 * g + 3]);
                 t.z = pack_bf16x2(v0[8 * g + 4], v0[8 * g + 5]);
                 t.w = pack_bf16x2(v0[8 * g + 6], v0[8 * g + 7]);
-                *reinterpret_cast<uint4*>(b + stg_off(lane, g)) = t;
+                *reinterpret_cast<uint4*>(stg + stg_off(lane, g)) = t;
                 t.x = pack_bf16x2(v1[8 * g], v1[8 * g + 1]);
                 t.y = pack_bf16x2(v1[8 * g + 2], v1[8 * g + 3]);
                 t.z = pack_bf16x2(v1[8 * g + 4], v1[8 * g + 5]);
                 t.w = pack_bf16x2(v1[8 * g + 6], v1[8 * g + 7]);
-                *reinterpret_cast<uint4*>(b + stg_off(lane, 4 + g)) = t;
+                *reinterpret_cast<uint4*>(stg + stg_off(lane, 4 + g)) = t;
               }
+              if (tr) DEVIT_TRACE(16, tr_e);
               fence_proxy_async_smem();
               __syncwarp();
-              if (lane == 0) {
-                tma_store_2d(&tmO0, b, n0 + c * 64, row0);
+              if (tr) DEVIT_TRACE(17, tr_e);
+              if (elect_one()) {
+                tma_store_2d(&tmO0, stg, n0 + c * 64, row0);
                 bulk_commit();
               }
-              buf ^= 1;
+              if (tr) DEVIT_TRACE(18, tr_e);
             }
           }
         } else {
-          // fp32 (optionally split hi/lo, optionally + residual): 32 columns = 128 B per chunk
+          // ---- fp32 output, 32 columns (128 B per row) per chunk
           const bool split = p.out_kind == DEVIT_OUT_F32_SPLIT;
-          const bool has_res = p.resid != nullptr;
           const int nchunk = (n_valid + 31) >> 5;
-          if (live && has_res && lane == 0) {  // residual chunk 0 can fly before the MMAs end
-            bulk_wait_read<0>();
-            mbar_expect_tx(&rbar[buf], 4096);
-            tma_load_2d(stg + buf * 4096, &tmR, &rbar[buf], n0, row0);
-          }
-          mbar_wait(&tmem_full[acc], acc_phase);
-          tc_fence_after();
-          if (live) {
+          if (has_res) {
+            // + fp32 residual (x += ...): warps 0..3 of the epilogue (one per lane quarter)
+            // stream the residual tile through two private buffers -- their own and the idle
+            // partner warp's -- with a one-chunk TMA prefetch; the sum is written back into the
+            // buffer and TMA-stored from there.
+            if (ew < 4 && live) {
+              uint8_t* bufs[2] = {stg, stg + 4 * 4096};
+              uint64_t* rbar = rfull_bar + quarter * 2;
+              int buf = 0;
 #pragma unroll 1
-            for (int c = 0; c < nchunk; ++c) {
-              uint32_t r[32];
-              __syncwarp();
-              tmem_ld_x32(t_row + c * 32, r);
-              if (lane == 0) {
-                if (has_res || split) bulk_wait_read<0>(); else bulk_wait_read<1>();
-                if (has_res && c + 1 < nchunk) {  // prefetch the next residual chunk
-                  mbar_expect_tx(&rbar[buf ^ 1], 4096);
-                  tma_load_2d(stg + (buf ^ 1) * 4096, &tmR, &rbar[buf ^ 1], n0 + (c + 1) * 32,
-                              row0);
+              for (int c = 0; c < nchunk; ++c) {
+                uint32_t r[32];
+                tmem_ld_x32(t_row + c * 32, r);
+                tmem_ld_wait();
+                if (elect_one()) {
+                  bulk_wait_read<0>();  // the store that used the other buffer has drained
+                  if (c + 1 < nchunk) {
+                    mbar_expect_tx(&rbar[buf ^ 1], 4096);
+                    tma_load_2d(bufs[buf ^ 1], &tmR, &rbar[buf ^ 1], n0 + (c + 1) * 32, row0);
+                  }
                 }
-              }
-              tmem_ld_wait();
-              float* v = reinterpret_cast<float*>(r);
-              bias_act32(p, v, n0 + c * 32);
-              __syncwarp();
-              uint8_t* b = stg + buf * 4096;
-              if (has_res) {
-                if (buf == 0) { mbar_wait(&rbar[0], rphase0); rphase0 ^= 1; }
-                else          { mbar_wait(&rbar[1], rphase1); rphase1 ^= 1; }
+                float* v = reinterpret_cast<float*>(r);
+                bias_act32(p, v, bias_s + c * 32);
+                mbar_wait_warp(&rbar[buf], (rphase_bits >> buf) & 1u);
+                rphase_bits ^= 1u << buf;
+                uint8_t* b = bufs[buf];
 #pragma unroll
                 for (int g = 0; g < 8; ++g) {
                   const float4 t = *reinterpret_cast<const float4*>(b + stg_off(lane, g));
                   v[4 * g] += t.x; v[4 * g + 1] += t.y; v[4 * g + 2] += t.z; v[4 * g + 3] += t.w;
                 }
-              }
-              if (p.alpha != 1.0f) {
+                if (p.alpha != 1.0f) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
-              }
-              if (!split) {
+                  for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
+                }
 #pragma unroll
                 for (int g = 0; g < 8; ++g)
                   *reinterpret_cast<float4*>(b + stg_off(lane, g)) =
                       make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
-              } else {
-                uint8_t* bl = stg + (buf ^ 1) * 4096;
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (elect_one()) {
+                  tma_store_2d(&tmO0, b, n0 + c * 32, row0);
+                  bulk_commit();
+                }
+                buf ^= 1;
+              }
+              if (elect_one()) bulk_wait_read<0>();  // partner's buffer is free again
+            }
+          } else if (live) {
+#pragma unroll 1
+            for (int c = half; c < nchunk; c += 2) {
+              uint32_t r[32];
+              tmem_ld_x32(t_row + c * 32, r);
+              tmem_ld_wait();
+              float* v = reinterpret_cast<float*>(r);
+              bias_act32(p, v, bias_s + c * 32);
+              if (p.alpha != 1.0f) {
 #pragma unroll
-                for (int g = 0; g < 8; ++g) {
-                  const float h0 = tf32_hi(v[4 * g]), h1 = tf32_hi(v[4 * g + 1]),
-                              h2 = tf32_hi(v[4 * g + 2]), h3 = tf32_hi(v[4 * g + 3]);
-                  *reinterpret_cast<float4*>(b + stg_off(lane, g)) = make_float4(h0, h1, h2, h3);
-                  *reinterpret_cast<float4*>(bl + stg_off(lane, g)) = make_float4(
-                      v[4 * g] - h0, v[4 * g + 1] - h1, v[4 * g + 2] - h2, v[4 * g + 3] - h3);
+                for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
+              }
+              if (elect_one()) bulk_wait_read<0>();  // this warp's previous store has drained
+              __syncwarp();
+              if (!split) {
+#pragma unroll
+                for (int g = 0; g < 8; ++g)
+                  *reinterpret_cast<float4*>(stg + stg_off(lane, g)) =
+                      make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (elect_one()) {
+                  tma_store_2d(&tmO0, stg, n0 + c * 32, row0);
+                  bulk_commit();
+                }
+              } else {  // hi plane, then lo plane through the same buffer (parity mode)
+#pragma unroll
+                for (int g = 0; g < 8; ++g)
+                  *reinterpret_cast<float4*>(stg + stg_off(lane, g)) =
+                      make_float4(tf32_hi(v[4 * g]), tf32_hi(v[4 * g + 1]),
+                                  tf32_hi(v[4 * g + 2]), tf32_hi(v[4 * g + 3]));
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (elect_one()) {
+                  tma_store_2d(&tmO0, stg, n0 + c * 32, row0);
+                  bulk_commit();
+                  bulk_wait_read<0>();
+                }
+                __syncwarp();
+#pragma unroll
+                for (int g = 0; g < 8; ++g)
+                  *reinterpret_cast<float4*>(stg + stg_off(lane, g)) = make_float4(
+                      v[4 * g] - tf32_hi(v[4 * g]), v[4 * g + 1] - tf32_hi(v[4 * g + 1]),
+                      v[4 * g + 2] - tf32_hi(v[4 * g + 2]), v[4 * g + 3] - tf32_hi(v[4 * g + 3]));
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (elect_one()) {
+                  tma_store_2d(&tmO1, stg, n0 + c * 32, row0);
+                  bulk_commit();
                 }
               }
-              fence_proxy_async_smem();
-              __syncwarp();
-              if (lane == 0) {
-                tma_store_2d(&tmO0, b, n0 + c * 32, row0);
-                if (split) tma_store_2d(&tmO1, stg + (buf ^ 1) * 4096, n0 + c * 32, row0);
-                bulk_commit();
-              }
-              if (!split) buf ^= 1;
             }
           }
         }
       } else {
         // ---- direct path (row-remapped patch embedding, unaligned / tiny outputs)
-        mbar_wait(&tmem_full[acc], acc_phase);
+        mbar_wait_warp(&tmem_full[acc], acc_phase);
         tc_fence_after();
         const int m = row0 + lane;
         const bool row_ok = m < p.M;
@@ -509,7 +611,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
           row_out = (long long)q * p.rowmap_stride + rb_row;
         }
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = half; c < BN / 32; c += 2) {
           const int col0 = n0 + c * 32;
           if (col0 >= p.N) break;
           uint32_t r[32];
@@ -528,6 +630,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
           }
         }
       }
+      if (ew == 0 && lane == 0) {
+        DEVIT_TRACE(11, tr_e);
+        ++tr_e;
+      }
       __syncwarp();
       tc_fence_before();
       if (CL == 1 || leader) mbar_arrive(&tmem_empty[acc]);
@@ -537,7 +643,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
         acc_phase ^= 1;
       }
     }
-    if (p.tma_epi && lane == 0) bulk_wait_all<0>();  // stores complete before the CTA retires
+    if (p.tma_epi && elect_one()) bulk_wait_all<0>();  // stores complete before the CTA retires
   }
 
   tc_fence_before();
@@ -599,7 +705,7 @@ static int launch_gemm_cl(int cl, const CUtensorMap* tm, const GemmKParams& p,
 
 static int pick_block_n(int n) {
   int best = 128, best_waste = 1 << 30;
-  const int cands[3] = {256, 192, 128};
+  const int cands[3] = {192, 256, 128};
   for (int i = 0; i < 3; ++i) {
     const int bn = cands[i];
     const int waste = ((n + bn - 1) / bn) * bn - n;
@@ -612,6 +718,12 @@ static int pick_block_n(int n) {
 }
 
 }  // namespace devit
+
+// Debug: device buffer of 20 x 512 int64 receiving clock64 stamps of CTA 0 (NULL disables).
+extern "C" int devit_debug_set_trace(long long* device_buf) {
+  devit::g_trace = device_buf;
+  return DEVIT_OK;
+}
 
 extern "C" int devit_gemm(const devit_gemm_args* a, void* stream_v) {
   using namespace devit;
@@ -638,6 +750,7 @@ extern "C" int devit_gemm(const devit_gemm_args* a, void* stream_v) {
   p.M = a->m;
   p.N = a->n;
   p.num_segs = 0;
+  p.total_kb = 0;
   for (int s = 0; s < a->num_segs; ++s) {
     const devit_gemm_seg& g = a->segs[s];
     DEVIT_REQUIRE(g.k_len > 0 && g.a_k_off >= 0 && g.b_k_off >= 0 && g.a_row_off >= 0,
@@ -652,10 +765,12 @@ extern "C" int devit_gemm(const devit_gemm_args* a, void* stream_v) {
     const int kbs = (g.k_len + block_k - 1) / block_k;
     if (kind == 0) {
       p.segs[p.num_segs++] = KSeg{g.a_row_off, g.a_k_off, g.b_k_off, kbs, 0, 0};
+      p.total_kb += kbs;
     } else {  // 3xTF32: small cross terms first, then hi*hi
       p.segs[p.num_segs++] = KSeg{g.a_row_off, g.a_k_off, g.b_k_off, kbs, 1, 0};
       p.segs[p.num_segs++] = KSeg{g.a_row_off, g.a_k_off, g.b_k_off, kbs, 0, 1};
       p.segs[p.num_segs++] = KSeg{g.a_row_off, g.a_k_off, g.b_k_off, kbs, 0, 0};
+      p.total_kb += 3 * kbs;
     }
   }
   p.out = a->out;
@@ -674,7 +789,7 @@ extern "C" int devit_gemm(const devit_gemm_args* a, void* stream_v) {
   p.rowmap_off = a->rowmap_off;
   DEVIT_REQUIRE(!(p.rowbias && p.rowmap_period <= 0),
                 "devit_gemm: rowbias needs rowmap_period > 0");
-  // 16-byte vector path requirements
+  // 16-byte vector requirements of the direct path
   const int out_elem = a->out_kind == DEVIT_OUT_BF16 ? 2 : 4;
   bool vec = (reinterpret_cast<uintptr_t>(a->out) % 16 == 0) && ((a->ldo * out_elem) % 16 == 0);
   if (a->out_kind == DEVIT_OUT_F32_SPLIT) vec = vec && ((a->out_plane_stride * 4) % 16 == 0);
@@ -693,10 +808,9 @@ extern "C" int devit_gemm(const devit_gemm_args* a, void* stream_v) {
   }
   DEVIT_REQUIRE(bn == 128 || bn == 192 || bn == 256, "devit_gemm: block_n %d unsupported", bn);
   // CTA pairs (cta_group::2, 256-row tiles) pay off once there are enough m-blocks
-  const int num_m_blocks = (a->m + kBlockM - 1) / kBlockM;
   int cl = a->cluster_m;
   if (cl == 0) {
-    cl = num_m_blocks >= 4 * num_sms() / 2 ? 2 : 1;
+    cl = 1;
     if (const char* e = getenv("DEVIT_GEMM_CLUSTER")) cl = atoi(e);
   }
   DEVIT_REQUIRE(cl == 1 || cl == 2, "devit_gemm: cluster_m %d unsupported", cl);
@@ -720,16 +834,22 @@ extern "C" int devit_gemm(const devit_gemm_args* a, void* stream_v) {
   }
 
   // ---- coalesced (TMA) epilogue eligibility
-  bool tma_epi = p.rowmap_period <= 0 && !p.rowbias && (a->n % 4 == 0) &&
+  bool tma_epi = p.rowmap_period <= 0 && !p.rowbias &&
                  (reinterpret_cast<uintptr_t>(a->out) % 16 == 0) && ((a->ldo * out_elem) % 16 == 0);
-  if (a->bias) tma_epi = tma_epi && (reinterpret_cast<uintptr_t>(a->bias) % 16 == 0);
   if (a->out_kind == DEVIT_OUT_BF16) tma_epi = tma_epi && !a->resid;
   if (a->out_kind == DEVIT_OUT_F32_SPLIT)
     tma_epi = tma_epi && !a->resid && ((a->out_plane_stride * 4) % 16 == 0);
   if (a->resid)
     tma_epi = tma_epi && (reinterpret_cast<uintptr_t>(a->resid) % 16 == 0) &&
               ((a->ldr * 4) % 16 == 0);
+  if (const char* e = getenv("DEVIT_GEMM_NO_TMA_EPI")) {
+    const int v = atoi(e);  // debug: 1 = never, 2 = not for residual GEMMs
+    if (v == 1 || (v == 2 && a->resid)) tma_epi = false;
+  }
   p.tma_epi = tma_epi ? 1 : 0;
+  p.dbg = 0;
+  p.trace = g_trace;
+  if (const char* e = getenv("DEVIT_GEMM_DBG")) p.dbg = atoi(e);
   CUtensorMap tm[7];
   tm[0] = ta0; tm[1] = ta1; tm[2] = tb0; tm[3] = tb1;
   tm[4] = ta0; tm[5] = ta0; tm[6] = ta0;  // placeholders when the direct epilogue is used

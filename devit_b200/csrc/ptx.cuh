@@ -15,6 +15,7 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 }
 
 __device__ __forceinline__ bool elect_one() {
+  __syncwarp();  // elect must see the whole warp, or two lanes could be "the one"
   uint32_t pred = 0;
   asm volatile(
       "{\n\t.reg .pred P;\n\t"
@@ -50,9 +51,28 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// non-blocking probe (returns immediately; try_wait may suspend the thread for a while)
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
+}
+// Warp-wide wait: every lane polls, then the warp explicitly reconverges, so that the
+// elect / .sync.aligned instructions that follow see all 32 lanes together.
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+  __syncwarp();
 }
 
 // ----------------------------------------------------------------------------- fences

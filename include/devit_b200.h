@@ -135,6 +135,10 @@ typedef struct devit_gemm_args {
 
 int devit_gemm(const devit_gemm_args* args, void* stream);
 
+/* Debug aid: device buffer of 20 x 512 int64 that receives clock64 stamps of the pipeline
+ * roles of GEMM CTA 0 (producer / MMA issuer / epilogue warp 0); NULL switches it off. */
+int devit_debug_set_trace(long long* device_buf);
+
 /* ---------------------------------------------------------------------------------------
  * devit_layernorm: y[r, :] = (x[r, :] - mean) * rstd * gamma + beta, biased variance,
  * one warp per row, fp32 statistics.   Replaces nn.LayerNorm (norm1/norm2)

@@ -90,6 +90,24 @@ def test_gemm_cta_pair(cl, bn):
     assert rel(o32[0] + o32[1], ref32) < 1e-5
 
 
+@pytest.mark.parametrize("bn,cl", [(128, 1), (192, 1), (192, 2), (256, 2), (0, 0)])
+@pytest.mark.parametrize("k", [384, 200, 848])
+def test_gemm_many_tiles_per_cta_residual(bn, cl, k):
+    """Persistent path: several tiles per CTA, so the operand ring wraps many times while the
+    fp32 residual tiles travel through it (in-place x += a w^T + b), plus the bf16 epilogue."""
+    m, n = 128 * 148 * 3 + 77, 384
+    a = _mk((m, k), 31).bfloat16()
+    w = _mk((n, k), 32, 0.05).bfloat16()
+    bias = _mk((n,), 33)
+    res = _mk((m, n), 34)
+    ref = a.float() @ w.float().t() + bias
+    xx = res.clone()
+    L.gemm(a, w, bias=bias, resid=xx, out=xx, out_kind=L.OUT_F32, block_n=bn, cluster_m=cl)
+    assert rel(xx, ref + res) < 2e-5
+    out = L.gemm(a, w, bias=bias, out_kind=L.OUT_BF16, block_n=bn, cluster_m=cl)
+    assert rel(out, ref) < 6e-3
+
+
 def test_gemm_gelu_bf16_output_fast_path():
     """bf16-output epilogue uses the tanh.approx-based erf-GELU fit: the result must stay within
     bf16 rounding of the exact erf form (abs error < 2e-3 + half a bf16 ulp)."""

@@ -17,6 +17,6 @@ w = (torch.randn(n, k, device="cuda", generator=g) * .05).bfloat16()
 b = torch.randn(n, device="cuda", generator=g)
 x = torch.randn(M, D, device="cuda", generator=g)
 out = x if resid else torch.empty(M, n, device="cuda", dtype=torch.bfloat16)
-for _ in range(3):
+for _ in range(int(sys.argv[4]) if len(sys.argv) > 4 else 3):
     L.gemm(a, w, bias=b, resid=x if resid else None, out=out, out_kind=ok, act=act, block_n=bn, cluster_m=cl)
 torch.cuda.synchronize()

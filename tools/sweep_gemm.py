@@ -33,6 +33,7 @@ def timeit(fn, n=10):
 
 mode = sys.argv[1] if len(sys.argv) > 1 else "dense"
 H, F = (6, 1536) if mode == "dense" else (4, 928)
+only = sys.argv[2].split(",") if len(sys.argv) > 2 else None
 shapes = {
     "qkv": dict(k=D, n=192 * H, out=L.OUT_BF16, resid=False, act=L.ACT_NONE),
     "proj": dict(k=64 * H, n=D, out=L.OUT_F32, resid=True, act=L.ACT_NONE),
@@ -41,6 +42,8 @@ shapes = {
 }
 x = rnd(M, D, dt=torch.float32)
 for name, sh in shapes.items():
+    if only and name not in only:
+        continue
     a = rnd(M, sh["k"])
     w = rnd(sh["n"], sh["k"], scale=0.05)
     b = rnd(sh["n"], dt=torch.float32)

@@ -41,9 +41,11 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
 attn_bf16_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                  __nv_bfloat16* __restrict__ out, int tokens, int heads, float scale_log2e) {
   using Cfg = AttnCfg<KVP>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>(
-      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  // Declared 1024-byte aligned (128B-swizzle atoms) and used directly: pointer arithmetic
+  // through uintptr_t would make the compiler lose the shared address space and turn every
+  // LDS/STS of the epilogue into a slower generic LD/ST.
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* sQ = smem;
   uint8_t* sK = smem + Cfg::kOffK;
   uint8_t* sP = smem;  // overlays Q and K once S has been computed
@@ -56,7 +58,8 @@ attn_bf16_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint64_t* bar_o = bars + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
 
-  const int warp = threadIdx.x >> 5;
+  // warp-uniform role id (see gemm.cu: keeps the async instructions free of waterfall loops)
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int mtile = blockIdx.x;
   const int head = blockIdx.y;
@@ -80,43 +83,49 @@ attn_bf16_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp == 4) {
-    if (lane == 0) {
+    {
       // ---- loads
-      mbar_expect_tx(bar_qk, Cfg::kQBytes + Cfg::kKVBytes);
-      tma_load_3d(sQ, &tmQ, bar_qk, head * 64, mtile * 128, img);
-      tma_load_3d(sK, &tmKV, bar_qk, (heads + head) * 64, 0, img);
-      mbar_expect_tx(bar_v, Cfg::kKVBytes);
-      tma_load_3d(sV, &tmKV, bar_v, (2 * heads + head) * 64, 0, img);
+      if (elect_one()) {
+        mbar_expect_tx(bar_qk, Cfg::kQBytes + Cfg::kKVBytes);
+        tma_load_3d(sQ, &tmQ, bar_qk, head * 64, mtile * 128, img);
+        tma_load_3d(sK, &tmKV, bar_qk, (heads + head) * 64, 0, img);
+        mbar_expect_tx(bar_v, Cfg::kKVBytes);
+        tma_load_3d(sV, &tmKV, bar_v, (2 * heads + head) * 64, 0, img);
+      }
       // ---- S = Q K^T   (M=128, N=KVP, K=64: 4 UMMAs of K=16)
-      mbar_wait(bar_qk, 0);
+      mbar_wait_warp(bar_qk, 0);
       tc_fence_after();
       {
         const uint32_t idesc = make_idesc(kFmtBF16, 128, KVP, 0, 0);
         const uint64_t dq = make_sw128_desc(smem_u32(sQ), 1024, 16);
         const uint64_t dk = make_sw128_desc(smem_u32(sK), 1024, 16);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, dq + 2 * k, dk + 2 * k, idesc, k > 0);
-        umma_commit(bar_s);
+          for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, dq + 2 * k, dk + 2 * k, idesc, k > 0);
+          umma_commit(bar_s);
+        }
       }
       // ---- O = P V     (M=128, N=64, K=KVP: KVP/16 UMMAs; V is MN-major, 16 keys = 2 KB)
-      mbar_wait(bar_p, 0);
+      mbar_wait_warp(bar_p, 0);
       tc_fence_after();
-      mbar_wait(bar_v, 0);
+      mbar_wait_warp(bar_v, 0);
       tc_fence_after();
       {
         const uint32_t idesc = make_idesc(kFmtBF16, 128, 64, 0, 1);
         const uint32_t p0 = smem_u32(sP);
         const uint32_t v0 = smem_u32(sV);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < KVP / 16; ++k) {
-          const uint64_t dp = make_sw128_desc(p0 + (k >> 2) * 16384 + (k & 3) * 32, 1024, 16);
-          const uint64_t dv = make_sw128_desc(v0 + k * 2048, 1024, 1024);
-          umma_bf16(tmem_base, dp, dv, idesc, k > 0);
+          for (int k = 0; k < KVP / 16; ++k) {
+            const uint64_t dp = make_sw128_desc(p0 + (k >> 2) * 16384 + (k & 3) * 32, 1024, 16);
+            const uint64_t dv = make_sw128_desc(v0 + k * 2048, 1024, 1024);
+            umma_bf16(tmem_base, dp, dv, idesc, k > 0);
+          }
+          umma_commit(bar_o);
         }
-        umma_commit(bar_o);
       }
     }
   } else {
@@ -128,7 +137,7 @@ attn_bf16_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     constexpr int kFull = KVP / 32;
     constexpr int kTail = KVP % 32;  // 0 or 16
 
-    mbar_wait(bar_s, 0);
+    mbar_wait_warp(bar_s, 0);
     tc_fence_after();
     float inv_sum = 0.f;
     if (warp_live) {
@@ -139,9 +148,14 @@ attn_bf16_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         uint32_t r[32];
         tmem_ld_x32(t_row + c * 32, r);
         tmem_ld_wait();
+        if ((c + 1) * 32 <= tokens) {  // whole chunk valid: no per-element test
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (c * 32 + j < tokens) mx = fmaxf(mx, __uint_as_float(r[j]));
+          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (c * 32 + j < tokens) mx = fmaxf(mx, __uint_as_float(r[j]));
+        }
       }
       if (kTail) {
         uint32_t r[16];
@@ -162,12 +176,21 @@ attn_bf16_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tmem_ld_x32(t_row + c * 32, r);
         tmem_ld_wait();
         float pv[32];
+        if ((c + 1) * 32 <= tokens) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float e = fast_exp2(fmaf(__uint_as_float(r[j]), scale_log2e, -moff));
-          e = (c * 32 + j < tokens) ? e : 0.f;
-          sum += e;
-          pv[j] = e;
+          for (int j = 0; j < 32; ++j) {
+            const float e = fast_exp2(fmaf(__uint_as_float(r[j]), scale_log2e, -moff));
+            sum += e;
+            pv[j] = e;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float e = fast_exp2(fmaf(__uint_as_float(r[j]), scale_log2e, -moff));
+            e = (c * 32 + j < tokens) ? e : 0.f;
+            sum += e;
+            pv[j] = e;
+          }
         }
         uint8_t* atom = prow + (c >> 1) * 16384;
 #pragma unroll
@@ -212,7 +235,7 @@ attn_bf16_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     tc_fence_before();
     mbar_arrive(bar_p);
 
-    mbar_wait(bar_o, 0);
+    mbar_wait_warp(bar_o, 0);
     tc_fence_after();
     if (warp_live) {
       uint32_t r0[32], r1[32];

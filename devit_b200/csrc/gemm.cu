@@ -217,9 +217,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
   constexpr int kBlockK = 128 / kElem;  // elements per k-block (one swizzle atom)
   constexpr int kStages = Cfg::kStages;
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>(
-      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  // Declared 1024-byte aligned (128B-swizzle atoms) and used directly: pointer arithmetic
+  // through uintptr_t would make the compiler lose the shared address space and turn every
+  // LDS/STS of the epilogue into a slower generic LD/ST.
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* epi_smem = smem + kStages * Cfg::kStageBytes;
   float* bias_smem = reinterpret_cast<float*>(epi_smem + Cfg::kEpiBytes);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + Cfg::kEpiBytes + Cfg::kBiasBytes);

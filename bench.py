@@ -28,7 +28,7 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-N_SUB, NUM_CLASS, BATCH = 4, 100, 256
+N_SUB, NUM_CLASS, BATCH = 4, 100, int(os.environ.get("DEVIT_BENCH_BATCH", "256"))
 D, HEADS, HIDDEN, TOKENS, PATCHES, DEPTH = 384, 6, 1536, 198, 196, 12
 METRIC = "images/sec, 4-way DeDeiT ensemble @224^2 bs256"
 

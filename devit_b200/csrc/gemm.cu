@@ -69,21 +69,23 @@ static long long* g_trace = nullptr;
 #define DEVIT_TRACE(slot_, idx_) do { (void)(idx_); } while (0)
 #endif
 
-template <int BN, int CL>
+template <int BN, int CL, bool RES = false>
 struct GemmCfg {
   static constexpr int kStageA = kBlockM * 128;
   static constexpr int kStageB = (BN / CL) * 128;  // a CTA pair splits B's rows half / half
   static constexpr int kStageBytes = kStageA + kStageB;
-  static constexpr int kEpiBytes = kEpiWarps * 4096;      // one [32 x 128 B] buffer per warp
+  // one [32 x 128 B] staging buffer per warp; the residual variant keeps a slot for every
+  // 32x32 fp32 chunk of the tile so the NEXT tile's residual is in flight during this one
+  static constexpr int kEpiBytes = RES ? kBlockM * BN * 4 : kEpiWarps * 4096;
   static constexpr int kBiasBytes = kEpiWarps * BN * 4;   // per-warp copy of the tile's bias
-  static constexpr int kBarBytes = (3 * 8 + 4) * 8 + 16 + 32;
+  static constexpr int kBarBytes = (2 * 8 + 32 + 4) * 8 + 16 + 32;
   static constexpr int kBudget = 227 * 1024 - 1024 - kEpiBytes - kBiasBytes - kBarBytes;
   static constexpr int kStages = kBudget / kStageBytes > 8 ? 8 : kBudget / kStageBytes;
   static constexpr int kAccStride = BN <= 128 ? 128 : 256;
   static constexpr int kTmemCols = 2 * kAccStride;
   static constexpr int kSmemBytes =
       kStages * kStageBytes + kEpiBytes + kBiasBytes + kBarBytes + 1024;
-  static_assert(kStages >= 3, "not enough shared memory for the operand ring");
+  static_assert(kStages >= (RES ? 2 : 3), "not enough shared memory for the operand ring");
 };
 
 // byte offset of 16-byte chunk j of row r inside a [rows x 128 B] 128B-swizzled buffer
@@ -206,13 +208,13 @@ __device__ __forceinline__ void bias_act32(const GemmKParams& p, float* v, const
   }
 }
 
-template <int BN, int KIND, int CL>
+template <int BN, int KIND, int CL, bool RES>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
             const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
             const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1,
             const __grid_constant__ CUtensorMap tmR, const __grid_constant__ GemmKParams p) {
-  using Cfg = GemmCfg<BN, CL>;
+  using Cfg = GemmCfg<BN, CL, RES>;
   constexpr int kElem = KIND == 0 ? 2 : 4;
   constexpr int kBlockK = 128 / kElem;  // elements per k-block (one swizzle atom)
   constexpr int kStages = Cfg::kStages;
@@ -226,8 +228,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
   float* bias_smem = reinterpret_cast<float*>(epi_smem + Cfg::kEpiBytes);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + Cfg::kEpiBytes + Cfg::kBiasBytes);
   uint64_t* empty_bar = full_bar + 8;
-  uint64_t* rfull_bar = empty_bar + 8;  // [4 quarters][2 buffers]: residual chunk has landed
-  uint64_t* tmem_full = rfull_bar + 8;
+  uint64_t* rfull_bar = empty_bar + 8;  // [8 warps][4 slots]: residual chunk has landed
+  uint64_t* tmem_full = rfull_bar + 32;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
@@ -243,7 +245,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
   const int cluster_id = blockIdx.x / CL;
   const int num_clusters = gridDim.x / CL;
   const bool leader = cta_rank == 0;
-  const bool has_res = p.tma_epi && p.resid != nullptr;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);
@@ -256,10 +257,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    for (int s = 0; s < 8; ++s) mbar_init(&rfull_bar[s], 1);
+    for (int s = 0; s < 32; ++s) mbar_init(&rfull_bar[s], 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 32 * kEpiWarps * CL);  // every epilogue thread (of the pair)
+      mbar_init(&tmem_empty[s], kEpiWarps * CL);  // one arrival per epilogue warp (of the pair)
     }
     if (p.tma_epi) {
       tma_prefetch_desc(&tmO0);
@@ -409,9 +410,34 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t rphase_bits = 0;      // parity of this warp's two residual-buffer barriers
-    uint8_t* stg = epi_smem + ew * 4096;
+    uint8_t* stg = epi_smem + ew * 4096;  // (non-residual variants)
     float* bias_s = bias_smem + ew * BN;
     int tr_e = 0;
+    // ---- residual variant: slot bookkeeping (see the RES epilogue below)
+    uint8_t* res_slots = epi_smem + ew * ((BN / 64) * 4096);
+    uint64_t* res_bar = rfull_bar + ew * 4;
+    int cur_cnt = 0, nxt_cnt = 0, nxt_row0 = 0, nxt_n0 = 0;
+    // number of this warp's chunks (= slots used) in tile u, and the tile's coordinates
+    auto res_tile = [&](int u, int* row0_, int* n0_) -> int {
+      *n0_ = (u % num_n) * BN;
+      *row0_ = ((u / num_n) * CL + cta_rank) * kBlockM + quarter * 32;
+      if (*row0_ >= p.M) return 0;
+      const int nv = (p.N - *n0_) < BN ? (p.N - *n0_) : BN;
+      const int nch = (nv + 31) >> 5;
+      return nch > half ? (nch - half + 1) >> 1 : 0;
+    };
+    auto res_issue = [&](int j, int row0_, int n0_) {
+      if (elect_one()) {
+        mbar_expect_tx(&res_bar[j], 4096);
+        tma_load_2d(res_slots + j * 4096, &tmR, &res_bar[j], n0_ + (half + 2 * j) * 32, row0_);
+      }
+    };
+    if constexpr (RES) {
+      if (cluster_id < num_units) {
+        cur_cnt = res_tile(cluster_id, &nxt_row0, &nxt_n0);
+        for (int j = 0; j < cur_cnt; ++j) res_issue(j, nxt_row0, nxt_n0);
+      }
+    }
     for (int unit = cluster_id; unit < num_units; unit += num_clusters) {
       const int m0 = ((unit / num_n) * CL + cta_rank) * kBlockM;
       const int n0 = (unit % num_n) * BN;
@@ -429,13 +455,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
             bias_s[i * 32 + lane] = col < p.N ? __ldg(p.bias + col) : 0.f;
           }
         }
-        if (has_res && ew < 4 && live) {
-          // residual chunk 0 can fly while the MMAs of this tile are still running
-          if (elect_one()) {
-            bulk_wait_read<0>();
-            mbar_expect_tx(&rfull_bar[quarter * 2], 4096);
-            tma_load_2d(stg, &tmR, &rfull_bar[quarter * 2], n0, row0);
-          }
+        if constexpr (RES) {
+          // residual chunks of the NEXT tile whose slots this tile does not use can fly now
+          nxt_cnt = 0;
+          if (unit + num_clusters < num_units)
+            nxt_cnt = res_tile(unit + num_clusters, &nxt_row0, &nxt_n0);
+          for (int j = cur_cnt; j < nxt_cnt; ++j) res_issue(j, nxt_row0, nxt_n0);
         }
         if (ew == 0 && lane == 0) DEVIT_TRACE(9, tr_e);
         mbar_wait_warp(&tmem_full[acc], acc_phase);
@@ -495,55 +520,59 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
           // ---- fp32 output, 32 columns (128 B per row) per chunk
           const bool split = p.out_kind == DEVIT_OUT_F32_SPLIT;
           const int nchunk = (n_valid + 31) >> 5;
-          if (has_res) {
-            // + fp32 residual (x += ...): warps 0..3 of the epilogue (one per lane quarter)
-            // stream the residual tile through two private buffers -- their own and the idle
-            // partner warp's -- with a one-chunk TMA prefetch; the sum is written back into the
-            // buffer and TMA-stored from there.
-            if (ew < 4 && live) {
-              uint8_t* bufs[2] = {stg, stg + 4 * 4096};
-              uint64_t* rbar = rfull_bar + quarter * 2;
-              int buf = 0;
+          if constexpr (RES) {
+            // + fp32 residual (x += ...).  Warp (quarter, half) owns chunks c = half + 2j of its
+            // 32 rows; slot j holds the residual of chunk c, TMA-prefetched one whole tile ahead.
+            // The sum is written back into the slot and TMA-stored from there; as soon as that
+            // store has read the slot, the same chunk of the next tile is requested into it.
 #pragma unroll 1
-              for (int c = 0; c < nchunk; ++c) {
-                uint32_t r[32];
-                tmem_ld_x32(t_row + c * 32, r);
-                tmem_ld_wait();
-                if (elect_one()) {
-                  bulk_wait_read<0>();  // the store that used the other buffer has drained
-                  if (c + 1 < nchunk) {
-                    mbar_expect_tx(&rbar[buf ^ 1], 4096);
-                    tma_load_2d(bufs[buf ^ 1], &tmR, &rbar[buf ^ 1], n0 + (c + 1) * 32, row0);
+            for (int j = 0; j < cur_cnt; ++j) {
+              const int c = half + 2 * j;
+              uint32_t r[32];
+              tmem_ld_x32(t_row + c * 32, r);
+              tmem_ld_wait();
+              float* v = reinterpret_cast<float*>(r);
+              bias_act32(p, v, bias_s + c * 32);
+              mbar_wait_warp(&res_bar[j], (rphase_bits >> j) & 1u);
+              rphase_bits ^= 1u << j;
+              uint8_t* b = res_slots + j * 4096;
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                const float4 t = *reinterpret_cast<const float4*>(b + stg_off(lane, g));
+                v[4 * g] += t.x; v[4 * g + 1] += t.y; v[4 * g + 2] += t.z; v[4 * g + 3] += t.w;
+              }
+              if (p.alpha != 1.0f) {
+#pragma unroll
+                for (int k = 0; k < 32; ++k) v[k] *= p.alpha;
+              }
+#pragma unroll
+              for (int g = 0; g < 8; ++g)
+                *reinterpret_cast<float4*>(b + stg_off(lane, g)) =
+                    make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+              fence_proxy_async_smem();
+              if (elect_one()) {
+                tma_store_2d(&tmO0, b, n0 + c * 32, row0);
+                bulk_commit();
+                if (j > 0) {
+                  bulk_wait_read<1>();  // the previous chunk's store has drained its slot
+                  if (j - 1 < nxt_cnt) {
+                    mbar_expect_tx(&res_bar[j - 1], 4096);
+                    tma_load_2d(b - 4096, &tmR, &res_bar[j - 1], nxt_n0 + (c - 2) * 32, nxt_row0);
                   }
                 }
-                float* v = reinterpret_cast<float*>(r);
-                bias_act32(p, v, bias_s + c * 32);
-                mbar_wait_warp(&rbar[buf], (rphase_bits >> buf) & 1u);
-                rphase_bits ^= 1u << buf;
-                uint8_t* b = bufs[buf];
-#pragma unroll
-                for (int g = 0; g < 8; ++g) {
-                  const float4 t = *reinterpret_cast<const float4*>(b + stg_off(lane, g));
-                  v[4 * g] += t.x; v[4 * g + 1] += t.y; v[4 * g + 2] += t.z; v[4 * g + 3] += t.w;
-                }
-                if (p.alpha != 1.0f) {
-#pragma unroll
-                  for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
-                }
-#pragma unroll
-                for (int g = 0; g < 8; ++g)
-                  *reinterpret_cast<float4*>(b + stg_off(lane, g)) =
-                      make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (elect_one()) {
-                  tma_store_2d(&tmO0, b, n0 + c * 32, row0);
-                  bulk_commit();
-                }
-                buf ^= 1;
               }
-              if (elect_one()) bulk_wait_read<0>();  // partner's buffer is free again
+              __syncwarp();
             }
+            if (cur_cnt > 0 && elect_one()) {
+              bulk_wait_read<0>();
+              if (cur_cnt - 1 < nxt_cnt) {
+                const int j = cur_cnt - 1;
+                mbar_expect_tx(&res_bar[j], 4096);
+                tma_load_2d(res_slots + j * 4096, &tmR, &res_bar[j], nxt_n0 + (half + 2 * j) * 32,
+                            nxt_row0);
+              }
+            }
+            cur_cnt = nxt_cnt;
           } else if (live) {
 #pragma unroll 1
             for (int c = half; c < nchunk; c += 2) {
@@ -636,10 +665,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
         DEVIT_TRACE(11, tr_e);
         ++tr_e;
       }
-      __syncwarp();
+      // every lane's TMEM reads are complete (tcgen05.wait::ld) and ordered before the warp
+      // barrier; one lane then releases the accumulator (a remote arrive per THREAD made the
+      // pair's hand-off the bottleneck: 256 serialized cluster transactions per tile)
       tc_fence_before();
-      if (CL == 1 || leader) mbar_arrive(&tmem_empty[acc]);
-      else mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));
+      __syncwarp();
+      if (lane == 0) {
+        if (CL == 1 || leader) mbar_arrive(&tmem_empty[acc]);
+        else mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));
+      }
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
@@ -658,15 +692,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
   }
 }
 
-template <int BN, int KIND, int CL>
+template <int BN, int KIND, int CL, bool RES = false>
 static int launch_gemm(const CUtensorMap* tm, const GemmKParams& p, cudaStream_t stream,
                        int tag) {
-  using Cfg = GemmCfg<BN, CL>;
+  using Cfg = GemmCfg<BN, CL, RES>;
   static bool attr_done[64] = {};  // per device; benign race: the attribute set is idempotent
   int dev = 0;
   DEVIT_CUDA_OK(cudaGetDevice(&dev));
   if (!attr_done[dev & 63]) {
-    DEVIT_CUDA_OK(cudaFuncSetAttribute(gemm_kernel<BN, KIND, CL>,
+    DEVIT_CUDA_OK(cudaFuncSetAttribute(gemm_kernel<BN, KIND, CL, RES>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg::kSmemBytes));
     attr_done[dev & 63] = true;
@@ -690,7 +724,7 @@ static int launch_gemm(const CUtensorMap* tm, const GemmKParams& p, cudaStream_t
   cfg.numAttrs = CL > 1 ? 1 : 0;
   {
     ProfScope ps(tag, stream);
-    DEVIT_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, KIND, CL>, tm[0], tm[1], tm[2], tm[3],
+    DEVIT_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, KIND, CL, RES>, tm[0], tm[1], tm[2], tm[3],
                                      tm[4], tm[5], tm[6], p));
   }
   DEVIT_CUDA_OK(cudaGetLastError());
@@ -698,21 +732,24 @@ static int launch_gemm(const CUtensorMap* tm, const GemmKParams& p, cudaStream_t
   return DEVIT_OK;
 }
 
-template <int BN, int KIND>
+template <int BN, int KIND, bool RES = false>
 static int launch_gemm_cl(int cl, const CUtensorMap* tm, const GemmKParams& p,
                           cudaStream_t stream, int tag) {
-  if (cl == 2) return launch_gemm<BN, KIND, 2>(tm, p, stream, tag);
-  return launch_gemm<BN, KIND, 1>(tm, p, stream, tag);
+  if (cl == 2) return launch_gemm<BN, KIND, 2, RES>(tm, p, stream, tag);
+  return launch_gemm<BN, KIND, 1, RES>(tm, p, stream, tag);
 }
 
-static int pick_block_n(int n) {
-  int best = 128, best_waste = 1 << 30;
-  const int cands[3] = {192, 256, 128};
+// The large-M GEMMs of this model are bound by the bytes each SM pulls through L2 per tile:
+// 128 rows of A plus BN / cl rows of B per k-block.  Pick the tile width that minimises that
+// (ragged last tiles are cheap: TMA clips them and the UMMA is issued narrower).
+static int pick_block_n(int n, int cl) {
+  int best = 128, best_cost = 1 << 30;
+  const int cands[3] = {256, 192, 128};
   for (int i = 0; i < 3; ++i) {
     const int bn = cands[i];
-    const int waste = ((n + bn - 1) / bn) * bn - n;
-    if (waste < best_waste) {
-      best_waste = waste;
+    const int cost = ((n + bn - 1) / bn) * (kBlockM + bn / cl);
+    if (cost < best_cost) {
+      best_cost = cost;
       best = bn;
     }
   }
@@ -804,19 +841,41 @@ extern "C" int devit_gemm(const devit_gemm_args* a, void* stream_v) {
   p.vec_ok = vec ? 1 : 0;
 
   const int tag = (a->profile_tag >= 0 && a->profile_tag < 8) ? a->profile_tag : 0;
-  int bn = a->block_n ? a->block_n : pick_block_n(a->n);
+  // CTA pairs (cta_group::2, 256-row tiles) pay off once there are enough m-blocks
+  // CTA pairs halve the weight-tile bytes each SM pulls through L2 (the binding resource at
+  // K = 384); measured on B200 they win for every large-M shape except the short-K residual
+  // GEMM (proj), see profiles/r1_gemm_sweep_v6.txt
+  int cl = a->cluster_m;
+  const int total_k = [&] { int t = 0; for (int s = 0; s < a->num_segs; ++s) t += a->segs[s].k_len; return t; }();
+  if (cl == 0) {
+    cl = (a->m >= 64 * kBlockM) ? 2 : 1;
+    if (a->resid && total_k < 512) cl = 1;
+    if (const char* e = getenv("DEVIT_GEMM_CLUSTER")) cl = atoi(e);
+  }
+  DEVIT_REQUIRE(cl == 1 || cl == 2, "devit_gemm: cluster_m %d unsupported", cl);
+  int bn = a->block_n ? a->block_n : pick_block_n(a->n, cl);
   if (!a->block_n) {
     if (const char* e = getenv("DEVIT_GEMM_BN")) bn = atoi(e);
   }
   DEVIT_REQUIRE(bn == 128 || bn == 192 || bn == 256, "devit_gemm: block_n %d unsupported", bn);
-  // CTA pairs (cta_group::2, 256-row tiles) pay off once there are enough m-blocks
-  int cl = a->cluster_m;
-  if (cl == 0) {
-    cl = 1;
-    if (const char* e = getenv("DEVIT_GEMM_CLUSTER")) cl = atoi(e);
-  }
-  DEVIT_REQUIRE(cl == 1 || cl == 2, "devit_gemm: cluster_m %d unsupported", cl);
 
+  // ---- coalesced (TMA) epilogue eligibility
+  bool tma_epi = p.rowmap_period <= 0 && !p.rowbias &&
+                 (reinterpret_cast<uintptr_t>(a->out) % 16 == 0) && ((a->ldo * out_elem) % 16 == 0);
+  if (a->out_kind == DEVIT_OUT_BF16) tma_epi = tma_epi && !a->resid;
+  if (a->out_kind == DEVIT_OUT_F32_SPLIT)
+    tma_epi = tma_epi && !a->resid && ((a->out_plane_stride * 4) % 16 == 0);
+  if (a->resid)
+    tma_epi = tma_epi && (reinterpret_cast<uintptr_t>(a->resid) % 16 == 0) &&
+              ((a->ldr * 4) % 16 == 0);
+  if (const char* e = getenv("DEVIT_GEMM_NO_TMA_EPI")) {
+    const int v = atoi(e);  // debug: 1 = never, 2 = not for residual GEMMs
+    if (v == 1 || (v == 2 && a->resid)) tma_epi = false;
+  }
+  if (tma_epi && a->resid) {  // residual variant: BN <= 192
+    if (!a->block_n && cl == 2 && a->n % 128 == 0) bn = 128;
+    if (bn == 256) bn = 192;
+  }
   CUtensorMap ta0, ta1, tb0, tb1;
   rc = encode_tmap_2d(&ta0, a->a, elem, a->a_cols, a->a_rows, a->lda, block_k, kBlockM, false);
   if (rc) return rc;
@@ -835,19 +894,6 @@ extern "C" int devit_gemm(const devit_gemm_args* a, void* stream_v) {
     if (rc) return rc;
   }
 
-  // ---- coalesced (TMA) epilogue eligibility
-  bool tma_epi = p.rowmap_period <= 0 && !p.rowbias &&
-                 (reinterpret_cast<uintptr_t>(a->out) % 16 == 0) && ((a->ldo * out_elem) % 16 == 0);
-  if (a->out_kind == DEVIT_OUT_BF16) tma_epi = tma_epi && !a->resid;
-  if (a->out_kind == DEVIT_OUT_F32_SPLIT)
-    tma_epi = tma_epi && !a->resid && ((a->out_plane_stride * 4) % 16 == 0);
-  if (a->resid)
-    tma_epi = tma_epi && (reinterpret_cast<uintptr_t>(a->resid) % 16 == 0) &&
-              ((a->ldr * 4) % 16 == 0);
-  if (const char* e = getenv("DEVIT_GEMM_NO_TMA_EPI")) {
-    const int v = atoi(e);  // debug: 1 = never, 2 = not for residual GEMMs
-    if (v == 1 || (v == 2 && a->resid)) tma_epi = false;
-  }
   p.tma_epi = tma_epi ? 1 : 0;
   p.dbg = 0;
   p.trace = g_trace;
@@ -872,6 +918,15 @@ extern "C" int devit_gemm(const devit_gemm_args* a, void* stream_v) {
     }
   }
 
+  if (tma_epi && a->resid) {
+    // residual variant: whole-tile residual slots in shared memory (BN <= 192, single CTA)
+    if (kind == 0) {
+      if (bn == 128) return launch_gemm_cl<128, 0, true>(cl, tm, p, stream, tag);
+      return launch_gemm_cl<192, 0, true>(cl, tm, p, stream, tag);
+    }
+    if (bn == 128) return launch_gemm_cl<128, 1, true>(cl, tm, p, stream, tag);
+    return launch_gemm_cl<192, 1, true>(cl, tm, p, stream, tag);
+  }
   if (kind == 0) {
     if (bn == 128) return launch_gemm_cl<128, 0>(cl, tm, p, stream, tag);
     if (bn == 192) return launch_gemm_cl<192, 0>(cl, tm, p, stream, tag);

@@ -127,8 +127,10 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t rank) 
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t mbar_cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(
-                   mbar_cluster_addr)
+  // default .release.cta semantics (as CUTLASS' ClusterBarrier::arrive): the accumulator
+  // hand-off is ordered by the tcgen05 fences, and a cluster-scope release costs a full
+  // memory fence per arrival
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(mbar_cluster_addr)
                : "memory");
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
@@ -136,7 +138,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
   while (!ok) {
     asm volatile(
         "{\n\t.reg .pred P;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, P;\n\t}\n"
         : "=r"(ok)
         : "r"(smem_u32(bar)), "r"(parity)

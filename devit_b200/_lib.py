@@ -16,6 +16,7 @@ import torch
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "lib" / "libdevit_b200.so"
 
+ABI_VERSION = 2
 DEVIT_BF16, DEVIT_FP32 = 0, 1
 OUT_BF16, OUT_F32, OUT_F32_SPLIT = 0, 1, 2
 ACT_NONE, ACT_GELU_ERF = 0, 1
@@ -45,6 +46,10 @@ class GemmArgs(C.Structure):
         ("act", C.c_int32), ("alpha", C.c_float),
         ("rowmap_period", C.c_int32), ("rowmap_stride", C.c_int32), ("rowmap_off", C.c_int32),
         ("block_n", C.c_int32), ("profile_tag", C.c_int32), ("cluster_m", C.c_int32),
+        # LayerNorm folding (see include/devit_b200.h)
+        ("ln_stats", C.c_void_p), ("ln_parts", C.c_int32), ("ln_dim", C.c_int32),
+        ("ln_eps", C.c_float), ("ln_colsum", C.c_void_p),
+        ("out_bf16", C.c_void_p), ("ld_out_bf16", C.c_int64), ("stats_out", C.c_void_p),
     ]
 
 
@@ -57,6 +62,7 @@ class LayerDesc(C.Structure):
         ("ln2_g", C.c_void_p), ("ln2_b", C.c_void_p),
         ("w_fc1", C.c_void_p), ("b_fc1", C.c_void_p),
         ("w_fc2", C.c_void_p), ("b_fc2", C.c_void_p),
+        ("cs_qkv", C.c_void_p), ("cs_fc1", C.c_void_p),
     ]
 
 
@@ -85,6 +91,8 @@ _SIGS = {
     "devit_debug_set_trace": (C.c_int, [C.c_void_p]),
     "devit_layernorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                   C.c_int32, C.c_float, C.c_int32, C.c_int64, C.c_void_p]),
+    "devit_rowstats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
+                                 C.c_void_p]),
     "devit_attention": (C.c_int, [C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                   C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p]),
     "devit_im2col_patch16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
@@ -118,7 +126,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.devit_abi_version() != 1:
+    if lib.devit_abi_version() != ABI_VERSION:
         raise DevitError("libdevit_b200.so ABI version mismatch")
     _lib = lib
     return lib
@@ -173,7 +181,8 @@ def operand_to_f32(t: torch.Tensor, precision: int) -> torch.Tensor:
 
 def gemm(a, b, *, precision=DEVIT_BF16, m=None, n=None, segs=None, out=None,
          out_kind=OUT_BF16, bias=None, resid=None, rowbias=None, act=ACT_NONE, alpha=1.0,
-         rowmap=(0, 0, 0), block_n=0, out_rows=None, tag=0, cluster_m=0):
+         rowmap=(0, 0, 0), block_n=0, out_rows=None, tag=0, cluster_m=0,
+         ln_stats=None, ln_colsum=None, ln_dim=0, ln_eps=0.0, out_bf16=None, stats_out=None):
     """out = epilogue(sum_s A_s B_s^T); see include/devit_b200.h (devit_gemm)."""
     lib = load()
     planes = 1 if precision == DEVIT_BF16 else 2
@@ -215,6 +224,12 @@ def gemm(a, b, *, precision=DEVIT_BF16, m=None, n=None, segs=None, out=None,
     g.block_n = block_n
     g.profile_tag = tag
     g.cluster_m = cluster_m
+    if ln_stats is not None:  # [parts, m, 2] partial (sum, sum^2) per row
+        g.ln_stats, g.ln_parts = ptr(ln_stats), ln_stats.shape[0]
+        g.ln_dim, g.ln_eps, g.ln_colsum = ln_dim, ln_eps, ptr(ln_colsum)
+    if out_bf16 is not None:
+        g.out_bf16, g.ld_out_bf16 = ptr(out_bf16), out_bf16.stride(0)
+    g.stats_out = ptr(stats_out)
     check(lib.devit_gemm(C.byref(g), stream_ptr()))
     return out
 
@@ -234,6 +249,15 @@ def profile_collect() -> dict:
     cnt = (C.c_longlong * 16)()
     check(load().devit_profile_collect(ms, cnt))
     return {TAGS[i]: (ms[i], cnt[i]) for i in range(len(TAGS)) if cnt[i]}
+
+
+def rowstats(x):
+    """bf16 copy + per-row (sum, sum of squares) of an fp32 matrix -> (xb, stats[1, rows, 2])."""
+    rows, dim = x.shape
+    xb = torch.empty(rows, dim, device=x.device, dtype=torch.bfloat16)
+    stats = torch.empty(1, rows, 2, device=x.device, dtype=torch.float32)
+    check(load().devit_rowstats(ptr(x), ptr(xb), ptr(stats), rows, dim, stream_ptr()))
+    return xb, stats
 
 
 def layernorm(x, gamma, beta, eps, out_kind=OUT_BF16):

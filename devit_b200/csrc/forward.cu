@@ -16,7 +16,8 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 struct VitLayout {
   int tokens, grid, max_heads, max_hidden_ld, planes, esz;
   long long M;
-  size_t off_x, off_y, off_qkv, off_o, off_hid, total;
+  size_t off_x, off_y, off_qkv, off_o, off_hid, off_stats, total;
+  int stat_parts;  // partial row sums written by a LayerNorm-folding producer GEMM
 };
 
 static int plan_layout(const devit_vit_desc* d, int batch, VitLayout* L) {
@@ -61,6 +62,9 @@ static int plan_layout(const devit_vit_desc* d, int batch, VitLayout* L) {
   off = align_up(off + static_cast<size_t>(L->M) * L->max_heads * 64 * pe, 256);
   L->off_hid = off;
   off = align_up(off + static_cast<size_t>(L->M) * L->max_hidden_ld * pe, 256);
+  L->off_stats = off;
+  L->stat_parts = 2 * ((d->dim + 127) / 128);
+  off = align_up(off + static_cast<size_t>(L->M) * L->stat_parts * 2 * sizeof(float), 256);
   L->total = off;
   return DEVIT_OK;
 }
@@ -149,12 +153,26 @@ extern "C" int devit_vit_forward(const devit_vit_desc* d, const float* images, i
   if ((rc = sync_debug("prefix", -1, stream))) return rc;
 
   const int nl = (num_layers_run < 0 || num_layers_run > d->depth) ? d->depth : num_layers_run;
+  // LayerNorm folding (bf16 mode, host packed gamma-folded weights): no LayerNorm kernel and no
+  // normalised tensor at all.  `y` holds the bf16 copy of the residual stream, written by the
+  // epilogue of whichever GEMM last updated x together with the rows' partial (sum, sum^2); the
+  // QKV / fc1 GEMMs consume both and apply mean / rstd in their epilogue.
+  bool fold = prec == DEVIT_BF16 && D % 128 == 0 && L.stat_parts <= 6;
+  for (int l = 0; l < d->depth; ++l) fold = fold && d->layers[l].cs_qkv && d->layers[l].cs_fc1;
+  float* stats = reinterpret_cast<float*>(ws + L.off_stats);
+  int parts = 1;
+  if (fold && nl > 0) {
+    rc = devit_rowstats(x, y, stats, M, D, stream);
+    if (rc) return rc;
+  }
   for (int l = 0; l < nl; ++l) {
     const devit_layer_desc& w = d->layers[l];
     const int hd = w.heads * 64;
     // x -> LN1 -> y                                              (models/de_vit.py:113)
-    rc = devit_layernorm(x, w.ln1_g, w.ln1_b, y, M, D, d->ln_eps, opk, M * D, stream);
-    if (rc) return rc;
+    if (!fold) {
+      rc = devit_layernorm(x, w.ln1_g, w.ln1_b, y, M, D, d->ln_eps, opk, M * D, stream);
+      if (rc) return rc;
+    }
     // qkv = y Wqkv^T + b                                         (:67)
     base_gemm(&g, prec);
     g.m = static_cast<int>(M); g.n = 3 * hd;
@@ -165,6 +183,10 @@ extern "C" int devit_vit_forward(const devit_vit_desc* d, const float* images, i
     g.out = qkv; g.ldo = 3 * hd; g.out_kind = opk; g.out_plane_stride = M * 3 * hd;
     if ((rc = sync_debug("ln1", l, stream))) return rc;
     g.bias = w.b_qkv;
+    if (fold) {
+      g.ln_stats = stats; g.ln_parts = parts; g.ln_dim = D; g.ln_eps = d->ln_eps;
+      g.ln_colsum = w.cs_qkv;
+    }
     g.profile_tag = DEVIT_TAG_GEMM_QKV;
     rc = devit_gemm(&g, stream);
     if (rc) return rc;
@@ -183,13 +205,19 @@ extern "C" int devit_vit_forward(const devit_vit_desc* d, const float* images, i
     g.segs[0] = devit_gemm_seg{0, 0, 0, hd};
     g.out = x; g.ldo = D; g.out_kind = DEVIT_OUT_F32;
     g.bias = w.b_proj; g.resid = x; g.ldr = D;
+    if (fold) {
+      g.out_bf16 = y; g.ld_out_bf16 = D; g.stats_out = stats;
+      parts = L.stat_parts;
+    }
     g.profile_tag = DEVIT_TAG_GEMM_PROJ;
     rc = devit_gemm(&g, stream);
     if (rc) return rc;
     if ((rc = sync_debug("proj gemm", l, stream))) return rc;
     // x -> LN2 -> y                                              (:115)
-    rc = devit_layernorm(x, w.ln2_g, w.ln2_b, y, M, D, d->ln_eps, opk, M * D, stream);
-    if (rc) return rc;
+    if (!fold) {
+      rc = devit_layernorm(x, w.ln2_g, w.ln2_b, y, M, D, d->ln_eps, opk, M * D, stream);
+      if (rc) return rc;
+    }
     // hid = gelu(y W1^T + b1), kept neurons only                 (:36-37)
     const int F = w.hidden_ld;
     base_gemm(&g, prec);
@@ -201,6 +229,10 @@ extern "C" int devit_vit_forward(const devit_vit_desc* d, const float* images, i
     g.out = hid; g.ldo = F; g.out_kind = opk; g.out_plane_stride = M * F;
     if ((rc = sync_debug("ln2", l, stream))) return rc;
     g.bias = w.b_fc1; g.act = DEVIT_ACT_GELU_ERF;
+    if (fold) {
+      g.ln_stats = stats; g.ln_parts = parts; g.ln_dim = D; g.ln_eps = d->ln_eps;
+      g.ln_colsum = w.cs_fc1;
+    }
     g.profile_tag = DEVIT_TAG_GEMM_FC1;
     rc = devit_gemm(&g, stream);
     if (rc) return rc;
@@ -214,6 +246,9 @@ extern "C" int devit_vit_forward(const devit_vit_desc* d, const float* images, i
     g.segs[0] = devit_gemm_seg{0, 0, 0, F};
     g.out = x; g.ldo = D; g.out_kind = DEVIT_OUT_F32;
     g.bias = w.b_fc2; g.resid = x; g.ldr = D;
+    if (fold && l + 1 < nl) {  // the next layer's norm1 input (the final norm reads x itself)
+      g.out_bf16 = y; g.ld_out_bf16 = D; g.stats_out = stats;
+    }
     g.profile_tag = DEVIT_TAG_GEMM_FC2;
     rc = devit_gemm(&g, stream);
     if (rc) return rc;

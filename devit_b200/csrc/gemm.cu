@@ -27,6 +27,7 @@ namespace devit {
 constexpr int kBlockM = 128;
 constexpr int kEpiWarps = 8;
 constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
+constexpr int kMaxLnParts = 6;  // partial row sums a LayerNorm-folded GEMM can combine
 constexpr int kMaxKSegs = 24;  // 8 logical segments x 3 passes in the 3xTF32 mode
 
 struct KSeg {
@@ -51,6 +52,13 @@ struct GemmKParams {
   int act;
   float alpha;
   int rowmap_period, rowmap_stride, rowmap_off;
+  // LayerNorm folding (see devit_gemm_args)
+  const float* ln_stats;   // consumer: [ln_parts][M][2]
+  int ln_parts;
+  float ln_inv_dim, ln_eps;
+  const float* ln_colsum;  // consumer: c1[n]
+  float* stats_out;        // producer: [2 * N / 128][M][2]
+  int xb_out;              // producer: 1 = also TMA-store the bf16 copy (tensor map tmO1)
   int vec_ok;
   int tma_epi;  // 1: coalesced epilogue (smem staging + TMA store, residual via R-slots)
   int dbg;      // DEVIT_GEMM_DBG bit0: no epilogue work, bit1: no TMA loads, bit2: no MMAs
@@ -76,8 +84,10 @@ struct GemmCfg {
   static constexpr int kStageBytes = kStageA + kStageB;
   // one [32 x 128 B] staging buffer per warp; the residual variant keeps a slot for every
   // 32x32 fp32 chunk of the tile so the NEXT tile's residual is in flight during this one
-  static constexpr int kEpiBytes = RES ? kBlockM * BN * 4 : kEpiWarps * 4096;
-  static constexpr int kBiasBytes = kEpiWarps * BN * 4;   // per-warp copy of the tile's bias
+  // (+ one bf16 staging buffer per warp for the optional bf16 copy of the output)
+  static constexpr int kEpiBytes = RES ? kBlockM * BN * 4 + kEpiWarps * 4096 : kEpiWarps * 4096;
+  // per-warp copies of the tile's bias and (LayerNorm folding) column sums
+  static constexpr int kBiasBytes = 2 * kEpiWarps * BN * 4;
   static constexpr int kBarBytes = (2 * 8 + 32 + 4) * 8 + 16 + 32;
   static constexpr int kBudget = 227 * 1024 - 1024 - kEpiBytes - kBiasBytes - kBarBytes;
   static constexpr int kStages = kBudget / kStageBytes > 8 ? 8 : kBudget / kStageBytes;
@@ -205,6 +215,24 @@ __device__ __forceinline__ void bias_act32(const GemmKParams& p, float* v, const
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
     }
+  }
+}
+
+// LayerNorm folding: v = rstd * acc + ((-rstd * mean) * c1 + c2), then the activation
+__device__ __forceinline__ void ln_bias_act32(const GemmKParams& p, float* v, const float* cs,
+                                              const float* bias_s, float rstd, float nmr) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 c = *reinterpret_cast<const float4*>(cs + 4 * j);      // warp broadcast
+    const float4 b = *reinterpret_cast<const float4*>(bias_s + 4 * j);  // (zeros if no bias)
+    v[4 * j] = fmaf(rstd, v[4 * j], fmaf(nmr, c.x, b.x));
+    v[4 * j + 1] = fmaf(rstd, v[4 * j + 1], fmaf(nmr, c.y, b.y));
+    v[4 * j + 2] = fmaf(rstd, v[4 * j + 2], fmaf(nmr, c.z, b.z));
+    v[4 * j + 3] = fmaf(rstd, v[4 * j + 3], fmaf(nmr, c.w, b.w));
+  }
+  if (p.act == DEVIT_ACT_GELU_ERF) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(v[j]);
   }
 }
 
@@ -412,9 +440,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
     uint32_t rphase_bits = 0;      // parity of this warp's two residual-buffer barriers
     uint8_t* stg = epi_smem + ew * 4096;  // (non-residual variants)
     float* bias_s = bias_smem + ew * BN;
+    float* cs_s = bias_smem + (kEpiWarps + ew) * BN;  // LayerNorm-folding column sums c1
     int tr_e = 0;
     // ---- residual variant: slot bookkeeping (see the RES epilogue below)
-    uint8_t* res_slots = epi_smem + ew * ((BN / 64) * 4096);
+    constexpr int kResSlots = BN / 64;  // this warp's chunks: c = half * kResSlots + j
+    uint8_t* res_slots = epi_smem + ew * (kResSlots * 4096);
+    uint8_t* xb_stg = epi_smem + kBlockM * BN * 4 + ew * 4096;  // bf16 copy staging (RES)
     uint64_t* res_bar = rfull_bar + ew * 4;
     int cur_cnt = 0, nxt_cnt = 0, nxt_row0 = 0, nxt_n0 = 0;
     // number of this warp's chunks (= slots used) in tile u, and the tile's coordinates
@@ -424,14 +455,44 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
       if (*row0_ >= p.M) return 0;
       const int nv = (p.N - *n0_) < BN ? (p.N - *n0_) : BN;
       const int nch = (nv + 31) >> 5;
-      return nch > half ? (nch - half + 1) >> 1 : 0;
+      const int mine = nch - half * kResSlots;
+      return mine < 0 ? 0 : (mine > kResSlots ? kResSlots : mine);
     };
     auto res_issue = [&](int j, int row0_, int n0_) {
       if (elect_one()) {
         mbar_expect_tx(&res_bar[j], 4096);
-        tma_load_2d(res_slots + j * 4096, &tmR, &res_bar[j], n0_ + (half + 2 * j) * 32, row0_);
+        tma_load_2d(res_slots + j * 4096, &tmR, &res_bar[j], n0_ + (half * kResSlots + j) * 32,
+                    row0_);
       }
     };
+    // ---- per-tile epilogue constants, requested one tile ahead into registers
+    float pf_bias[BN / 32], pf_cs[BN / 32];
+    float2 pf_st[kMaxLnParts];
+    auto epi_prefetch = [&](int u) {
+      const int n0_ = (u % num_n) * BN;
+      if (p.bias) {
+#pragma unroll
+        for (int i = 0; i < BN / 32; ++i) {
+          const int col = n0_ + i * 32 + lane;
+          pf_bias[i] = col < p.N ? __ldg(p.bias + col) : 0.f;
+        }
+      }
+      if (!RES && p.ln_stats) {
+#pragma unroll
+        for (int i = 0; i < BN / 32; ++i) {
+          const int col = n0_ + i * 32 + lane;
+          pf_cs[i] = col < p.N ? __ldg(p.ln_colsum + col) : 0.f;
+        }
+        const int m = ((u / num_n) * CL + cta_rank) * kBlockM + quarter * 32 + lane;
+#pragma unroll
+        for (int q = 0; q < kMaxLnParts; ++q)
+          pf_st[q] = (q < p.ln_parts && m < p.M)
+                         ? __ldg(reinterpret_cast<const float2*>(p.ln_stats) +
+                                 static_cast<long long>(q) * p.M + m)
+                         : make_float2(0.f, 0.f);
+      }
+    };
+    if (p.tma_epi && cluster_id < num_units) epi_prefetch(cluster_id);
     if constexpr (RES) {
       if (cluster_id < num_units) {
         cur_cnt = res_tile(cluster_id, &nxt_row0, &nxt_n0);
@@ -447,14 +508,30 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
       const int n_valid = (p.N - n0) < BN ? (p.N - n0) : BN;
       const bool live = row0 < p.M;  // warp-uniform
       if (p.tma_epi) {
-        // the tile's bias -> this warp's shared-memory copy (overlaps the wait for the MMAs)
+        // The tile's bias (and, LayerNorm folding, column sums + this lane's row statistics)
+        // were requested one tile ago (pf_* registers): store them to this warp's shared-memory
+        // copies, then request the next tile's so their latency never sits in front of the
+        // accumulator read.
+        float ln_rstd = 1.f, ln_nmr = 0.f;  // v = rstd * acc + (-rstd * mean) * c1 + c2
         if (p.bias) {
 #pragma unroll
-          for (int i = 0; i < BN / 32; ++i) {
-            const int col = n0 + i * 32 + lane;
-            bias_s[i * 32 + lane] = col < p.N ? __ldg(p.bias + col) : 0.f;
-          }
+          for (int i = 0; i < BN / 32; ++i) bias_s[i * 32 + lane] = pf_bias[i];
         }
+        if (!RES && p.ln_stats) {
+#pragma unroll
+          for (int i = 0; i < BN / 32; ++i) cs_s[i * 32 + lane] = pf_cs[i];
+          float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+          for (int q = 0; q < kMaxLnParts; ++q) {
+            s1 += pf_st[q].x;
+            s2 += pf_st[q].y;
+          }
+          const float mean = s1 * p.ln_inv_dim;
+          const float var = fmaxf(fmaf(s2, p.ln_inv_dim, -mean * mean), 0.f);
+          ln_rstd = rsqrtf(var + p.ln_eps);
+          ln_nmr = -ln_rstd * mean;
+        }
+        if (unit + num_clusters < num_units) epi_prefetch(unit + num_clusters);
         if constexpr (RES) {
           // residual chunks of the NEXT tile whose slots this tile does not use can fly now
           nxt_cnt = 0;
@@ -481,8 +558,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
               if (tr) DEVIT_TRACE(13, tr_e);
               float* v0 = reinterpret_cast<float*>(r0);
               float* v1 = reinterpret_cast<float*>(r1);
-              bias_act32(p, v0, bias_s + c * 64);
-              bias_act32(p, v1, bias_s + c * 64 + 32);
+              if (p.ln_stats) {
+                ln_bias_act32(p, v0, cs_s + c * 64, bias_s + c * 64, ln_rstd, ln_nmr);
+                ln_bias_act32(p, v1, cs_s + c * 64 + 32, bias_s + c * 64 + 32, ln_rstd, ln_nmr);
+              } else {
+                bias_act32(p, v0, bias_s + c * 64);
+                bias_act32(p, v1, bias_s + c * 64 + 32);
+              }
               if (p.alpha != 1.0f) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) { v0[j] *= p.alpha; v1[j] *= p.alpha; }
@@ -521,13 +603,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
           const bool split = p.out_kind == DEVIT_OUT_F32_SPLIT;
           const int nchunk = (n_valid + 31) >> 5;
           if constexpr (RES) {
-            // + fp32 residual (x += ...).  Warp (quarter, half) owns chunks c = half + 2j of its
-            // 32 rows; slot j holds the residual of chunk c, TMA-prefetched one whole tile ahead.
-            // The sum is written back into the slot and TMA-stored from there; as soon as that
-            // store has read the slot, the same chunk of the next tile is requested into it.
+            // + fp32 residual (x += ...).  Warp (quarter, half) owns the kResSlots consecutive
+            // chunks c = half * kResSlots + j of its 32 rows; slot j holds the residual of chunk
+            // c, TMA-prefetched one whole tile ahead.  The sum is written back into the slot and
+            // TMA-stored from there; as soon as that store has read the slot, the same chunk of
+            // the next tile is requested into it.  Optionally (LayerNorm folding, producer side)
+            // the warp also emits the bf16 copy of its 64 columns and their partial row sums.
+            float st1 = 0.f, st2 = 0.f;
 #pragma unroll 1
             for (int j = 0; j < cur_cnt; ++j) {
-              const int c = half + 2 * j;
+              const int c = half * kResSlots + j;
               uint32_t r[32];
               tmem_ld_x32(t_row + c * 32, r);
               tmem_ld_wait();
@@ -549,15 +634,36 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
               for (int g = 0; g < 8; ++g)
                 *reinterpret_cast<float4*>(b + stg_off(lane, g)) =
                     make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+              if (p.xb_out) {  // BN == 128: j in {0, 1} -> 16-byte groups 4j .. 4j+3 of the row
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                  uint4 t;
+                  t.x = pack_bf16x2(v[8 * g], v[8 * g + 1]);
+                  t.y = pack_bf16x2(v[8 * g + 2], v[8 * g + 3]);
+                  t.z = pack_bf16x2(v[8 * g + 4], v[8 * g + 5]);
+                  t.w = pack_bf16x2(v[8 * g + 6], v[8 * g + 7]);
+                  *reinterpret_cast<uint4*>(xb_stg + stg_off(lane, 4 * j + g)) = t;
+                }
+              }
+              if (p.stats_out) {
+#pragma unroll
+                for (int k = 0; k < 32; ++k) {
+                  st1 += v[k];
+                  st2 = fmaf(v[k], v[k], st2);
+                }
+              }
               fence_proxy_async_smem();
               if (elect_one()) {
                 tma_store_2d(&tmO0, b, n0 + c * 32, row0);
+                if (p.xb_out && j == kResSlots - 1)
+                  tma_store_2d(&tmO1, xb_stg, n0 + half * 64, row0);
                 bulk_commit();
                 if (j > 0) {
                   bulk_wait_read<1>();  // the previous chunk's store has drained its slot
                   if (j - 1 < nxt_cnt) {
                     mbar_expect_tx(&res_bar[j - 1], 4096);
-                    tma_load_2d(b - 4096, &tmR, &res_bar[j - 1], nxt_n0 + (c - 2) * 32, nxt_row0);
+                    tma_load_2d(b - 4096, &tmR, &res_bar[j - 1],
+                                nxt_n0 + (half * kResSlots + j - 1) * 32, nxt_row0);
                   }
                 }
               }
@@ -568,9 +674,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
               if (cur_cnt - 1 < nxt_cnt) {
                 const int j = cur_cnt - 1;
                 mbar_expect_tx(&res_bar[j], 4096);
-                tma_load_2d(res_slots + j * 4096, &tmR, &res_bar[j], nxt_n0 + (half + 2 * j) * 32,
-                            nxt_row0);
+                tma_load_2d(res_slots + j * 4096, &tmR, &res_bar[j],
+                            nxt_n0 + (half * kResSlots + j) * 32, nxt_row0);
               }
+            }
+            if (p.stats_out && cur_cnt > 0 && row0 + lane < p.M) {
+              // part index = 2 * (n0 / 128) + half   (BN == 128 when stats are requested)
+              float2* so = reinterpret_cast<float2*>(p.stats_out) +
+                           static_cast<long long>(2 * (n0 / BN) + half) * p.M + row0 + lane;
+              *so = make_float2(st1, st2);
             }
             cur_cnt = nxt_cnt;
           } else if (live) {
@@ -828,6 +940,36 @@ extern "C" int devit_gemm(const devit_gemm_args* a, void* stream_v) {
   p.rowmap_off = a->rowmap_off;
   DEVIT_REQUIRE(!(p.rowbias && p.rowmap_period <= 0),
                 "devit_gemm: rowbias needs rowmap_period > 0");
+  // ---- LayerNorm folding
+  const bool ln_consumer = a->ln_stats != nullptr;
+  const bool ln_producer = a->out_bf16 != nullptr || a->stats_out != nullptr;
+  if (ln_consumer) {
+    DEVIT_REQUIRE(kind == 0 && a->out_kind == DEVIT_OUT_BF16 && !a->resid,
+                  "devit_gemm: ln_stats needs bf16 operands and a bf16 output without residual");
+    DEVIT_REQUIRE(a->ln_colsum && a->bias && a->ln_parts >= 1 && a->ln_parts <= kMaxLnParts &&
+                      a->ln_dim > 0,
+                  "devit_gemm: ln_stats needs ln_colsum, bias, 1 <= ln_parts <= %d and ln_dim > 0",
+                  kMaxLnParts);
+    DEVIT_REQUIRE(reinterpret_cast<uintptr_t>(a->ln_stats) % 8 == 0,
+                  "devit_gemm: ln_stats must be 8-byte aligned");
+  }
+  if (ln_producer) {
+    DEVIT_REQUIRE(a->out_kind == DEVIT_OUT_F32 && a->resid && a->n % 128 == 0 &&
+                      a->rowmap_period <= 0,
+                  "devit_gemm: out_bf16 / stats_out need an fp32 residual output with n %% 128 == 0");
+    DEVIT_REQUIRE(!a->out_bf16 || (reinterpret_cast<uintptr_t>(a->out_bf16) % 16 == 0 &&
+                                   (a->ld_out_bf16 * 2) % 16 == 0),
+                  "devit_gemm: out_bf16 must be 16-byte aligned with a 16-byte row pitch");
+    DEVIT_REQUIRE(!a->stats_out || reinterpret_cast<uintptr_t>(a->stats_out) % 8 == 0,
+                  "devit_gemm: stats_out must be 8-byte aligned");
+  }
+  p.ln_stats = a->ln_stats;
+  p.ln_parts = a->ln_parts;
+  p.ln_inv_dim = ln_consumer ? 1.0f / static_cast<float>(a->ln_dim) : 0.f;
+  p.ln_eps = a->ln_eps;
+  p.ln_colsum = a->ln_colsum;
+  p.stats_out = a->stats_out;
+  p.xb_out = a->out_bf16 ? 1 : 0;
   // 16-byte vector requirements of the direct path
   const int out_elem = a->out_kind == DEVIT_OUT_BF16 ? 2 : 4;
   bool vec = (reinterpret_cast<uintptr_t>(a->out) % 16 == 0) && ((a->ldo * out_elem) % 16 == 0);
@@ -872,9 +1014,12 @@ extern "C" int devit_gemm(const devit_gemm_args* a, void* stream_v) {
     const int v = atoi(e);  // debug: 1 = never, 2 = not for residual GEMMs
     if (v == 1 || (v == 2 && a->resid)) tma_epi = false;
   }
+  DEVIT_REQUIRE(!(ln_consumer || ln_producer) || tma_epi,
+                "devit_gemm: LayerNorm folding needs 16-byte aligned outputs (TMA epilogue)");
   if (tma_epi && a->resid) {  // residual variant: BN <= 192
     if (!a->block_n && cl == 2 && a->n % 128 == 0) bn = 128;
     if (bn == 256) bn = 192;
+    if (ln_producer) bn = 128;  // one 64-column bf16 box + one stats part per epilogue warp
   }
   CUtensorMap ta0, ta1, tb0, tb1;
   rc = encode_tmap_2d(&ta0, a->a, elem, a->a_cols, a->a_rows, a->lda, block_k, kBlockM, false);
@@ -909,6 +1054,10 @@ extern "C" int devit_gemm(const devit_gemm_args* a, void* stream_v) {
     if (a->out_kind == DEVIT_OUT_F32_SPLIT) {
       rc = encode_tmap_2d(&tm[5], static_cast<float*>(a->out) + a->out_plane_stride, 4, a->n,
                           a->m, a->ldo, 32, 32, false);
+      if (rc) return rc;
+    }
+    if (a->out_bf16) {
+      rc = encode_tmap_2d(&tm[5], a->out_bf16, 2, a->n, a->m, a->ld_out_bf16, 64, 32, false);
       if (rc) return rc;
     }
     tm[6] = tm[4];

@@ -75,6 +75,34 @@ ln_kernel(const float* __restrict__ x, const float* __restrict__ g, const float*
             static_cast<uint8_t*>(y) + row * D * esz, plane, nullptr);
 }
 
+// bf16 copy of the fp32 residual stream + (sum, sum of squares) per row: the one-part input of
+// a LayerNorm-folded GEMM (include/devit_b200.h, devit_rowstats).
+template <int V>
+__global__ void __launch_bounds__(256)
+rowstats_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ xb,
+                float* __restrict__ stats, long long rows) {
+  constexpr int D = V * 128;
+  const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * D);
+  uint2* br = reinterpret_cast<uint2*>(xb + row * D);
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const float4 v = xr[lane + 32 * i];
+    s1 += (v.x + v.y) + (v.z + v.w);
+    s2 += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+    uint2 t;
+    t.x = pack_bf16x2(v.x, v.y);
+    t.y = pack_bf16x2(v.z, v.w);
+    br[lane + 32 * i] = t;
+  }
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  if (lane == 0) *reinterpret_cast<float2*>(stats + 2 * row) = make_float2(s1, s2);
+}
+
 template <int V>
 __global__ void __launch_bounds__(256)
 gather_ln_kernel(const float* __restrict__ x, const float* __restrict__ g,
@@ -158,6 +186,27 @@ extern "C" int devit_layernorm(const float* x, const float* gamma, const float* 
     case 384: ln_kernel<3><<<grid, 256, 0, stream>>>(x, gamma, beta, y, rows, eps, out_kind, out_plane_stride); break;
     case 768: ln_kernel<6><<<grid, 256, 0, stream>>>(x, gamma, beta, y, rows, eps, out_kind, out_plane_stride); break;
     default: return set_error(DEVIT_ERR_ARG, "devit_layernorm: dim %d not in {256,384,768}", dim);
+  }
+  DEVIT_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return DEVIT_OK;
+}
+
+extern "C" int devit_rowstats(const float* x, void* xb, float* stats, int64_t rows, int32_t dim,
+                              void* stream_v) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  int rc = check_device();
+  if (rc) return rc;
+  DEVIT_REQUIRE(x && xb && stats, "devit_rowstats: null pointer");
+  DEVIT_REQUIRE(rows > 0, "devit_rowstats: rows must be > 0");
+  const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
+  __nv_bfloat16* b = static_cast<__nv_bfloat16*>(xb);
+  ProfScope ps(kTagLayerNorm, stream);
+  switch (dim) {
+    case 256: rowstats_kernel<2><<<grid, 256, 0, stream>>>(x, b, stats, rows); break;
+    case 384: rowstats_kernel<3><<<grid, 256, 0, stream>>>(x, b, stats, rows); break;
+    case 768: rowstats_kernel<6><<<grid, 256, 0, stream>>>(x, b, stats, rows); break;
+    default: return set_error(DEVIT_ERR_ARG, "devit_rowstats: dim %d not in {256,384,768}", dim);
   }
   DEVIT_CUDA_OK(cudaGetLastError());
   count_launch();

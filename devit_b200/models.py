@@ -320,7 +320,8 @@ class VisionTransformer(nn.Module):
         ver = packing.module_version(self)
         hit = self._packs.get(key)
         if hit is None or hit[0] != ver:
-            hit = (ver, packing.PackedVit(self, _PREC[self.precision], device))
+            fold = os.environ.get('DEVIT_FOLD_LN', '1') != '0'  # debug switch, see packing.py
+            hit = (ver, packing.PackedVit(self, _PREC[self.precision], device, fold_ln=fold))
             self._packs = {key: hit}  # one live pack per model
         return hit[1]
 

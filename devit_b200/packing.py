@@ -31,9 +31,10 @@ def kept_indices(gate: torch.Tensor) -> torch.Tensor:
 class PackedVit:
     """Device-resident packed weights + the ctypes descriptor passed to devit_vit_forward."""
 
-    def __init__(self, model, precision: int, device: torch.device):
+    def __init__(self, model, precision: int, device: torch.device, fold_ln: bool = True):
         self.precision = precision
         self.device = device
+        self.fold_ln = fold_ln
         self._keep = []  # tensors referenced by raw pointers in the descriptors
         self.kept_heads = []
         self.kept_neurons = []
@@ -89,9 +90,16 @@ class PackedVit:
             d = self.layers[i]
             d.heads, d.hidden, d.hidden_ld = int(hk.numel()), max(f, 1), f_ld
             d.ln1_g, d.ln1_b = f32(blk.norm1.weight), f32(blk.norm1.bias)
-            d.w_qkv, d.b_qkv = op(wq[rows]), f32(bq[rows])
-            d.w_proj, d.b_proj = op(wp), f32(attn.proj.bias)
             d.ln2_g, d.ln2_b = f32(blk.norm2.weight), f32(blk.norm2.bias)
+            wqk, bqk = wq[rows], bq[rows]
+            if precision == L.DEVIT_BF16 and fold_ln and dim % 128 == 0:
+                # LayerNorm folding (include/devit_b200.h, devit_gemm_args.ln_stats):
+                # LN(x) W^T + b = rstd (x (gamma.W)^T - mean c1) + c2 with c1 = rowsum of the
+                # folded weights AS THE TENSOR CORE SEES THEM (bf16-rounded), c2 = b + W beta.
+                wqk, d.cs_qkv, bqk = self._fold(wqk, bqk, blk.norm1, f32)
+                w1, d.cs_fc1, b1 = self._fold(w1, b1, blk.norm2, f32)
+            d.w_qkv, d.b_qkv = op(wqk), f32(bqk)
+            d.w_proj, d.b_proj = op(wp), f32(attn.proj.bias)
             d.w_fc1, d.b_fc1 = op(w1), f32(b1)
             d.w_fc2, d.b_fc2 = op(w2), f32(mlp.fc2.bias)
 
@@ -114,6 +122,15 @@ class PackedVit:
         self.desc = desc
         self.tokens = (desc.img // 16) ** 2 + desc.num_prefix
         self.dim = dim
+
+    @staticmethod
+    def _fold(w, b, norm, f32):
+        gamma = norm.weight.detach().float().cpu()
+        beta = norm.bias.detach().float().cpu()
+        wf = w * gamma[None, :]
+        c1 = wf.to(torch.bfloat16).float().sum(1)
+        c2 = b + w @ beta
+        return wf, f32(c1), c2
 
     def workspace_bytes(self, batch: int) -> int:
         n = L.load().devit_vit_workspace_bytes(C.byref(self.desc), batch)

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define DEVIT_ABI_VERSION 1
+#define DEVIT_ABI_VERSION 2
 
 enum {
   DEVIT_OK = 0,
@@ -131,6 +131,26 @@ typedef struct devit_gemm_args {
   int32_t profile_tag; /* DEVIT_TAG_GEMM_* bucket used by devit_profile_collect */
   int32_t cluster_m;   /* 1 = one CTA per 128-row tile; 2 = CTA pair (cta_group::2) per
                           256-row tile, each CTA staging half of the weight tile; 0 = auto */
+  /* ---- LayerNorm folding (DEVIT_BF16 operands only; all NULL/0 = off).
+   * A LayerNorm followed by a Linear (norm1 -> qkv, models/de_vit.py:113 + :67; norm2 -> fc1,
+   * :115 + :36) is computed WITHOUT materialising the normalised tensor:
+   *     LN(x) W^T + b = rstd_m * (x (gamma .* W)^T - mean_m * c1) + c2,
+   *     c1[n] = sum_k gamma_k W[n,k],  c2[n] = b[n] + sum_k beta_k W[n,k].
+   * Consumer GEMM (bf16 output): `a` is the raw residual stream rounded to bf16, `b` holds the
+   * gamma-folded weights, `bias` holds c2, `ln_colsum` holds c1 and `ln_stats` the per-row
+   * partial sums [ln_parts][m][2] = (sum x, sum x^2) over disjoint column ranges of the fp32
+   * stream (1 <= ln_parts <= 6); the epilogue derives mean / rstd (biased variance over ln_dim, + ln_eps) per row.
+   * Producer GEMM (fp32 output with `resid`, n % 128 == 0): additionally writes the bf16 copy
+   * of its output to `out_bf16` and the partial row sums of its output to `stats_out`
+   * [2 * n / 128][m][2] (one part per 64 output columns). */
+  const float* ln_stats;
+  int32_t ln_parts;
+  int32_t ln_dim;
+  float ln_eps;
+  const float* ln_colsum;
+  void* out_bf16;
+  int64_t ld_out_bf16;
+  float* stats_out;
 } devit_gemm_args;
 
 int devit_gemm(const devit_gemm_args* args, void* stream);
@@ -147,6 +167,15 @@ int devit_debug_set_trace(long long* device_buf);
 int devit_layernorm(const float* x, const float* gamma, const float* beta, void* y,
                     int64_t rows, int32_t dim, float eps, int32_t out_kind,
                     int64_t out_plane_stride, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * devit_rowstats: xb[r, :] = bf16(x[r, :]) and stats[r] = (sum_k x[r,k], sum_k x[r,k]^2): the
+ * one-part input of a LayerNorm-folded GEMM (see devit_gemm_args.ln_stats) for a residual
+ * stream that was not produced by a devit_gemm (the token embedding, models/de_vit.py:258-264).
+ * x fp32 [rows, dim], dim in {256,384,768}; one warp per row.
+ * ------------------------------------------------------------------------------------- */
+int devit_rowstats(const float* x, void* xb, float* stats, int64_t rows, int32_t dim,
+                   void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * devit_attention: out[b, t, h*64:(h+1)*64] = softmax(q k^T * scale) v   per (b, h).
@@ -214,6 +243,11 @@ typedef struct devit_layer_desc {
   const float* b_fc1; /* [hidden_ld]       */
   const void* w_fc2; /* [dim, hidden_ld] (cols >= hidden are zero) */
   const float* b_fc2;
+  /* LayerNorm folding (DEVIT_BF16 only, both NULL = off): when set, w_qkv / w_fc1 hold the
+   * gamma-folded weights, b_qkv / b_fc1 hold c2 and these hold c1 (devit_gemm_args.ln_colsum);
+   * ln1/ln2 are then not read and no normalised tensor is ever written. */
+  const float* cs_qkv; /* [3*h_l*64] */
+  const float* cs_fc1; /* [hidden_ld] */
 } devit_layer_desc;
 
 typedef struct devit_vit_desc {

@@ -67,6 +67,64 @@ def test_gemm_epilogue_gelu_resid_alpha():
     assert rel(x, ref) < 2e-5
 
 
+@pytest.mark.parametrize("m", [520, 128 * 70 + 9])
+@pytest.mark.parametrize("k", [256, 928])
+def test_gemm_ln_fold_producer(m, k):
+    """Residual GEMM that also emits the bf16 copy of its output and the partial row sums
+    (LayerNorm folding, producer side): x += a w^T + b; xb = bf16(x); stats = (sum, sum^2)."""
+    n = 384
+    a = _mk((m, k), 31).bfloat16()
+    w = _mk((n, k), 32, 0.05).bfloat16()
+    bias = _mk((n,), 33)
+    res = _mk((m, n), 34)
+    x = res.clone()
+    xb = torch.full((m, n), 7.0, device="cuda", dtype=torch.bfloat16)
+    parts = 2 * (n // 128)
+    stats = torch.full((parts, m, 2), -1.0, device="cuda")
+    L.gemm(a, w, bias=bias, resid=x, out=x, out_kind=L.OUT_F32, out_bf16=xb, stats_out=stats)
+    ref = a.float() @ w.float().t() + bias + res
+    assert rel(x, ref) < 2e-5
+    assert torch.equal(xb, x.bfloat16())          # the copy is the rounding of what was stored
+    cols = x.view(m, parts, 64)
+    assert rel(stats[..., 0].t(), cols.sum(-1)) < 1e-5
+    assert rel(stats[..., 1].t(), (cols * cols).sum(-1)) < 1e-5
+
+
+@pytest.mark.parametrize("m,n", [(520, 576), (128 * 70 + 9, 928), (300, 1152)])
+@pytest.mark.parametrize("parts", [1, 6])
+@pytest.mark.parametrize("act", [L.ACT_NONE, L.ACT_GELU_ERF])
+def test_gemm_ln_fold_consumer(m, n, parts, act):
+    """y = act(LN(x) W^T + b) computed from bf16(x), gamma-folded weights and row statistics
+    (LayerNorm folding, consumer side) against LayerNorm + Linear in fp32."""
+    d, eps = 384, 1e-6
+    x = _mk((m, d), 41) * 1.5 + _mk((1, d), 45) * 0.5   # per-channel offsets like a real stream
+    gamma = 1.0 + 0.1 * _mk((d,), 42)
+    beta = 0.1 * _mk((d,), 43)
+    w = _mk((n, d), 44, 0.05)
+    bias = _mk((n,), 46, 0.1)
+    wf = (w * gamma[None, :]).bfloat16()
+    c1 = wf.float().sum(1).contiguous()
+    c2 = (bias + w @ beta).contiguous()
+    if parts == 1:
+        xb, stats = L.rowstats(x)
+        assert torch.equal(xb, x.bfloat16())
+        assert rel(stats[0, :, 0], x.sum(-1)) < 1e-5 and rel(stats[0, :, 1], (x * x).sum(-1)) < 1e-5
+    else:
+        xb = x.bfloat16()
+        cols = x.view(m, parts, d // parts)
+        stats = torch.stack([cols.sum(-1).t(), (cols * cols).sum(-1).t()], -1).contiguous()
+    out = L.gemm(xb, wf, bias=c2, act=act, out_kind=L.OUT_BF16, ln_stats=stats, ln_colsum=c1,
+                 ln_dim=d, ln_eps=eps)
+    ref = torch.nn.functional.layer_norm(x, (d,), gamma, beta, eps) @ w.t() + bias
+    if act == L.ACT_GELU_ERF:
+        ref = torch.nn.functional.gelu(ref)
+    assert rel(out, ref) < 1.2e-2, rel(out, ref)
+    # and against the unfolded bf16 pipeline (LayerNorm -> bf16 -> GEMM): same error class
+    y = L.layernorm(x, gamma, beta, eps, L.OUT_BF16)
+    base = L.gemm(y, w.bfloat16(), bias=bias, act=act, out_kind=L.OUT_BF16)
+    assert rel(out, ref) < 2.0 * rel(base, ref) + 2e-3, (rel(out, ref), rel(base, ref))
+
+
 @pytest.mark.parametrize("cl", [1, 2])
 @pytest.mark.parametrize("bn", [128, 192, 256])
 def test_gemm_cta_pair(cl, bn):

@@ -160,7 +160,10 @@ class EnsMLP(nn.Module):
         if n > 8:
             raise L.DevitError("EnsMLP: at most 8 sub-models per fusion GEMM")
         a = slab.view(n * kinds * B, D) if prec == L.DEVIT_BF16 else slab.view(2, n * kinds * B, D)
-        segs = [((j * kinds + kind) * B, 0, order[j] * D, D) for j in range(n)]
+        # segments are issued in SUB-MODEL order whatever the slab layout, so the fp32
+        # accumulation order -- hence every logit bit -- is the same for any world size
+        segs = sorted(((j * kinds + kind) * B, 0, order[j] * D, D) for j in range(n))
+        segs.sort(key=lambda sg: sg[2])
         return L.gemm(a, pk.w, precision=prec, m=B, segs=segs, bias=pk.b, out_kind=out_kind,
                       tag=6, **epi)
 

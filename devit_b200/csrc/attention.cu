@@ -15,6 +15,8 @@
 //   ~92 KB smem and 256 TMEM columns per CTA -> two CTAs per SM, so one CTA's softmax
 //   overlaps the other's loads and MMAs.
 // fp32 path (attn_f32_kernel): CUDA-core fp32 for the parity mode.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -276,6 +278,340 @@ attn_bf16_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   }
 }
 
+// ------------------------------------------------------------------ persistent bf16 path
+// attn_persist_kernel: one CTA per SM loops over (image, kept head) items; used when every key
+// of a head fits 208 columns (ViT: 197/198 tokens).  Per item:
+//   * TMA brings the head's Q (two 128-row tiles), K and V ONCE (the per-tile kernel above loads
+//     K and V once per query tile), double-buffered so item i+1 lands during item i;
+//   * S_t = Q_t K^T for both query tiles goes to TMEM columns [256 t, 256 t + 208);
+//   * 16 softmax warps: warp w works on TMEM lane quarter w % 4 of query tile (w / 4) % 2 and on
+//     key half w / 8 (keys [0, 112) or [112, 208)) -- a thread owns half a score row.  A lone
+//     warp sustains only one exp2 per ~16 cycles, so the row is split to put four warps per
+//     scheduler on the exp2 unit.  Row max / row sum are exchanged through shared memory with
+//     a 64-thread named barrier per (tile, quarter).  P is written as packed bf16 pairs back
+//     INTO TMEM over S columns the thread has already consumed (keys [0,112) -> columns
+//     [0, 56), keys [112, 208) -> columns [112, 160)) -- no shared-memory round trip;
+//   * O_t = P_t V is a tcgen05.mma with the A operand in tensor memory, accumulating into
+//     columns [192, 256) of the tile (the S tail there is dead by then); each warp scales half
+//     of the 64 output columns by 1/rowsum and stores them.
+// TMEM: 2 x 256 columns = all 512 (hence one CTA per SM); smem: 2 stages x 84 KB.
+constexpr int kPersistThreads = 17 * 32;  // 16 softmax warps + 1 control warp
+constexpr int kSplitKeys = 112;           // keys [0, 112) -> half 0, [112, KVP) -> half 1
+
+long long* g_attn_trace = nullptr;  // devit_debug_set_trace (shared with the GEMM trace buffer)
+#ifdef DEVIT_GEMM_TRACE
+#define ATTN_TRACE(slot_, idx_)                                                         \
+  do {                                                                                  \
+    if (trace && blockIdx.x == 0 && lane == 0 && (idx_) < 512)                          \
+      trace[(slot_) * 512 + (idx_)] = clock64();                                        \
+  } while (0)
+#else
+#define ATTN_TRACE(slot_, idx_) do { } while (0)
+#endif
+
+template <int KVP>
+struct AttnPersistCfg {
+  static constexpr int kQBytes = 2 * 128 * 128;  // two query tiles
+  static constexpr int kKVBytes = KVP * 128;
+  static constexpr int kStageBytes = kQBytes + 2 * kKVBytes;
+  static constexpr int kOffBar = 2 * kStageBytes;
+  static constexpr int kOffXchg = kOffBar + 128;          // [2 tiles][2 halves][128 rows] x 2
+  static constexpr int kSmemBytes = kOffXchg + 4096 + 1024;
+  static constexpr int kOCols = 192;  // O accumulator: columns [192, 256) of the tile
+  static_assert(KVP == 208, "column split / P placement are laid out for 208 padded keys");
+};
+
+template <int KVP>
+__global__ void __launch_bounds__(kPersistThreads, 1)
+attn_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                    __nv_bfloat16* __restrict__ out, int tokens, int heads, int num_items,
+                    float scale_log2e, int dephase, long long* trace) {
+  using Cfg = AttnPersistCfg<KVP>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBar);
+  uint64_t* full_qk = bars + 0;   // [2 stages]  Q and K landed
+  uint64_t* full_v = bars + 2;    // [2 stages]  V landed
+  uint64_t* empty = bars + 4;     // [2 stages]  every MMA that reads the stage has finished
+  uint64_t* s_full = bars + 6;    // [2 tiles]   S_t complete
+  uint64_t* p_full = bars + 8;    // [2 tiles]   P_t written (4 warp arrivals)
+  uint64_t* o_full = bars + 10;   // [2 tiles]   O_t complete
+  uint64_t* o_empty = bars + 12;  // [2 tiles]   O_t read out, S_t columns reusable (4 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  float* x_max = reinterpret_cast<float*>(smem + Cfg::kOffXchg);  // [tile][half][row]
+  float* x_sum = x_max + 512;
+
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 16) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmQ);
+      tma_prefetch_desc(&tmKV);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&full_qk[i], 1);
+        mbar_init(&full_v[i], 1);
+        mbar_init(&empty[i], 1);
+        mbar_init(&s_full[i], 1);
+        mbar_init(&p_full[i], 8);
+        mbar_init(&o_full[i], 1);
+        mbar_init(&o_empty[i], 8);
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  const int first = blockIdx.x, step = gridDim.x;
+
+  if (warp == 16) {
+    // ------------------------------------------------------------ control: TMA + MMA issue
+    auto load_item = [&](int item, int stage) {
+      const int img = item / heads, head = item - img * heads;
+      uint8_t* sq = smem + stage * Cfg::kStageBytes;
+      uint8_t* sk = sq + Cfg::kQBytes;
+      uint8_t* sv = sk + Cfg::kKVBytes;
+      if (elect_one()) {
+        mbar_expect_tx(&full_qk[stage], Cfg::kQBytes + Cfg::kKVBytes);
+        tma_load_3d(sq, &tmQ, &full_qk[stage], head * 64, 0, img);
+        tma_load_3d(sq + 16384, &tmQ, &full_qk[stage], head * 64, 128, img);
+        tma_load_3d(sk, &tmKV, &full_qk[stage], (heads + head) * 64, 0, img);
+        mbar_expect_tx(&full_v[stage], Cfg::kKVBytes);
+        tma_load_3d(sv, &tmKV, &full_v[stage], (2 * heads + head) * 64, 0, img);
+      }
+    };
+    const uint32_t idesc_s = make_idesc(kFmtBF16, 128, KVP, 0, 0);
+    const uint32_t idesc_o = make_idesc(kFmtBF16, 128, 64, 0, 1);
+    const int n_mine = first < num_items ? (num_items - first + step - 1) / step : 0;
+    // Event loop.  The two query tiles are independent pipelines (S -> softmax -> PV -> store)
+    // that share the exp2 unit; issuing them in lock-step makes both hit it at the same time and
+    // both idle together afterwards.  So every step is issued as soon as ITS inputs are ready
+    // (non-blocking barrier probes), and tile 1's first S waits for tile 0's first P, which puts
+    // the pipelines half a period apart: one tile's exp2 pass runs under the other's MMAs,
+    // stores and max pass.
+    int k_load = 0;            // next item to request (stage k_load & 1)
+    int k_s[2] = {0, 0};       // next item whose S_t is to be issued
+    int k_pv[2] = {0, 0};      // next item whose P_t V is to be issued
+    auto ready = [&](uint64_t* bar, uint32_t parity) -> bool {
+      return __shfl_sync(0xffffffffu, mbar_test_wait(bar, parity) ? 1 : 0, 0) != 0;
+    };
+    while (k_pv[0] < n_mine || k_pv[1] < n_mine) {
+      bool progress = false;
+      // ---- loads: two stages; stage of item k is free once both P V of item k-2 retired
+      if (k_load < n_mine && (k_load < 2 || ready(&empty[k_load & 1], ((k_load - 2) >> 1) & 1))) {
+        load_item(first + k_load * step, k_load & 1);
+        ++k_load;
+        progress = true;
+      }
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        if (k_s[t] == k_pv[t] && k_s[t] < n_mine) {
+          // ---- S_t = Q_t K^T (M=128, N=KVP, K=64: 4 UMMAs)
+          const int k = k_s[t], stage = k & 1;
+          bool ok = k < k_load && ready(&full_qk[stage], (k >> 1) & 1);
+          if (ok && k >= 1) ok = ready(&o_empty[t], (k - 1) & 1);       // tile's columns free
+          if (ok && (dephase & 1) && t == 1 && k == 0) ok = ready(&p_full[0], 0);  // phase offset
+          if (ok) {
+            tc_fence_after();
+            const uint32_t sq = smem_u32(smem + stage * Cfg::kStageBytes);
+            const uint64_t dq = make_sw128_desc(sq + t * 16384, 1024, 16);
+            const uint64_t dk = make_sw128_desc(sq + Cfg::kQBytes, 1024, 16);
+            if (elect_one()) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                umma_bf16(tmem_base + t * 256, dq + 2 * j, dk + 2 * j, idesc_s, j > 0);
+              umma_commit(&s_full[t]);
+            }
+            ATTN_TRACE(2 + t, k);
+            ++k_s[t];
+            progress = true;
+          }
+        } else if (k_pv[t] < k_s[t]) {
+          // ---- O_t = P_t V (A from TMEM, V MN-major in smem: 16 keys = 2 KB per UMMA)
+          const int k = k_pv[t], stage = k & 1;
+          if (ready(&p_full[t], k & 1) && ready(&full_v[stage], (k >> 1) & 1)) {
+            ATTN_TRACE(4 + t, k);
+            tc_fence_after();
+            const uint32_t sv =
+                smem_u32(smem + stage * Cfg::kStageBytes) + Cfg::kQBytes + Cfg::kKVBytes;
+            if (elect_one()) {
+#pragma unroll
+              for (int j = 0; j < KVP / 16; ++j) {
+                const uint64_t dv = make_sw128_desc(sv + j * 2048, 1024, 1024);
+                // P of keys [0,112) sits in columns [0,56), of keys [112,208) in [112,160)
+                const uint32_t pcol = j < kSplitKeys / 16 ? 8 * j : kSplitKeys + 8 * (j - kSplitKeys / 16);
+                umma_bf16_ts(tmem_base + t * 256 + Cfg::kOCols, tmem_base + t * 256 + pcol, dv,
+                             idesc_o, j > 0);
+              }
+              umma_commit(&o_full[t]);
+              // the stage is free once BOTH tiles' P V of this item retired: commit after the
+              // second of the two to be issued (a commit covers every earlier MMA)
+              if (k_pv[t ^ 1] > k) umma_commit(&empty[stage]);
+            }
+            ATTN_TRACE(6 + t, k);
+            ++k_pv[t];
+            progress = true;
+          }
+        }
+      }
+      if (!progress) __nanosleep(40);  // leave the issue slots to the softmax warps
+    }
+  } else {
+    // ------------------------------------------------------------ softmax + epilogue warps
+    const int quarter = warp & 3;         // TMEM lane quarter
+    const int t = (warp >> 2) & 1;        // query tile
+    const int h = warp >> 3;              // key half
+    const int row_in_tile = quarter * 32 + lane;
+    const int row = t * 128 + row_in_tile;
+    const bool warp_live = (t * 128 + quarter * 32) < tokens;
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + t * 256;
+    const uint32_t s_col = h ? kSplitKeys : 0;   // first S column (= key) of this half
+    const uint32_t p_col = h ? kSplitKeys : 0;   // first P column of this half
+    const int pair_bar = 1 + t * 4 + quarter;    // named barrier of the two warps of a row
+    float* my_max = x_max + (t * 2 + h) * 128 + row_in_tile;
+    float* other_max = x_max + (t * 2 + (h ^ 1)) * 128 + row_in_tile;
+    float* my_sum = x_sum + (t * 2 + h) * 128 + row_in_tile;
+    float* other_sum = x_sum + (t * 2 + (h ^ 1)) * 128 + row_in_tile;
+    int k = 0;
+    for (int item = first; item < num_items; item += step, ++k) {
+      const int img = item / heads, head = item - img * heads;
+      if (quarter == 0 && h == 0) ATTN_TRACE(8 + 6 * t, k);
+      mbar_wait_warp(&s_full[t], k & 1);
+      if (quarter == 0 && h == 0) ATTN_TRACE(9 + 6 * t, k);
+      tc_fence_after();
+      float sum = 0.f;
+      if (warp_live) {
+        // Three 32-column chunks per half (+ one 16-column chunk for half 0), fully unrolled,
+        // with the TMEM load of the next chunk in flight while the current one is processed.
+        uint32_t r[4][32];
+        // ---- pass 1: max over this half's valid keys, then exchange with the other half
+        float mx = -INFINITY;
+        tmem_ld_x32(t_row + s_col, r[0]);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          tmem_ld_wait();
+          if (c < 2) tmem_ld_x32(t_row + s_col + (c + 1) * 32, r[c + 1]);
+          else if (h == 0) tmem_ld_x16(t_row + 96, r[3]);
+          if (h == 0 || kSplitKeys + (c + 1) * 32 <= tokens) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 2)
+              mx = fmax3(mx, __uint_as_float(r[c][j]), __uint_as_float(r[c][j + 1]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (kSplitKeys + c * 32 + j < tokens) mx = fmaxf(mx, __uint_as_float(r[c][j]));
+          }
+        }
+        if (h == 0) {
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; j += 2)
+            mx = fmax3(mx, __uint_as_float(r[3][j]), __uint_as_float(r[3][j + 1]));
+        }
+        *my_max = mx;
+        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+        mx = fmaxf(mx, *other_max);
+        if (quarter == 0 && h == 0) ATTN_TRACE(10 + 6 * t, k);
+        // ---- pass 2: p = exp2(s*c - max*c), partial row sum, P -> TMEM as packed bf16 pairs
+        const float moff = mx * scale_log2e;
+        tmem_ld_x32(t_row + s_col, r[0]);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          tmem_ld_wait();
+          if (c < 2) tmem_ld_x32(t_row + s_col + (c + 1) * 32, r[c + 1]);
+          else if (h == 0) tmem_ld_x16(t_row + 96, r[3]);
+          uint32_t pk[16];
+          if (h == 0 || kSplitKeys + (c + 1) * 32 <= tokens) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float e0 = fast_exp2(fmaf(__uint_as_float(r[c][2 * j]), scale_log2e, -moff));
+              const float e1 =
+                  fast_exp2(fmaf(__uint_as_float(r[c][2 * j + 1]), scale_log2e, -moff));
+              sum += e0 + e1;
+              pk[j] = pack_bf16x2(e0, e1);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float e0 = fast_exp2(fmaf(__uint_as_float(r[c][2 * j]), scale_log2e, -moff));
+              float e1 = fast_exp2(fmaf(__uint_as_float(r[c][2 * j + 1]), scale_log2e, -moff));
+              e0 = (kSplitKeys + c * 32 + 2 * j < tokens) ? e0 : 0.f;
+              e1 = (kSplitKeys + c * 32 + 2 * j + 1 < tokens) ? e1 : 0.f;
+              sum += e0 + e1;
+              pk[j] = pack_bf16x2(e0, e1);
+            }
+          }
+          // P chunk c -> 16 columns inside the S columns this thread has already consumed
+          tmem_st_x16(t_row + p_col + c * 16, pk);
+        }
+        if (h == 0) {
+          tmem_ld_wait();
+          uint32_t pk[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float e0 = fast_exp2(fmaf(__uint_as_float(r[3][2 * j]), scale_log2e, -moff));
+            const float e1 = fast_exp2(fmaf(__uint_as_float(r[3][2 * j + 1]), scale_log2e, -moff));
+            sum += e0 + e1;
+            pk[j] = pack_bf16x2(e0, e1);
+          }
+          tmem_st_x8(t_row + 48, pk);
+        }
+        tmem_st_wait();
+        *my_sum = sum;  // read by the other half after o_full (ordered by the barrier chain)
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[t]);
+      if (quarter == 0 && h == 0) ATTN_TRACE(11 + 6 * t, k);
+
+      mbar_wait_warp(&o_full[t], k & 1);
+      if (quarter == 0 && h == 0) ATTN_TRACE(12 + 6 * t, k);
+      tc_fence_after();
+      if (warp_live) {
+        const float inv_sum = 1.0f / (sum + *other_sum);
+        uint32_t r0[32];
+        tmem_ld_x32(t_row + Cfg::kOCols + h * 32, r0);   // this half's 32 output columns
+        tmem_ld_wait();
+        // O is in registers: hand the tile's TMEM columns back BEFORE converting and storing
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&o_empty[t]);
+        if (row < tokens) {
+          __nv_bfloat16* o = out + (static_cast<long long>(img) * tokens + row) * (heads * 64) +
+                             head * 64 + h * 32;
+          uint4* o4 = reinterpret_cast<uint4*>(o);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 v;
+            v.x = pack_bf16x2(__uint_as_float(r0[8 * g]) * inv_sum, __uint_as_float(r0[8 * g + 1]) * inv_sum);
+            v.y = pack_bf16x2(__uint_as_float(r0[8 * g + 2]) * inv_sum, __uint_as_float(r0[8 * g + 3]) * inv_sum);
+            v.z = pack_bf16x2(__uint_as_float(r0[8 * g + 4]) * inv_sum, __uint_as_float(r0[8 * g + 5]) * inv_sum);
+            v.w = pack_bf16x2(__uint_as_float(r0[8 * g + 6]) * inv_sum, __uint_as_float(r0[8 * g + 7]) * inv_sum);
+            o4[g] = v;
+          }
+        }
+      } else {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&o_empty[t]);
+      }
+      if (quarter == 0 && h == 0) ATTN_TRACE(13 + 6 * t, k);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 16) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // ------------------------------------------------------------------------- fp32 parity path
 // One CTA per (head, image); K (padded rows, conflict-free) and V live in shared memory as
 // fp32; each warp owns query rows round-robin.
@@ -387,6 +723,38 @@ static int launch_attn_bf16(const void* qkv, void* out, int batch, int tokens, i
   return DEVIT_OK;
 }
 
+template <int KVP>
+static int launch_attn_persist(const void* qkv, void* out, int batch, int tokens, int heads,
+                               float scale, cudaStream_t stream) {
+  using Cfg = AttnPersistCfg<KVP>;
+  static bool attr_done[64] = {};
+  int dev = 0;
+  DEVIT_CUDA_OK(cudaGetDevice(&dev));
+  if (!attr_done[dev & 63]) {
+    DEVIT_CUDA_OK(cudaFuncSetAttribute(attn_persist_kernel<KVP>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Cfg::kSmemBytes));
+    attr_done[dev & 63] = true;
+  }
+  const uint64_t ld = 3ull * heads * 64;
+  CUtensorMap tq, tkv;
+  int rc = encode_tmap_3d(&tq, qkv, 2, ld, tokens, batch, ld, ld * tokens, 64, 128, 1);
+  if (rc) return rc;
+  rc = encode_tmap_3d(&tkv, qkv, 2, ld, tokens, batch, ld, ld * tokens, 64, KVP, 1);
+  if (rc) return rc;
+  const int items = batch * heads;
+  const int grid = items < num_sms() ? items : num_sms();
+  {
+    ProfScope ps(kTagAttention, stream);
+    attn_persist_kernel<KVP><<<grid, kPersistThreads, Cfg::kSmemBytes, stream>>>(
+        tq, tkv, static_cast<__nv_bfloat16*>(out), tokens, heads, items,
+        scale * 1.4426950408889634f, getenv("DEVIT_ATTN_LOCKSTEP") ? 0 : 1, g_attn_trace);
+  }
+  DEVIT_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return DEVIT_OK;
+}
+
 }  // namespace devit
 
 extern "C" int devit_attention(int32_t precision, const void* qkv, int64_t qkv_plane_stride,
@@ -402,7 +770,14 @@ extern "C" int devit_attention(int32_t precision, const void* qkv, int64_t qkv_p
                 heads, tokens);
   if (precision == DEVIT_BF16) {
     const int kvp = (tokens + 15) & ~15;
+    static int persist = -1;  // DEVIT_ATTN_PERSIST=0: per-tile kernel only (debug / comparison)
+    if (persist < 0) {
+      const char* e = getenv("DEVIT_ATTN_PERSIST");
+      persist = (e && e[0] == '0') ? 0 : 1;
+    }
     if (kvp <= 64) return launch_attn_bf16<64>(qkv, out, batch, tokens, heads, scale, stream);
+    if (kvp <= 208 && kvp > 128 && persist)
+      return launch_attn_persist<208>(qkv, out, batch, tokens, heads, scale, stream);
     if (kvp <= 208) return launch_attn_bf16<208>(qkv, out, batch, tokens, heads, scale, stream);
     return launch_attn_bf16<256>(qkv, out, batch, tokens, heads, scale, stream);
   }

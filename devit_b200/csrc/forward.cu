@@ -157,8 +157,14 @@ extern "C" int devit_vit_forward(const devit_vit_desc* d, const float* images, i
   // normalised tensor at all.  `y` holds the bf16 copy of the residual stream, written by the
   // epilogue of whichever GEMM last updated x together with the rows' partial (sum, sum^2); the
   // QKV / fc1 GEMMs consume both and apply mean / rstd in their epilogue.
-  bool fold = prec == DEVIT_BF16 && D % 128 == 0 && L.stat_parts <= 6;
-  for (int l = 0; l < d->depth; ++l) fold = fold && d->layers[l].cs_qkv && d->layers[l].cs_fc1;
+  int n_folded = 0;
+  for (int l = 0; l < d->depth; ++l) n_folded += (d->layers[l].cs_qkv && d->layers[l].cs_fc1) ? 1 : 0;
+  const bool fold = n_folded == d->depth;
+  DEVIT_REQUIRE(n_folded == 0 || fold, "devit_vit_forward: cs_qkv / cs_fc1 must be set for all "
+                "layers or for none");
+  DEVIT_REQUIRE(!fold || (prec == DEVIT_BF16 && D % 128 == 0 && L.stat_parts <= 6),
+                "devit_vit_forward: LayerNorm-folded weights need DEVIT_BF16 and dim in {128, 256, "
+                "384} (got dim %d)", D);
   float* stats = reinterpret_cast<float*>(ws + L.off_stats);
   int parts = 1;
   if (fold && nl > 0) {

@@ -871,8 +871,10 @@ static int pick_block_n(int n, int cl) {
 }  // namespace devit
 
 // Debug: device buffer of 20 x 512 int64 receiving clock64 stamps of CTA 0 (NULL disables).
+namespace devit { extern long long* g_attn_trace; }
 extern "C" int devit_debug_set_trace(long long* device_buf) {
   devit::g_trace = device_buf;
+  devit::g_attn_trace = device_buf;
   return DEVIT_OK;
 }
 

@@ -230,7 +230,11 @@ def _attn_ref(qkv, batch, tokens, heads, scale):
 
 
 @pytest.mark.parametrize("batch,tokens,heads", [(2, 198, 6), (3, 197, 3), (1, 198, 1),
-                                                (2, 64, 4), (2, 256, 4), (5, 100, 2)])
+                                                (2, 64, 4), (2, 256, 4), (5, 100, 2),
+                                                # persistent kernel: 2.6, 5.4 and 7.8 items per
+                                                # CTA (stage / parity cycling), short sequences
+                                                (64, 198, 6), (200, 197, 4), (230, 198, 5),
+                                                (40, 150, 4), (150, 129, 3)])
 def test_attention_bf16(batch, tokens, heads):
     qkv = _mk((batch * tokens, 3 * heads * 64), 7).bfloat16()
     out = L.attention(qkv, batch, tokens, heads, 0.125)

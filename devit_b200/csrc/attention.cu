@@ -284,19 +284,17 @@ attn_bf16_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 //   * TMA brings the head's Q (two 128-row tiles), K and V ONCE (the per-tile kernel above loads
 //     K and V once per query tile), double-buffered so item i+1 lands during item i;
 //   * S_t = Q_t K^T for both query tiles goes to TMEM columns [256 t, 256 t + 208);
-//   * 16 softmax warps: warp w works on TMEM lane quarter w % 4 of query tile (w / 4) % 2 and on
-//     key half w / 8 (keys [0, 112) or [112, 208)) -- a thread owns half a score row.  A lone
-//     warp sustains only one exp2 per ~16 cycles, so the row is split to put four warps per
-//     scheduler on the exp2 unit.  Row max / row sum are exchanged through shared memory with
-//     a 64-thread named barrier per (tile, quarter).  P is written as packed bf16 pairs back
-//     INTO TMEM over S columns the thread has already consumed (keys [0,112) -> columns
-//     [0, 56), keys [112, 208) -> columns [112, 160)) -- no shared-memory round trip;
+//   * 8 softmax warps (warp w: TMEM lane quarter w % 4 of query tile w / 4), one score row per
+//     thread, two passes over the row (max, then exp2 / sum) with the next TMEM load in flight,
+//     P written as packed bf16 pairs back INTO TMEM over S columns the thread has already
+//     consumed (P row = columns [0, 104)) -- no shared-memory round trip, no proxy fence.
+//     (Splitting each row over two warps -- 16 softmax warps -- was measured SLOWER: the pass
+//     is bound by the exp2 unit, 4 lanes / clock / scheduler, not by per-warp latency.)
 //   * O_t = P_t V is a tcgen05.mma with the A operand in tensor memory, accumulating into
-//     columns [192, 256) of the tile (the S tail there is dead by then); each warp scales half
-//     of the 64 output columns by 1/rowsum and stores them.
+//     columns [192, 256) of the tile (the S tail there is dead by then); the same warps scale
+//     by 1/rowsum and store.
 // TMEM: 2 x 256 columns = all 512 (hence one CTA per SM); smem: 2 stages x 84 KB.
-constexpr int kPersistThreads = 17 * 32;  // 16 softmax warps + 1 control warp
-constexpr int kSplitKeys = 112;           // keys [0, 112) -> half 0, [112, KVP) -> half 1
+constexpr int kPersistThreads = 9 * 32;  // 8 softmax warps + 1 control warp
 
 long long* g_attn_trace = nullptr;  // devit_debug_set_trace (shared with the GEMM trace buffer)
 #ifdef DEVIT_GEMM_TRACE
@@ -315,10 +313,9 @@ struct AttnPersistCfg {
   static constexpr int kKVBytes = KVP * 128;
   static constexpr int kStageBytes = kQBytes + 2 * kKVBytes;
   static constexpr int kOffBar = 2 * kStageBytes;
-  static constexpr int kOffXchg = kOffBar + 128;          // [2 tiles][2 halves][128 rows] x 2
-  static constexpr int kSmemBytes = kOffXchg + 4096 + 1024;
+  static constexpr int kSmemBytes = kOffBar + 256 + 1024;
   static constexpr int kOCols = 192;  // O accumulator: columns [192, 256) of the tile
-  static_assert(KVP == 208, "column split / P placement are laid out for 208 padded keys");
+  static_assert(KVP % 32 == 16 && KVP <= 208 && KVP / 2 <= kOCols, "P and O must not overlap");
 };
 
 template <int KVP>
@@ -338,13 +335,11 @@ attn_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint64_t* o_full = bars + 10;   // [2 tiles]   O_t complete
   uint64_t* o_empty = bars + 12;  // [2 tiles]   O_t read out, S_t columns reusable (4 arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
-  float* x_max = reinterpret_cast<float*>(smem + Cfg::kOffXchg);  // [tile][half][row]
-  float* x_sum = x_max + 512;
 
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
 
-  if (warp == 16) {
+  if (warp == 8) {
     if (lane == 0) {
       tma_prefetch_desc(&tmQ);
       tma_prefetch_desc(&tmKV);
@@ -353,9 +348,9 @@ attn_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         mbar_init(&full_v[i], 1);
         mbar_init(&empty[i], 1);
         mbar_init(&s_full[i], 1);
-        mbar_init(&p_full[i], 8);
+        mbar_init(&p_full[i], 4);
         mbar_init(&o_full[i], 1);
-        mbar_init(&o_empty[i], 8);
+        mbar_init(&o_empty[i], 4);
       }
       fence_mbar_init();
     }
@@ -369,7 +364,7 @@ attn_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   const int first = blockIdx.x, step = gridDim.x;
 
-  if (warp == 16) {
+  if (warp == 8) {
     // ------------------------------------------------------------ control: TMA + MMA issue
     auto load_item = [&](int item, int stage) {
       const int img = item / heads, head = item - img * heads;
@@ -415,7 +410,7 @@ attn_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           const int k = k_s[t], stage = k & 1;
           bool ok = k < k_load && ready(&full_qk[stage], (k >> 1) & 1);
           if (ok && k >= 1) ok = ready(&o_empty[t], (k - 1) & 1);       // tile's columns free
-          if (ok && (dephase & 1) && t == 1 && k == 0) ok = ready(&p_full[0], 0);  // phase offset
+          if (ok && dephase && t == 1 && k == 0) ok = ready(&p_full[0], 0);  // phase offset
           if (ok) {
             tc_fence_after();
             const uint32_t sq = smem_u32(smem + stage * Cfg::kStageBytes);
@@ -443,9 +438,7 @@ attn_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
               for (int j = 0; j < KVP / 16; ++j) {
                 const uint64_t dv = make_sw128_desc(sv + j * 2048, 1024, 1024);
-                // P of keys [0,112) sits in columns [0,56), of keys [112,208) in [112,160)
-                const uint32_t pcol = j < kSplitKeys / 16 ? 8 * j : kSplitKeys + 8 * (j - kSplitKeys / 16);
-                umma_bf16_ts(tmem_base + t * 256 + Cfg::kOCols, tmem_base + t * 256 + pcol, dv,
+                umma_bf16_ts(tmem_base + t * 256 + Cfg::kOCols, tmem_base + t * 256 + 8 * j, dv,
                              idesc_o, j > 0);
               }
               umma_commit(&o_full[t]);
@@ -463,70 +456,58 @@ attn_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     }
   } else {
     // ------------------------------------------------------------ softmax + epilogue warps
-    const int quarter = warp & 3;         // TMEM lane quarter
-    const int t = (warp >> 2) & 1;        // query tile
-    const int h = warp >> 3;              // key half
-    const int row_in_tile = quarter * 32 + lane;
-    const int row = t * 128 + row_in_tile;
+    const int quarter = warp & 3;  // TMEM lane quarter
+    const int t = warp >> 2;       // query tile
+    const int row = t * 128 + quarter * 32 + lane;
     const bool warp_live = (t * 128 + quarter * 32) < tokens;
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + t * 256;
-    const uint32_t s_col = h ? kSplitKeys : 0;   // first S column (= key) of this half
-    const uint32_t p_col = h ? kSplitKeys : 0;   // first P column of this half
-    const int pair_bar = 1 + t * 4 + quarter;    // named barrier of the two warps of a row
-    float* my_max = x_max + (t * 2 + h) * 128 + row_in_tile;
-    float* other_max = x_max + (t * 2 + (h ^ 1)) * 128 + row_in_tile;
-    float* my_sum = x_sum + (t * 2 + h) * 128 + row_in_tile;
-    float* other_sum = x_sum + (t * 2 + (h ^ 1)) * 128 + row_in_tile;
+    constexpr int kFull = KVP / 32;  // 32-column chunks, then one 16-column tail
     int k = 0;
     for (int item = first; item < num_items; item += step, ++k) {
       const int img = item / heads, head = item - img * heads;
-      if (quarter == 0 && h == 0) ATTN_TRACE(8 + 6 * t, k);
+      if (quarter == 0) ATTN_TRACE(8 + 6 * t, k);
       mbar_wait_warp(&s_full[t], k & 1);
-      if (quarter == 0 && h == 0) ATTN_TRACE(9 + 6 * t, k);
+      if (quarter == 0) ATTN_TRACE(9 + 6 * t, k);
       tc_fence_after();
-      float sum = 0.f;
+      float inv_sum = 0.f;
       if (warp_live) {
-        // Three 32-column chunks per half (+ one 16-column chunk for half 0), fully unrolled,
-        // with the TMEM load of the next chunk in flight while the current one is processed.
-        uint32_t r[4][32];
-        // ---- pass 1: max over this half's valid keys, then exchange with the other half
+        // Both passes are fully unrolled with the TMEM load of chunk c+1 in flight while chunk c
+        // is processed (tcgen05.wait::ld waits for everything outstanding, so one load ahead).
+        uint32_t r[kFull + 1][32];
+        // ---- pass 1: row max over the valid keys
         float mx = -INFINITY;
-        tmem_ld_x32(t_row + s_col, r[0]);
+        tmem_ld_x32(t_row, r[0]);
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
+        for (int c = 0; c < kFull; ++c) {
           tmem_ld_wait();
-          if (c < 2) tmem_ld_x32(t_row + s_col + (c + 1) * 32, r[c + 1]);
-          else if (h == 0) tmem_ld_x16(t_row + 96, r[3]);
-          if (h == 0 || kSplitKeys + (c + 1) * 32 <= tokens) {
+          if (c + 1 < kFull) tmem_ld_x32(t_row + (c + 1) * 32, r[c + 1]);
+          else tmem_ld_x16(t_row + kFull * 32, r[kFull]);
+          if ((c + 1) * 32 <= tokens) {
 #pragma unroll
             for (int j = 0; j < 32; j += 2)
               mx = fmax3(mx, __uint_as_float(r[c][j]), __uint_as_float(r[c][j + 1]));
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (kSplitKeys + c * 32 + j < tokens) mx = fmaxf(mx, __uint_as_float(r[c][j]));
+              if (c * 32 + j < tokens) mx = fmaxf(mx, __uint_as_float(r[c][j]));
           }
         }
-        if (h == 0) {
-          tmem_ld_wait();
+        tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; j += 2)
-            mx = fmax3(mx, __uint_as_float(r[3][j]), __uint_as_float(r[3][j + 1]));
-        }
-        *my_max = mx;
-        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
-        mx = fmaxf(mx, *other_max);
-        if (quarter == 0 && h == 0) ATTN_TRACE(10 + 6 * t, k);
-        // ---- pass 2: p = exp2(s*c - max*c), partial row sum, P -> TMEM as packed bf16 pairs
+        for (int j = 0; j < 16; ++j)
+          if (kFull * 32 + j < tokens) mx = fmaxf(mx, __uint_as_float(r[kFull][j]));
+        if (quarter == 0) ATTN_TRACE(10 + 6 * t, k);
+        // ---- pass 2: p = exp2(s*c - max*c), row sum, P -> TMEM as packed bf16 pairs
         const float moff = mx * scale_log2e;
-        tmem_ld_x32(t_row + s_col, r[0]);
+        float sum = 0.f;
+        tmem_ld_x32(t_row, r[0]);
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
+        for (int c = 0; c < kFull; ++c) {
           tmem_ld_wait();
-          if (c < 2) tmem_ld_x32(t_row + s_col + (c + 1) * 32, r[c + 1]);
-          else if (h == 0) tmem_ld_x16(t_row + 96, r[3]);
+          if (c + 1 < kFull) tmem_ld_x32(t_row + (c + 1) * 32, r[c + 1]);
+          else tmem_ld_x16(t_row + kFull * 32, r[kFull]);
           uint32_t pk[16];
-          if (h == 0 || kSplitKeys + (c + 1) * 32 <= tokens) {
+          if ((c + 1) * 32 <= tokens) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const float e0 = fast_exp2(fmaf(__uint_as_float(r[c][2 * j]), scale_log2e, -moff));
@@ -540,50 +521,53 @@ attn_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             for (int j = 0; j < 16; ++j) {
               float e0 = fast_exp2(fmaf(__uint_as_float(r[c][2 * j]), scale_log2e, -moff));
               float e1 = fast_exp2(fmaf(__uint_as_float(r[c][2 * j + 1]), scale_log2e, -moff));
-              e0 = (kSplitKeys + c * 32 + 2 * j < tokens) ? e0 : 0.f;
-              e1 = (kSplitKeys + c * 32 + 2 * j + 1 < tokens) ? e1 : 0.f;
+              e0 = (c * 32 + 2 * j < tokens) ? e0 : 0.f;
+              e1 = (c * 32 + 2 * j + 1 < tokens) ? e1 : 0.f;
               sum += e0 + e1;
               pk[j] = pack_bf16x2(e0, e1);
             }
           }
-          // P chunk c -> 16 columns inside the S columns this thread has already consumed
-          tmem_st_x16(t_row + p_col + c * 16, pk);
+          // P chunk c -> columns [16c, 16c + 16): S columns this thread has already consumed
+          // (chunk c+1, in flight, lies above them)
+          tmem_st_x16(t_row + c * 16, pk);
         }
-        if (h == 0) {
+        {
           tmem_ld_wait();
           uint32_t pk[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float e0 = fast_exp2(fmaf(__uint_as_float(r[3][2 * j]), scale_log2e, -moff));
-            const float e1 = fast_exp2(fmaf(__uint_as_float(r[3][2 * j + 1]), scale_log2e, -moff));
+            float e0 = fast_exp2(fmaf(__uint_as_float(r[kFull][2 * j]), scale_log2e, -moff));
+            float e1 = fast_exp2(fmaf(__uint_as_float(r[kFull][2 * j + 1]), scale_log2e, -moff));
+            e0 = (kFull * 32 + 2 * j < tokens) ? e0 : 0.f;
+            e1 = (kFull * 32 + 2 * j + 1 < tokens) ? e1 : 0.f;
             sum += e0 + e1;
             pk[j] = pack_bf16x2(e0, e1);
           }
-          tmem_st_x8(t_row + 48, pk);
+          tmem_st_x8(t_row + kFull * 16, pk);
         }
         tmem_st_wait();
-        *my_sum = sum;  // read by the other half after o_full (ordered by the barrier chain)
+        inv_sum = 1.0f / sum;
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[t]);
-      if (quarter == 0 && h == 0) ATTN_TRACE(11 + 6 * t, k);
+      if (quarter == 0) ATTN_TRACE(11 + 6 * t, k);
 
       mbar_wait_warp(&o_full[t], k & 1);
-      if (quarter == 0 && h == 0) ATTN_TRACE(12 + 6 * t, k);
+      if (quarter == 0) ATTN_TRACE(12 + 6 * t, k);
       tc_fence_after();
       if (warp_live) {
-        const float inv_sum = 1.0f / (sum + *other_sum);
-        uint32_t r0[32];
-        tmem_ld_x32(t_row + Cfg::kOCols + h * 32, r0);   // this half's 32 output columns
+        uint32_t r0[32], r1[32];
+        tmem_ld_x32(t_row + Cfg::kOCols, r0);
+        tmem_ld_x32(t_row + Cfg::kOCols + 32, r1);
         tmem_ld_wait();
         // O is in registers: hand the tile's TMEM columns back BEFORE converting and storing
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&o_empty[t]);
         if (row < tokens) {
-          __nv_bfloat16* o = out + (static_cast<long long>(img) * tokens + row) * (heads * 64) +
-                             head * 64 + h * 32;
+          __nv_bfloat16* o =
+              out + (static_cast<long long>(img) * tokens + row) * (heads * 64) + head * 64;
           uint4* o4 = reinterpret_cast<uint4*>(o);
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
@@ -594,19 +578,28 @@ attn_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             v.w = pack_bf16x2(__uint_as_float(r0[8 * g + 6]) * inv_sum, __uint_as_float(r0[8 * g + 7]) * inv_sum);
             o4[g] = v;
           }
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 v;
+            v.x = pack_bf16x2(__uint_as_float(r1[8 * g]) * inv_sum, __uint_as_float(r1[8 * g + 1]) * inv_sum);
+            v.y = pack_bf16x2(__uint_as_float(r1[8 * g + 2]) * inv_sum, __uint_as_float(r1[8 * g + 3]) * inv_sum);
+            v.z = pack_bf16x2(__uint_as_float(r1[8 * g + 4]) * inv_sum, __uint_as_float(r1[8 * g + 5]) * inv_sum);
+            v.w = pack_bf16x2(__uint_as_float(r1[8 * g + 6]) * inv_sum, __uint_as_float(r1[8 * g + 7]) * inv_sum);
+            o4[4 + g] = v;
+          }
         }
       } else {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&o_empty[t]);
       }
-      if (quarter == 0 && h == 0) ATTN_TRACE(13 + 6 * t, k);
+      if (quarter == 0) ATTN_TRACE(13 + 6 * t, k);
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 16) {
+  if (warp == 8) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }

@@ -988,7 +988,7 @@ extern "C" int devit_gemm(const devit_gemm_args* a, void* stream_v) {
   // CTA pairs (cta_group::2, 256-row tiles) pay off once there are enough m-blocks
   // CTA pairs halve the weight-tile bytes each SM pulls through L2 (the binding resource at
   // K = 384); measured on B200 they win for every large-M shape except the short-K residual
-  // GEMM (proj), see profiles/r1_gemm_sweep_v6.txt
+  // GEMM (proj); sweeps in profiles/r1_gemm_sweep_*.txt, pipeline traces in profiles/r1_trace_qkv_*.txt
   int cl = a->cluster_m;
   const int total_k = [&] { int t = 0; for (int s = 0; s < a->num_segs; ++s) t += a->segs[s].k_len; return t; }();
   if (cl == 0) {

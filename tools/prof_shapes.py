@@ -1,4 +1,5 @@
-"""Micro-driver for ncu: launches each hot kernel at its bs-256 dedeit shape a few times.
+"""Micro-driver for ncu: launches each hot kernel at its bs-256 dedeit shape (shrunk widths:
+4 kept heads, 928 kept neurons; LayerNorm-folded epilogues as the forward uses them).
   ncu --set full -k regex:gemm_kernel ... python tools/prof_shapes.py gemm
 """
 import sys
@@ -9,9 +10,9 @@ import torch
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 from devit_b200 import _lib as L  # noqa: E402
 
-M, D = 256 * 198, 384
+M, D, H, F = 256 * 198, 384, 4, 928
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
-reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 dev = "cuda"
 g = torch.Generator(device=dev).manual_seed(0)
 
@@ -20,27 +21,34 @@ def rnd(*s, dt=torch.bfloat16, scale=1.0):
     return (torch.randn(*s, device=dev, generator=g) * scale).to(dt)
 
 
-y = rnd(M, D)
 x = rnd(M, D, dt=torch.float32)
+xb, stats1 = L.rowstats(x)
 if which in ("gemm", "all"):
-    w_qkv, b_qkv = rnd(1152, D, scale=.05), rnd(1152, dt=torch.float32)
-    w_proj, b_proj = rnd(D, D, scale=.05), rnd(D, dt=torch.float32)
-    w1, b1 = rnd(1536, D, scale=.05), rnd(1536, dt=torch.float32)
-    w2, b2 = rnd(D, 1536, scale=.05), rnd(D, dt=torch.float32)
-    qkv = torch.empty(M, 1152, device=dev, dtype=torch.bfloat16)
-    hid = torch.empty(M, 1536, device=dev, dtype=torch.bfloat16)
+    w_qkv, c1q, c2q = rnd(192 * H, D, scale=.05), rnd(192 * H, dt=torch.float32), rnd(192 * H, dt=torch.float32)
+    w_proj, b_proj = rnd(D, 64 * H, scale=.05), rnd(D, dt=torch.float32)
+    w1, c11, c21 = rnd(F, D, scale=.05), rnd(F, dt=torch.float32), rnd(F, dt=torch.float32)
+    w2, b2 = rnd(D, F, scale=.05), rnd(D, dt=torch.float32)
+    qkv = torch.empty(M, 192 * H, device=dev, dtype=torch.bfloat16)
+    o = rnd(M, 64 * H)
+    hid = torch.empty(M, F, device=dev, dtype=torch.bfloat16)
+    stats = torch.empty(6, M, 2, device=dev)
     for _ in range(reps):
-        L.gemm(y, w_qkv, bias=b_qkv, out=qkv, out_kind=L.OUT_BF16, tag=2)
-        L.gemm(y, w_proj, bias=b_proj, resid=x, out=x, out_kind=L.OUT_F32, tag=3)
-        L.gemm(y, w1, bias=b1, act=L.ACT_GELU_ERF, out=hid, out_kind=L.OUT_BF16, tag=4)
-        L.gemm(hid, w2, bias=b2, resid=x, out=x, out_kind=L.OUT_F32, tag=5)
+        L.gemm(xb, w_qkv, bias=c2q, out=qkv, out_kind=L.OUT_BF16, tag=2, ln_stats=stats1,
+               ln_colsum=c1q, ln_dim=D, ln_eps=1e-6)
+        L.gemm(o, w_proj, bias=b_proj, resid=x, out=x, out_kind=L.OUT_F32, tag=3, out_bf16=xb,
+               stats_out=stats)
+        L.gemm(xb, w1, bias=c21, act=L.ACT_GELU_ERF, out=hid, out_kind=L.OUT_BF16, tag=4,
+               ln_stats=stats, ln_colsum=c11, ln_dim=D, ln_eps=1e-6)
+        L.gemm(hid, w2, bias=b2, resid=x, out=x, out_kind=L.OUT_F32, tag=5, out_bf16=xb,
+               stats_out=stats)
 if which in ("attn", "all"):
-    qkv = rnd(M, 1152)
+    qkv = rnd(M, 192 * H)
     for _ in range(reps):
-        L.attention(qkv, 256, 198, 6, 0.125)
-if which in ("ln", "all"):
+        L.attention(qkv, 256, 198, H, 0.125)
+if which in ("rows", "all"):
     gam, bet = rnd(D, dt=torch.float32), rnd(D, dt=torch.float32)
     for _ in range(reps):
+        L.rowstats(x)
         L.layernorm(x, gam, bet, 1e-6, L.OUT_BF16)
 torch.cuda.synchronize()
 print("done")

@@ -66,6 +66,16 @@ class LayerDesc(C.Structure):
     ]
 
 
+class MlpArgs(C.Structure):
+    _fields_ = [
+        ("m", C.c_int32), ("dim", C.c_int32), ("hidden_ld", C.c_int32),
+        ("xb", C.c_void_p), ("w1", C.c_void_p), ("c1", C.c_void_p), ("c2", C.c_void_p),
+        ("ln_stats", C.c_void_p), ("ln_parts", C.c_int32), ("ln_eps", C.c_float),
+        ("w2", C.c_void_p), ("b2", C.c_void_p), ("x", C.c_void_p), ("xb_out", C.c_void_p),
+        ("stats_out", C.c_void_p),
+    ]
+
+
 class VitDesc(C.Structure):
     _fields_ = [
         ("precision", C.c_int32), ("dim", C.c_int32), ("depth", C.c_int32),
@@ -91,6 +101,7 @@ _SIGS = {
     "devit_debug_set_trace": (C.c_int, [C.c_void_p]),
     "devit_layernorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                   C.c_int32, C.c_float, C.c_int32, C.c_int64, C.c_void_p]),
+    "devit_mlp_fused": (C.c_int, [C.POINTER(MlpArgs), C.c_void_p]),
     "devit_rowstats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                                  C.c_void_p]),
     "devit_attention": (C.c_int, [C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
@@ -258,6 +269,18 @@ def rowstats(x):
     stats = torch.empty(1, rows, 2, device=x.device, dtype=torch.float32)
     check(load().devit_rowstats(ptr(x), ptr(xb), ptr(stats), rows, dim, stream_ptr()))
     return xb, stats
+
+
+def mlp_fused(x, xb, ln_stats, w1, c1, c2, w2, b2, eps, xb_out=None, stats_out=None):
+    """In-place x += gelu(LN(x) W1^T + b1) W2^T + b2 (LayerNorm folded); see devit_mlp_fused."""
+    a = MlpArgs()
+    a.m, a.dim, a.hidden_ld = x.shape[0], x.shape[1], w1.shape[0]
+    a.xb, a.w1, a.c1, a.c2 = ptr(xb), ptr(w1), ptr(c1), ptr(c2)
+    a.ln_stats, a.ln_parts, a.ln_eps = ptr(ln_stats), ln_stats.shape[0], eps
+    a.w2, a.b2, a.x = ptr(w2), ptr(b2), ptr(x)
+    a.xb_out, a.stats_out = ptr(xb_out), ptr(stats_out)
+    check(load().devit_mlp_fused(C.byref(a), stream_ptr()))
+    return x
 
 
 def layernorm(x, gamma, beta, eps, out_kind=OUT_BF16):

@@ -165,6 +165,11 @@ extern "C" int devit_vit_forward(const devit_vit_desc* d, const float* images, i
   DEVIT_REQUIRE(!fold || (prec == DEVIT_BF16 && D % 128 == 0 && L.stat_parts <= 6),
                 "devit_vit_forward: LayerNorm-folded weights need DEVIT_BF16 and dim in {128, 256, "
                 "384} (got dim %d)", D);
+  static int fused_mlp = -1;  // DEVIT_FUSED_MLP=0: separate fc1 / fc2 GEMMs (comparison)
+  if (fused_mlp < 0) {
+    const char* e = getenv("DEVIT_FUSED_MLP");
+    fused_mlp = (e && e[0] == '0') ? 0 : 1;
+  }
   float* stats = reinterpret_cast<float*>(ws + L.off_stats);
   int parts = 1;
   if (fold && nl > 0) {
@@ -224,8 +229,22 @@ extern "C" int devit_vit_forward(const devit_vit_desc* d, const float* images, i
       rc = devit_layernorm(x, w.ln2_g, w.ln2_b, y, M, D, d->ln_eps, opk, M * D, stream);
       if (rc) return rc;
     }
-    // hid = gelu(y W1^T + b1), kept neurons only                 (:36-37)
     const int F = w.hidden_ld;
+    if (fold && fused_mlp && D == 384) {
+      // x += gelu(LN2(x) W1^T + b1) W2^T + b2 in one kernel, hidden kept on chip   (:35-47, :115)
+      devit_mlp_args ma;
+      std::memset(&ma, 0, sizeof(ma));
+      ma.m = static_cast<int>(M); ma.dim = D; ma.hidden_ld = F;
+      ma.xb = y; ma.w1 = w.w_fc1; ma.c1 = w.cs_fc1; ma.c2 = w.b_fc1;
+      ma.ln_stats = stats; ma.ln_parts = parts; ma.ln_eps = d->ln_eps;
+      ma.w2 = w.w_fc2; ma.b2 = w.b_fc2; ma.x = x;
+      if (l + 1 < nl) { ma.xb_out = y; ma.stats_out = stats; }
+      rc = devit_mlp_fused(&ma, stream);
+      if (rc) return rc;
+      if ((rc = sync_debug("fused mlp", l, stream))) return rc;
+      continue;
+    }
+    // hid = gelu(y W1^T + b1), kept neurons only                 (:36-37)
     base_gemm(&g, prec);
     g.m = static_cast<int>(M); g.n = F;
     g.a = y; g.a_rows = static_cast<int>(M); g.a_cols = D; g.lda = D; g.a_plane_stride = M * D;

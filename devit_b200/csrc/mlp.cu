@@ -1,0 +1,464 @@
+// Fused MLP block of one transformer layer (include/devit_b200.h, devit_mlp_fused):
+//     x += gelu( LN(x) W1^T + b1 ) W2^T + b2            models/de_vit.py:35-47 + :115
+// as ONE kernel: the hidden activation never leaves the SM pair.
+//
+// A CTA pair (cta_group::2) owns 256 token rows.  Per pair-tile:
+//   * TMA loads the bf16 copy of the residual stream for its rows once (Y, 128 x 384 per CTA,
+//     K-major, 128B swizzle) and streams W1 / W2 in 64-neuron chunks through two 2-slot rings;
+//     each CTA stages HALF of every weight chunk (the pair's MMA reads both halves).
+//   * GEMM1 chunk c: acc1[c&1] (128 x 64 fp32 per CTA, TMEM columns 384 + 64 (c&1)) = Y W1_c^T.
+//   * 8 epilogue warps turn acc1 into H_c = gelu(rstd (acc - mean c1) + c2)  (LayerNorm folded
+//     into the epilogue, see devit_gemm_args.ln_stats) and write it back INTO TMEM as packed
+//     bf16 pairs over columns they have already consumed.
+//   * GEMM2 chunk c: acc2 (128 x 384 fp32, TMEM columns [0, 384)) += H_c W2_c^T with the A operand
+//     read from tensor memory (two N = 192 UMMAs per K = 16 step).  GEMM1 of chunk c+1 is issued
+//     before GEMM2 of chunk c, so the tensor pipe works while the GELU of chunk c runs.
+//   * Final epilogue: acc2 + b2 + residual -> x (fp32, through shared-memory slots carved out of
+//     the dead Y buffer, residual TMA-prefetched as soon as the last GEMM1 retired), plus the
+//     bf16 copy and the partial row sums the next layer's LayerNorm-folded QKV GEMM consumes.
+// TMEM: 384 + 2 x 64 = 512 columns.  smem: Y 96 KB + W1 ring 48 KB + W2 ring 48 KB.
+#include <cstdlib>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace devit {
+
+constexpr int kMlpDim = 384;
+constexpr int kMlpThreads = 11 * 32;  // 0: Y+W1 loads, 1: MMA, 2..9: epilogue, 10: W2 loads
+constexpr int kYBytes = 6 * 16384;    // 6 K-atoms of [128 rows x 128 B]
+constexpr int kW1Slot = 6 * 4096;     // 6 K-atoms of [32 rows x 128 B]  (this CTA's half chunk)
+constexpr int kW2Slot = 2 * 12288;    // 2 N-halves of [96 rows x 128 B]
+constexpr int kOffW1 = kYBytes;
+constexpr int kOffW2 = kOffW1 + 2 * kW1Slot;
+constexpr int kOffBarM = kOffW2 + 2 * kW2Slot;
+constexpr int kMlpSmem = kOffBarM + 64 * 8 + 1024;
+constexpr int kAcc1Col = 384;
+
+struct MlpParams {
+  int M, F_ld, num_chunks;
+  const float* c1;
+  const float* c2;
+  const float* b2;
+  const float* ln_stats;
+  int ln_parts;
+  float ln_inv_dim, ln_eps;
+  __nv_bfloat16* xb_out;
+  float* stats_out;
+};
+
+__device__ __forceinline__ void umma_bf16_ts_cg2(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
+                                                 uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ int mlp_off(int r, int j) { return r * 128 + ((j ^ (r & 7)) << 4); }
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1)
+mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmW1,
+                 const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmX,
+                 const __grid_constant__ MlpParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBarM);
+  uint64_t* y_full = bars + 0;
+  uint64_t* y_empty = bars + 1;     // last GEMM1 of the tile retired (Y is dead)
+  uint64_t* y_free = bars + 2;      // final epilogue done with the Y-buffer slots (8 arrivals)
+  uint64_t* w1_full = bars + 3;     // [2]
+  uint64_t* w1_empty = bars + 5;    // [2]
+  uint64_t* w2_full = bars + 7;     // [2]
+  uint64_t* w2_empty = bars + 9;    // [2]
+  uint64_t* acc1_full = bars + 11;  // [2]
+  uint64_t* h_ready = bars + 13;    // [2]  (leader: 16 warp arrivals)
+  uint64_t* acc2_full = bars + 15;
+  uint64_t* acc2_empty = bars + 16;  // (leader: 16 warp arrivals)
+  uint64_t* rfull = bars + 17;       // [8 warps][3 slots]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 41);
+
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int cta_rank = __shfl_sync(0xffffffffu, static_cast<int>(cluster_ctarank()), 0);
+  const bool leader = cta_rank == 0;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+  const int num_pairs = (p.M + 255) / 256;
+  const int NC = p.num_chunks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmY);
+    tma_prefetch_desc(&tmW1);
+    tma_prefetch_desc(&tmW2);
+    tma_prefetch_desc(&tmX);
+    mbar_init(y_full, 1);
+    mbar_init(y_empty, 1);
+    mbar_init(y_free, 8);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&w1_full[i], 1);
+      mbar_init(&w1_empty[i], 1);
+      mbar_init(&w2_full[i], 1);
+      mbar_init(&w2_empty[i], 1);
+      mbar_init(&acc1_full[i], 1);
+      mbar_init(&h_ready[i], 16);
+    }
+    mbar_init(acc2_full, 1);
+    mbar_init(acc2_empty, 16);
+    for (int i = 0; i < 24; ++i) mbar_init(&rfull[i], 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_cg2(tmem_slot, 512);
+    tmem_relinquish_cg2();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+  // width of chunk c (multiple of 16; only the last chunk can be narrower than 64)
+  auto chunk_n = [&](int c) -> int {
+    const int n = p.F_ld - c * 64;
+    return n < 64 ? n : 64;
+  };
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ loads: Y and the W1 ring
+    uint32_t g1 = 0;
+    int it = 0;
+    for (int pt = cluster_id; pt < num_pairs; pt += num_clusters, ++it) {
+      const int m0 = (pt * 2 + cta_rank) * 128;
+      if (it >= 1) mbar_wait_warp(y_free, (it - 1) & 1);
+      if (elect_one()) {
+        const uint32_t bar = mapa_u32(smem_u32(y_full), 0);
+        if (leader) mbar_expect_tx(y_full, 2 * kYBytes);
+#pragma unroll
+        for (int a = 0; a < 6; ++a) tma_load_2d_cg2(smem + a * 16384, &tmY, bar, a * 64, m0);
+      }
+      for (int c = 0; c < NC; ++c, ++g1) {
+        const int s = g1 & 1;
+        mbar_wait_warp(&w1_empty[s], ((g1 >> 1) & 1) ^ 1);
+        if (elect_one()) {
+          const uint32_t bar = mapa_u32(smem_u32(&w1_full[s]), 0);
+          if (leader) mbar_expect_tx(&w1_full[s], 2 * kW1Slot);
+          const int row0 = c * 64 + cta_rank * (chunk_n(c) / 2);
+          uint8_t* dst = smem + kOffW1 + s * kW1Slot;
+#pragma unroll
+          for (int a = 0; a < 6; ++a) tma_load_2d_cg2(dst + a * 4096, &tmW1, bar, a * 64, row0);
+        }
+      }
+    }
+  } else if (warp == 10) {
+    // ------------------------------------------------------------ loads: the W2 ring
+    uint32_t g2 = 0;
+    for (int pt = cluster_id; pt < num_pairs; pt += num_clusters) {
+      for (int c = 0; c < NC; ++c, ++g2) {
+        const int s = g2 & 1;
+        mbar_wait_warp(&w2_empty[s], ((g2 >> 1) & 1) ^ 1);
+        if (elect_one()) {
+          const uint32_t bar = mapa_u32(smem_u32(&w2_full[s]), 0);
+          if (leader) mbar_expect_tx(&w2_full[s], 2 * kW2Slot);
+          uint8_t* dst = smem + kOffW2 + s * kW2Slot;
+          // output columns [192 hh + 96 rank, +96) of W2, K = neurons [64c, 64c + 64)
+          tma_load_2d_cg2(dst, &tmW2, bar, c * 64, cta_rank * 96);
+          tma_load_2d_cg2(dst + 12288, &tmW2, bar, c * 64, 192 + cta_rank * 96);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issue (leader only)
+    if (leader) {
+      uint32_t g1 = 0, g2 = 0;
+      int it = 0;
+      const uint32_t idesc2 = make_idesc(kFmtBF16, 256, 192, 0, 0);
+      auto gemm2 = [&](int cc, bool first_of_tile) {
+        const int b = g2 & 1;
+        const uint32_t par = (g2 >> 1) & 1;
+        mbar_wait_warp(&h_ready[b], par);
+        mbar_wait_warp(&w2_full[b], par);
+        if (first_of_tile && it >= 1) mbar_wait_warp(acc2_empty, (it - 1) & 1);
+        tc_fence_after();
+        const uint32_t sw = smem_u32(smem + kOffW2 + b * kW2Slot);
+        const int ksteps = chunk_n(cc) / 16;
+        if (elect_one()) {
+          for (int j = 0; j < ksteps; ++j) {
+            // H of neurons [0,32) of the chunk sits in columns [0,16), of [32,64) in [48,64)
+            const uint32_t a_t = tmem_base + kAcc1Col + 64 * b + (j < 2 ? 8 * j : 48 + 8 * (j - 2));
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              const uint64_t db = make_sw128_desc(sw + hh * 12288, 1024, 16) + 2 * j;
+              umma_bf16_ts_cg2(tmem_base + 192 * hh, a_t, db, idesc2,
+                               (first_of_tile && j == 0) ? 0u : 1u);
+            }
+          }
+          umma_commit_cg2(&w2_empty[b], 3);
+        }
+        ++g2;
+      };
+      for (int pt = cluster_id; pt < num_pairs; pt += num_clusters, ++it) {
+        mbar_wait_warp(y_full, it & 1);
+        for (int c = 0; c < NC; ++c) {
+          const int s = g1 & 1;
+          mbar_wait_warp(&w1_full[s], (g1 >> 1) & 1);
+          tc_fence_after();
+          const uint32_t idesc1 = make_idesc(kFmtBF16, 256, chunk_n(c), 0, 0);
+          const uint32_t sy = smem_u32(smem);
+          const uint32_t sw = smem_u32(smem + kOffW1 + s * kW1Slot);
+          if (elect_one()) {
+#pragma unroll
+            for (int a = 0; a < 6; ++a) {
+              const uint64_t da = make_sw128_desc(sy + a * 16384, 1024, 16);
+              const uint64_t db = make_sw128_desc(sw + a * 4096, 1024, 16);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16_cg2(tmem_base + kAcc1Col + 64 * s, da + 2 * k, db + 2 * k, idesc1,
+                              (a | k) ? 1u : 0u);
+            }
+            umma_commit_cg2(&w1_empty[s], 3);
+            umma_commit_cg2(&acc1_full[s], 3);
+            if (c == NC - 1) umma_commit_cg2(y_empty, 3);
+          }
+          ++g1;
+          if (c >= 1) gemm2(c - 1, c == 1);
+        }
+        gemm2(NC - 1, NC == 1);
+        if (elect_one()) umma_commit_cg2(acc2_full, 3);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue warps
+    const int ew = warp - 2;
+    const int quarter = warp & 3;  // TMEM lane quarter
+    const int half = ew >> 2;
+    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    uint8_t* slots = smem + ew * (3 * 4096);  // final-epilogue slots inside the Y buffer
+    uint64_t* rbar = rfull + ew * 3;
+    const uint32_t h_ready_leader0 = mapa_u32(smem_u32(&h_ready[0]), 0);
+    const uint32_t h_ready_leader1 = mapa_u32(smem_u32(&h_ready[1]), 0);
+    const uint32_t acc2_empty_leader = mapa_u32(smem_u32(acc2_empty), 0);
+    uint32_t ecnt = 0, rphase = 0;
+    int it = 0;
+    for (int pt = cluster_id; pt < num_pairs; pt += num_clusters, ++it) {
+      const int m0 = (pt * 2 + cta_rank) * 128;
+      const int row0 = m0 + quarter * 32;
+      const int row = row0 + lane;
+      // ---- this row's LayerNorm statistics (folded into the fc1 epilogue)
+      float rstd, nmr;
+      {
+        float s1 = 0.f, s2 = 0.f;
+        if (row < p.M) {
+          for (int q = 0; q < p.ln_parts; ++q) {
+            const float2 t = __ldg(reinterpret_cast<const float2*>(p.ln_stats) +
+                                   static_cast<long long>(q) * p.M + row);
+            s1 += t.x;
+            s2 += t.y;
+          }
+        }
+        const float mean = s1 * p.ln_inv_dim;
+        const float var = fmaxf(fmaf(s2, p.ln_inv_dim, -mean * mean), 0.f);
+        rstd = rsqrtf(var + p.ln_eps);
+        nmr = -rstd * mean;
+      }
+      // ---- hidden chunks: acc1 -> H (bf16, in TMEM)
+      for (int c = 0; c < NC; ++c, ++ecnt) {
+        const int b = ecnt & 1;
+        mbar_wait_warp(&acc1_full[b], (ecnt >> 1) & 1);
+        tc_fence_after();
+        if (c == NC - 1) {
+          // the last GEMM1 has retired: Y is dead, start fetching the residual into its slots
+          if (elect_one()) {
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+              mbar_expect_tx(&rbar[s], 4096);
+              tma_load_2d(slots + s * 4096, &tmX, &rbar[s], half * 192 + s * 32, row0);
+            }
+          }
+        }
+        const uint32_t t_acc = tmem_base + lane_off + kAcc1Col + 64 * b;
+        uint32_t r[32];
+        tmem_ld_x32(t_acc + 32 * half, r);
+        tmem_ld_wait();
+        const int col0 = c * 64 + 32 * half;
+        uint32_t pk[16];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          float4 cs = make_float4(0.f, 0.f, 0.f, 0.f), bs = cs;
+          if (col0 + 4 * g < p.F_ld) {
+            cs = __ldg(reinterpret_cast<const float4*>(p.c1 + col0) + g);
+            bs = __ldg(reinterpret_cast<const float4*>(p.c2 + col0) + g);
+          }
+          const float v0 = gelu_erf_fast(fmaf(rstd, __uint_as_float(r[4 * g]), fmaf(nmr, cs.x, bs.x)));
+          const float v1 = gelu_erf_fast(fmaf(rstd, __uint_as_float(r[4 * g + 1]), fmaf(nmr, cs.y, bs.y)));
+          const float v2 = gelu_erf_fast(fmaf(rstd, __uint_as_float(r[4 * g + 2]), fmaf(nmr, cs.z, bs.z)));
+          const float v3 = gelu_erf_fast(fmaf(rstd, __uint_as_float(r[4 * g + 3]), fmaf(nmr, cs.w, bs.w)));
+          pk[2 * g] = pack_bf16x2(v0, v1);
+          pk[2 * g + 1] = pack_bf16x2(v2, v3);
+        }
+        // half 0: neurons [0,32) -> columns [0,16); half 1: neurons [32,64) -> columns [48,64)
+        tmem_st_x16(t_acc + (half ? 48 : 0), pk);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (leader) mbar_arrive(&h_ready[b]);
+          else mbar_arrive_cluster(b ? h_ready_leader1 : h_ready_leader0);
+        }
+      }
+      // ---- final epilogue: x += acc2 + b2, bf16 copy, partial row sums
+      mbar_wait_warp(acc2_full, it & 1);
+      tc_fence_after();
+      float st1 = 0.f, st2 = 0.f;
+#pragma unroll 1
+      for (int j = 0; j < 6; ++j) {
+        const int s = j % 3;
+        const int col0 = half * 192 + j * 32;
+        uint32_t r[32];
+        tmem_ld_x32(tmem_base + lane_off + col0, r);
+        tmem_ld_wait();
+        float* v = reinterpret_cast<float*>(r);
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(p.b2 + col0) + g);
+          v[4 * g] += t.x; v[4 * g + 1] += t.y; v[4 * g + 2] += t.z; v[4 * g + 3] += t.w;
+        }
+        mbar_wait_warp(&rbar[s], (rphase >> s) & 1u);
+        rphase ^= 1u << s;
+        uint8_t* bsl = slots + s * 4096;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const float4 t = *reinterpret_cast<const float4*>(bsl + mlp_off(lane, g));
+          v[4 * g] += t.x; v[4 * g + 1] += t.y; v[4 * g + 2] += t.z; v[4 * g + 3] += t.w;
+        }
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          *reinterpret_cast<float4*>(bsl + mlp_off(lane, g)) =
+              make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+        fence_proxy_async_smem();
+        if (elect_one()) {
+          tma_store_2d(&tmX, bsl, col0, row0);
+          bulk_commit();
+          if (j < 3) {
+            // refill this slot with the residual of chunk j + 3 once the store has read it
+            bulk_wait_read<0>();
+            mbar_expect_tx(&rbar[s], 4096);
+            tma_load_2d(bsl, &tmX, &rbar[s], col0 + 96, row0);
+          }
+        }
+        __syncwarp();
+        if (p.xb_out && row < p.M) {
+          uint4* o = reinterpret_cast<uint4*>(p.xb_out + static_cast<long long>(row) * kMlpDim + col0);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 t;
+            t.x = pack_bf16x2(v[8 * g], v[8 * g + 1]);
+            t.y = pack_bf16x2(v[8 * g + 2], v[8 * g + 3]);
+            t.z = pack_bf16x2(v[8 * g + 4], v[8 * g + 5]);
+            t.w = pack_bf16x2(v[8 * g + 6], v[8 * g + 7]);
+            o[g] = t;
+          }
+        }
+        if (p.stats_out) {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) {
+            st1 += v[k];
+            st2 = fmaf(v[k], v[k], st2);
+          }
+          if (j & 1) {  // a 64-column part is complete: part index = (192 half + 32 (j-1)) / 64
+            if (row < p.M)
+              reinterpret_cast<float2*>(p.stats_out)[static_cast<long long>(3 * half + (j >> 1)) * p.M + row] =
+                  make_float2(st1, st2);
+            st1 = 0.f;
+            st2 = 0.f;
+          }
+        }
+      }
+      // acc2 has been read: release it; the Y buffer is free once our stores have drained it
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(acc2_empty);
+        else mbar_arrive_cluster(acc2_empty_leader);
+      }
+      if (elect_one()) {
+        bulk_wait_read<0>();
+        mbar_arrive(y_free);
+      }
+      __syncwarp();
+    }
+    if (elect_one()) bulk_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_cg2(tmem_base, 512);
+  }
+}
+
+}  // namespace devit
+
+using namespace devit;
+
+extern "C" int devit_mlp_fused(const devit_mlp_args* a, void* stream_v) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  DEVIT_REQUIRE(a != nullptr, "devit_mlp_fused: null args");
+  int rc = check_device();
+  if (rc) return rc;
+  DEVIT_REQUIRE(a->dim == kMlpDim, "devit_mlp_fused: dim %d unsupported (built for 384)", a->dim);
+  DEVIT_REQUIRE(a->m > 0 && a->hidden_ld >= 16 && a->hidden_ld % 16 == 0,
+                "devit_mlp_fused: need m > 0 and hidden_ld a positive multiple of 16");
+  DEVIT_REQUIRE(a->xb && a->w1 && a->c1 && a->c2 && a->w2 && a->b2 && a->x && a->ln_stats,
+                "devit_mlp_fused: null pointer");
+  DEVIT_REQUIRE(a->ln_parts >= 1, "devit_mlp_fused: ln_parts must be >= 1");
+  DEVIT_REQUIRE(reinterpret_cast<uintptr_t>(a->c1) % 16 == 0 &&
+                    reinterpret_cast<uintptr_t>(a->c2) % 16 == 0 &&
+                    reinterpret_cast<uintptr_t>(a->b2) % 16 == 0 &&
+                    (!a->xb_out || reinterpret_cast<uintptr_t>(a->xb_out) % 16 == 0),
+                "devit_mlp_fused: c1 / c2 / b2 / xb_out must be 16-byte aligned");
+  static bool attr_done[64] = {};
+  int dev = 0;
+  DEVIT_CUDA_OK(cudaGetDevice(&dev));
+  if (!attr_done[dev & 63]) {
+    DEVIT_CUDA_OK(cudaFuncSetAttribute(mlp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       kMlpSmem));
+    attr_done[dev & 63] = true;
+  }
+  CUtensorMap tY, tW1, tW2, tX;
+  rc = encode_tmap_2d(&tY, a->xb, 2, kMlpDim, a->m, kMlpDim, 64, 128, false);
+  if (rc) return rc;
+  rc = encode_tmap_2d(&tW1, a->w1, 2, kMlpDim, a->hidden_ld, kMlpDim, 64, 32, true);
+  if (rc) return rc;
+  rc = encode_tmap_2d(&tW2, a->w2, 2, a->hidden_ld, kMlpDim, a->hidden_ld, 64, 96, true);
+  if (rc) return rc;
+  rc = encode_tmap_2d(&tX, a->x, 4, kMlpDim, a->m, kMlpDim, 32, 32, false);
+  if (rc) return rc;
+  MlpParams p;
+  p.M = a->m;
+  p.F_ld = a->hidden_ld;
+  p.num_chunks = (a->hidden_ld + 63) / 64;
+  p.c1 = a->c1;
+  p.c2 = a->c2;
+  p.b2 = a->b2;
+  p.ln_stats = a->ln_stats;
+  p.ln_parts = a->ln_parts;
+  p.ln_inv_dim = 1.0f / static_cast<float>(kMlpDim);
+  p.ln_eps = a->ln_eps;
+  p.xb_out = static_cast<__nv_bfloat16*>(a->xb_out);
+  p.stats_out = a->stats_out;
+  const int num_pairs = (a->m + 255) / 256;
+  int clusters = num_sms() / 2;
+  if (clusters > num_pairs) clusters = num_pairs;
+  {
+    ProfScope ps(kTagGemmFc2, stream);
+    mlp_fused_kernel<<<clusters * 2, kMlpThreads, kMlpSmem, stream>>>(tY, tW1, tW2, tX, p);
+  }
+  DEVIT_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return DEVIT_OK;
+}

@@ -169,6 +169,38 @@ int devit_layernorm(const float* x, const float* gamma, const float* beta, void*
                     int64_t out_plane_stride, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * devit_mlp_fused:  x += gelu( LN(x) W1^T + b1 ) W2^T + b2   as ONE kernel (DEVIT_BF16, dim 384).
+ * Replaces norm2 + Mlp.forward + the residual add, models/de_vit.py:35-47 and :115: fc1, the
+ * erf-GELU, the (compacted) neuron gate and fc2 run per CTA pair on 256 token rows with the
+ * hidden activation kept in tensor memory, so the [rows, hidden] tensor never exists in HBM.
+ * LayerNorm is folded exactly as in devit_gemm_args.ln_stats: `xb` is the bf16 copy of the fp32
+ * residual stream `x`, `w1` holds gamma-folded weights [hidden_ld, dim], `c1` / `c2` the column
+ * sums / folded bias [hidden_ld] (zero beyond the kept neurons), `ln_stats` the partial row sums
+ * [ln_parts][m][2].  `w2` is [dim, hidden_ld] (zero columns beyond the kept neurons).
+ * Outputs: x (fp32, in place), optionally the bf16 copy of the new x (`xb_out`, may alias `xb`)
+ * and its partial row sums `stats_out` [6][m][2] (one part per 64 columns) for the next layer.
+ * ------------------------------------------------------------------------------------- */
+typedef struct devit_mlp_args {
+  int32_t m;
+  int32_t dim;       /* must be 384 */
+  int32_t hidden_ld; /* kept neurons rounded up to a multiple of 16 */
+  const void* xb;
+  const void* w1;
+  const float* c1;
+  const float* c2;
+  const float* ln_stats;
+  int32_t ln_parts;
+  float ln_eps;
+  const void* w2;
+  const float* b2;
+  float* x;
+  void* xb_out;
+  float* stats_out;
+} devit_mlp_args;
+
+int devit_mlp_fused(const devit_mlp_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * devit_rowstats: xb[r, :] = bf16(x[r, :]) and stats[r] = (sum_k x[r,k], sum_k x[r,k]^2): the
  * one-part input of a LayerNorm-folded GEMM (see devit_gemm_args.ln_stats) for a residual
  * stream that was not produced by a devit_gemm (the token embedding, models/de_vit.py:258-264).

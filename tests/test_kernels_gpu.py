@@ -125,6 +125,39 @@ def test_gemm_ln_fold_consumer(m, n, parts, act):
     assert rel(out, ref) < 2.0 * rel(base, ref) + 2e-3, (rel(out, ref), rel(base, ref))
 
 
+@pytest.mark.parametrize("m", [200, 520, 256 * 160 + 9])
+@pytest.mark.parametrize("f", [16, 64, 80, 928, 1536])
+def test_mlp_fused(m, f):
+    """x += gelu(LN(x) W1^T + b1) W2^T + b2 in one kernel (LayerNorm folded, hidden in TMEM)
+    against LayerNorm + Linear + exact-erf GELU + Linear in fp32; also the bf16 copy and the
+    partial row sums it emits for the next layer."""
+    d, eps = 384, 1e-6
+    x0 = _mk((m, d), 51) * 1.5 + _mk((1, d), 52) * 0.5
+    gamma = 1.0 + 0.1 * _mk((d,), 53)
+    beta = 0.1 * _mk((d,), 54)
+    w1 = _mk((f, d), 55, 0.05)
+    b1 = _mk((f,), 56, 0.1)
+    w2 = _mk((d, f), 57, 0.05)
+    b2 = _mk((d,), 58, 0.1)
+    w1f = (w1 * gamma[None, :]).bfloat16()
+    c1 = w1f.float().sum(1).contiguous()
+    c2 = (b1 + w1 @ beta).contiguous()
+    xb, stats = L.rowstats(x0)
+    x = x0.clone()
+    xb_out = torch.zeros(m, d, device="cuda", dtype=torch.bfloat16)
+    stats_out = torch.full((6, m, 2), -1.0, device="cuda")
+    L.mlp_fused(x, xb, stats, w1f, c1, c2, w2.bfloat16().contiguous(), b2, eps, xb_out=xb_out,
+                stats_out=stats_out)
+    torch.cuda.synchronize()
+    h = torch.nn.functional.gelu(torch.nn.functional.layer_norm(x0, (d,), gamma, beta, eps) @ w1.t() + b1)
+    ref = x0 + h @ w2.t() + b2
+    assert rel(x - x0, ref - x0) < 1.5e-2, rel(x - x0, ref - x0)
+    assert torch.equal(xb_out, x.bfloat16())
+    cols = x.view(m, 6, 64)
+    assert rel(stats_out[..., 0].t(), cols.sum(-1)) < 1e-5
+    assert rel(stats_out[..., 1].t(), (cols * cols).sum(-1)) < 1e-5
+
+
 @pytest.mark.parametrize("cl", [1, 2])
 @pytest.mark.parametrize("bn", [128, 192, 256])
 def test_gemm_cta_pair(cl, bn):

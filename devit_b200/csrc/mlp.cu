@@ -25,7 +25,12 @@
 namespace devit {
 
 constexpr int kMlpDim = 384;
-constexpr int kMlpThreads = 11 * 32;  // 0: Y+W1 loads, 1: MMA, 2..9: epilogue, 10: W2 loads
+// warps: 0 = Y + W1 loads, 1 = MMA issue, 2..17 = epilogue (four per TMEM lane quarter: every
+// hidden chunk is split 4 x 16 columns, because GEMM1 of chunk c+1 has to wait for the GELU of
+// chunk c-1 -- two accumulator buffers -- so the GELU LATENCY of a chunk is what bounds the loop;
+// the first two warps of each quarter also run the final epilogue), 18 = W2 loads
+constexpr int kMlpThreads = 19 * 32;
+constexpr int kW2Warp = 18;
 constexpr int kYBytes = 6 * 16384;    // 6 K-atoms of [128 rows x 128 B]
 constexpr int kW1Slot = 6 * 4096;     // 6 K-atoms of [32 rows x 128 B]  (this CTA's half chunk)
 constexpr int kW2Slot = 2 * 12288;    // 2 N-halves of [96 rows x 128 B]
@@ -35,7 +40,19 @@ constexpr int kOffBarM = kOffW2 + 2 * kW2Slot;
 constexpr int kMlpSmem = kOffBarM + 64 * 8 + 1024;
 constexpr int kAcc1Col = 384;
 
+extern long long* g_attn_trace;  // devit_debug_set_trace buffer (shared)
+#ifdef DEVIT_GEMM_TRACE
+#define MLP_TRACE(slot_, idx_)                                                          \
+  do {                                                                                  \
+    if (p.trace && blockIdx.x == 0 && lane == 0 && (idx_) < 512)                        \
+      p.trace[(slot_) * 512 + (idx_)] = clock64();                                      \
+  } while (0)
+#else
+#define MLP_TRACE(slot_, idx_) do { } while (0)
+#endif
+
 struct MlpParams {
+  long long* trace;
   int M, F_ld, num_chunks;
   const float* c1;
   const float* c2;
@@ -74,7 +91,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
   uint64_t* w2_full = bars + 7;     // [2]
   uint64_t* w2_empty = bars + 9;    // [2]
   uint64_t* acc1_full = bars + 11;  // [2]
-  uint64_t* h_ready = bars + 13;    // [2]  (leader: 16 warp arrivals)
+  uint64_t* h_ready = bars + 13;    // [2]  (leader: 32 warp arrivals)
   uint64_t* acc2_full = bars + 15;
   uint64_t* acc2_empty = bars + 16;  // (leader: 16 warp arrivals)
   uint64_t* rfull = bars + 17;       // [8 warps][3 slots]
@@ -103,7 +120,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
       mbar_init(&w2_full[i], 1);
       mbar_init(&w2_empty[i], 1);
       mbar_init(&acc1_full[i], 1);
-      mbar_init(&h_ready[i], 16);
+      mbar_init(&h_ready[i], 32);
     }
     mbar_init(acc2_full, 1);
     mbar_init(acc2_empty, 16);
@@ -152,7 +169,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         }
       }
     }
-  } else if (warp == 10) {
+  } else if (warp == kW2Warp) {
     // ------------------------------------------------------------ loads: the W2 ring
     uint32_t g2 = 0;
     for (int pt = cluster_id; pt < num_pairs; pt += num_clusters) {
@@ -178,16 +195,19 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
       auto gemm2 = [&](int cc, bool first_of_tile) {
         const int b = g2 & 1;
         const uint32_t par = (g2 >> 1) & 1;
+        MLP_TRACE(3, g2);
         mbar_wait_warp(&h_ready[b], par);
+        MLP_TRACE(4, g2);
         mbar_wait_warp(&w2_full[b], par);
+        MLP_TRACE(5, g2);
         if (first_of_tile && it >= 1) mbar_wait_warp(acc2_empty, (it - 1) & 1);
         tc_fence_after();
         const uint32_t sw = smem_u32(smem + kOffW2 + b * kW2Slot);
         const int ksteps = chunk_n(cc) / 16;
         if (elect_one()) {
           for (int j = 0; j < ksteps; ++j) {
-            // H of neurons [0,32) of the chunk sits in columns [0,16), of [32,64) in [48,64)
-            const uint32_t a_t = tmem_base + kAcc1Col + 64 * b + (j < 2 ? 8 * j : 48 + 8 * (j - 2));
+            // H of neurons [16j, 16j + 16) of the chunk sits in columns [16j, 16j + 8)
+            const uint32_t a_t = tmem_base + kAcc1Col + 64 * b + 16 * j;
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
               const uint64_t db = make_sw128_desc(sw + hh * 12288, 1024, 16) + 2 * j;
@@ -197,13 +217,18 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
           }
           umma_commit_cg2(&w2_empty[b], 3);
         }
+        MLP_TRACE(6, g2);
         ++g2;
       };
       for (int pt = cluster_id; pt < num_pairs; pt += num_clusters, ++it) {
+        MLP_TRACE(7, it);
         mbar_wait_warp(y_full, it & 1);
+        MLP_TRACE(8, it);
         for (int c = 0; c < NC; ++c) {
           const int s = g1 & 1;
+          MLP_TRACE(0, g1);
           mbar_wait_warp(&w1_full[s], (g1 >> 1) & 1);
+          MLP_TRACE(1, g1);
           tc_fence_after();
           const uint32_t idesc1 = make_idesc(kFmtBF16, 256, chunk_n(c), 0, 0);
           const uint32_t sy = smem_u32(smem);
@@ -222,6 +247,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
             umma_commit_cg2(&acc1_full[s], 3);
             if (c == NC - 1) umma_commit_cg2(y_empty, 3);
           }
+          MLP_TRACE(2, g1);
           ++g1;
           if (c >= 1) gemm2(c - 1, c == 1);
         }
@@ -231,9 +257,10 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
     }
   } else {
     // ------------------------------------------------------------ epilogue warps
-    const int ew = warp - 2;
-    const int quarter = warp & 3;  // TMEM lane quarter
-    const int half = ew >> 2;
+    const int quarter = warp & 3;        // TMEM lane quarter
+    const int sub = (warp - 2) >> 2;     // 16-column slice of every hidden chunk (0..3)
+    const int half = sub & 1;            // final epilogue (sub < 2 only): columns [192 half, +192)
+    const int ew = half * 4 + quarter;   // final-epilogue slot owner index (0..7)
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
     uint8_t* slots = smem + ew * (3 * 4096);  // final-epilogue slots inside the Y buffer
     uint64_t* rbar = rfull + ew * 3;
@@ -263,43 +290,43 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         rstd = rsqrtf(var + p.ln_eps);
         nmr = -rstd * mean;
       }
-      // ---- hidden chunks: acc1 -> H (bf16, in TMEM)
+      // ---- hidden chunks: acc1 -> H (bf16, in TMEM).  Slice `sub` of chunk c: neurons
+      //      [64c + 16 sub, +16) = acc1 columns [16 sub, +16) -> H columns [16 sub, +8).
       for (int c = 0; c < NC; ++c, ++ecnt) {
         const int b = ecnt & 1;
-        mbar_wait_warp(&acc1_full[b], (ecnt >> 1) & 1);
-        tc_fence_after();
-        if (c == NC - 1) {
-          // the last GEMM1 has retired: Y is dead, start fetching the residual into its slots
-          if (elect_one()) {
+        // fold constants of this slice, fetched and combined BEFORE the accumulator is awaited
+        float t[16];
+        {
+          const int col0 = c * 64 + 16 * sub;
 #pragma unroll
-            for (int s = 0; s < 3; ++s) {
-              mbar_expect_tx(&rbar[s], 4096);
-              tma_load_2d(slots + s * 4096, &tmX, &rbar[s], half * 192 + s * 32, row0);
+          for (int g = 0; g < 4; ++g) {
+            float4 cs = make_float4(0.f, 0.f, 0.f, 0.f), bs = cs;
+            if (col0 + 4 * g < p.F_ld) {
+              cs = __ldg(reinterpret_cast<const float4*>(p.c1 + col0) + g);
+              bs = __ldg(reinterpret_cast<const float4*>(p.c2 + col0) + g);
             }
+            t[4 * g] = fmaf(nmr, cs.x, bs.x);
+            t[4 * g + 1] = fmaf(nmr, cs.y, bs.y);
+            t[4 * g + 2] = fmaf(nmr, cs.z, bs.z);
+            t[4 * g + 3] = fmaf(nmr, cs.w, bs.w);
           }
         }
-        const uint32_t t_acc = tmem_base + lane_off + kAcc1Col + 64 * b;
-        uint32_t r[32];
-        tmem_ld_x32(t_acc + 32 * half, r);
+        if (warp == 2) MLP_TRACE(9, ecnt);
+        mbar_wait_warp(&acc1_full[b], (ecnt >> 1) & 1);
+        if (warp == 2) MLP_TRACE(10, ecnt);
+        tc_fence_after();
+        const uint32_t t_acc = tmem_base + lane_off + kAcc1Col + 64 * b + 16 * sub;
+        uint32_t r[16];
+        tmem_ld_x16(t_acc, r);
         tmem_ld_wait();
-        const int col0 = c * 64 + 32 * half;
-        uint32_t pk[16];
+        uint32_t pk[8];
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
-          float4 cs = make_float4(0.f, 0.f, 0.f, 0.f), bs = cs;
-          if (col0 + 4 * g < p.F_ld) {
-            cs = __ldg(reinterpret_cast<const float4*>(p.c1 + col0) + g);
-            bs = __ldg(reinterpret_cast<const float4*>(p.c2 + col0) + g);
-          }
-          const float v0 = gelu_erf_fast(fmaf(rstd, __uint_as_float(r[4 * g]), fmaf(nmr, cs.x, bs.x)));
-          const float v1 = gelu_erf_fast(fmaf(rstd, __uint_as_float(r[4 * g + 1]), fmaf(nmr, cs.y, bs.y)));
-          const float v2 = gelu_erf_fast(fmaf(rstd, __uint_as_float(r[4 * g + 2]), fmaf(nmr, cs.z, bs.z)));
-          const float v3 = gelu_erf_fast(fmaf(rstd, __uint_as_float(r[4 * g + 3]), fmaf(nmr, cs.w, bs.w)));
-          pk[2 * g] = pack_bf16x2(v0, v1);
-          pk[2 * g + 1] = pack_bf16x2(v2, v3);
+          const float v0 = gelu_erf_fast(fmaf(rstd, __uint_as_float(r[2 * g]), t[2 * g]));
+          const float v1 = gelu_erf_fast(fmaf(rstd, __uint_as_float(r[2 * g + 1]), t[2 * g + 1]));
+          pk[g] = pack_bf16x2(v0, v1);
         }
-        // half 0: neurons [0,32) -> columns [0,16); half 1: neurons [32,64) -> columns [48,64)
-        tmem_st_x16(t_acc + (half ? 48 : 0), pk);
+        tmem_st_x8(t_acc, pk);  // over the first 8 of the 16 columns this thread just consumed
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
@@ -307,9 +334,23 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
           if (leader) mbar_arrive(&h_ready[b]);
           else mbar_arrive_cluster(b ? h_ready_leader1 : h_ready_leader0);
         }
+        if (warp == 2) MLP_TRACE(11, ecnt);
       }
-      // ---- final epilogue: x += acc2 + b2, bf16 copy, partial row sums
+      if (sub >= 2) continue;  // the other eight warps go straight to the next tile's chunks
+      // ---- final epilogue (warps with sub < 2): x += acc2 + b2, bf16 copy, partial row sums.
+      // Once the tile's last GEMM1 has retired (y_empty) the Y buffer is dead: its 96 KB become
+      // 24 residual slots and the first three chunks of every warp are requested right away.
+      mbar_wait_warp(y_empty, it & 1);
+      if (elect_one()) {
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+          mbar_expect_tx(&rbar[s], 4096);
+          tma_load_2d(slots + s * 4096, &tmX, &rbar[s], half * 192 + s * 32, row0);
+        }
+      }
+      if (warp == 2) MLP_TRACE(12, it);
       mbar_wait_warp(acc2_full, it & 1);
+      if (warp == 2) MLP_TRACE(13, it);
       tc_fence_after();
       float st1 = 0.f, st2 = 0.f;
 #pragma unroll 1
@@ -341,11 +382,13 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         if (elect_one()) {
           tma_store_2d(&tmX, bsl, col0, row0);
           bulk_commit();
-          if (j < 3) {
-            // refill this slot with the residual of chunk j + 3 once the store has read it
-            bulk_wait_read<0>();
-            mbar_expect_tx(&rbar[s], 4096);
-            tma_load_2d(bsl, &tmX, &rbar[s], col0 + 96, row0);
+          if (j >= 1 && j <= 3) {
+            // the PREVIOUS chunk's store has drained its slot: refill it with the residual of
+            // the chunk three positions further on (slot of chunk j-1 serves chunk j+2)
+            bulk_wait_read<1>();
+            const int sp = (j - 1) % 3;
+            mbar_expect_tx(&rbar[sp], 4096);
+            tma_load_2d(slots + sp * 4096, &tmX, &rbar[sp], col0 + 64, row0);
           }
         }
         __syncwarp();
@@ -388,6 +431,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         mbar_arrive(y_free);
       }
       __syncwarp();
+      if (warp == 2) MLP_TRACE(14, it);
     }
     if (elect_one()) bulk_wait_all<0>();
   }
@@ -451,6 +495,7 @@ extern "C" int devit_mlp_fused(const devit_mlp_args* a, void* stream_v) {
   p.ln_eps = a->ln_eps;
   p.xb_out = static_cast<__nv_bfloat16*>(a->xb_out);
   p.stats_out = a->stats_out;
+  p.trace = g_attn_trace;
   const int num_pairs = (a->m + 255) / 256;
   int clusters = num_sms() / 2;
   if (clusters > num_pairs) clusters = num_pairs;

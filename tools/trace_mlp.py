@@ -1,0 +1,41 @@
+"""clock64 trace of the fused MLP kernel, CTA 0 (needs the -DDEVIT_GEMM_TRACE build):
+   DEVIT_B200_LIB=devit_b200/lib/libdevit_b200_trace.so python tools/trace_mlp.py [hidden]"""
+import sys
+from pathlib import Path
+import torch
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+from devit_b200 import _lib as L  # noqa: E402
+F = int(sys.argv[1]) if len(sys.argv) > 1 else 928
+M, D = 256 * 198, 384
+g = torch.Generator(device="cuda").manual_seed(0)
+x = torch.randn(M, D, device="cuda", generator=g)
+xb, stats = L.rowstats(x)
+w1 = (torch.randn(F, D, device="cuda", generator=g) * .05).bfloat16()
+w2 = (torch.randn(D, F, device="cuda", generator=g) * .05).bfloat16()
+c1, c2, b2 = (torch.randn(n, device="cuda", generator=g) * .1 for n in (F, F, D))
+so = torch.empty(6, M, 2, device="cuda")
+def run():
+    L.mlp_fused(x, xb, stats, w1, c1, c2, w2, b2, 1e-6, xb_out=xb, stats_out=so)
+for _ in range(3):
+    run()
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(10):
+    run()
+e1.record()
+torch.cuda.synchronize()
+print(f"F={F}: {e0.elapsed_time(e1) / 10 * 1e3:.1f} us per launch")
+buf = torch.zeros(20, 512, device="cuda", dtype=torch.int64)
+L.load().devit_debug_set_trace(buf.data_ptr())
+run()
+torch.cuda.synchronize()
+L.load().devit_debug_set_trace(None)
+t = buf.cpu()
+t0 = int(t[7, 0])
+NC = (F + 63) // 64
+def r(s, i): return int(t[s, i]) - t0
+for it in range(3):
+    print(f"tile {it}: mma wait Y {r(7,it)} got {r(8,it)} | epi wait acc2 {r(12,it)} got {r(13,it)} final done {r(14,it)}")
+    for c in range(it * NC, it * NC + NC):
+        print(f"   c{c - it * NC:2d}: G1 [wait {r(0,c)} got {r(1,c)} issued {r(2,c)}]  G2 [wait {r(3,c)} h {r(4,c)} w2 {r(5,c)} issued {r(6,c)}]  epi [wait {r(9,c)} got {r(10,c)} done {r(11,c)}]")

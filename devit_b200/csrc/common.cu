@@ -113,7 +113,7 @@ static EncodeTiledFn get_encode() {
 
 static int encode(CUtensorMap* map, const void* base, int elem_bytes, int rank,
                   const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                  const cuuint32_t* box, bool weight_like) {
+                  const cuuint32_t* box, bool weight_like, bool swizzle128 = true) {
   EncodeTiledFn fn = get_encode();
   if (!fn) return set_error(DEVIT_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0)
@@ -122,13 +122,16 @@ static int encode(CUtensorMap* map, const void* base, int elem_bytes, int rank,
     if (strides_bytes[i] % 16 != 0)
       return set_error(DEVIT_ERR_ARG, "TMA stride %llu bytes is not a multiple of 16",
                        (unsigned long long)strides_bytes[i]);
-  if (box[0] * (cuuint32_t)elem_bytes != 128)
+  if (swizzle128 && box[0] * (cuuint32_t)elem_bytes != 128)
     return set_error(DEVIT_ERR_ARG, "TMA inner box must be 128 bytes for SWIZZLE_128B");
+  if (!swizzle128 && box[0] * (cuuint32_t)elem_bytes != 64)
+    return set_error(DEVIT_ERR_ARG, "TMA inner box must be 64 bytes for SWIZZLE_64B");
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUtensorMapDataType dt =
       elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   CUresult r = fn(map, dt, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box,
-                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                   weight_like ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
                               : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -148,6 +151,14 @@ int encode_tmap_2d(CUtensorMap* map, const void* base, int elem_bytes, uint64_t 
   cuuint64_t strides[1] = {ld * (uint64_t)elem_bytes};
   cuuint32_t box[2] = {box_cols, box_rows};
   return encode(map, base, elem_bytes, 2, dims, strides, box, weight_like);
+}
+
+int encode_tmap_2d_sw64(CUtensorMap* map, const void* base, int elem_bytes, uint64_t cols,
+                          uint64_t rows, uint64_t ld, uint32_t box_cols, uint32_t box_rows) {
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * (uint64_t)elem_bytes};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  return encode(map, base, elem_bytes, 2, dims, strides, box, false, false);
 }
 
 int encode_tmap_3d(CUtensorMap* map, const void* base, int elem_bytes, uint64_t d0, uint64_t d1,

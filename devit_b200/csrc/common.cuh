@@ -46,6 +46,10 @@ struct ProfScope {
 int encode_tmap_2d(CUtensorMap* map, const void* base, int elem_bytes, uint64_t cols,
                    uint64_t rows, uint64_t ld, uint32_t box_cols, uint32_t box_rows,
                    bool weight_like);
+// 2D map with the 64-byte swizzle: shared-memory rows of 64 B, 16-byte chunk c of row r stored
+// at chunk c ^ ((r >> 1) & 3)
+int encode_tmap_2d_sw64(CUtensorMap* map, const void* base, int elem_bytes, uint64_t cols,
+                          uint64_t rows, uint64_t ld, uint32_t box_cols, uint32_t box_rows);
 int encode_tmap_3d(CUtensorMap* map, const void* base, int elem_bytes, uint64_t d0, uint64_t d1,
                    uint64_t d2, uint64_t stride1, uint64_t stride2, uint32_t box0,
                    uint32_t box1, uint32_t box2);

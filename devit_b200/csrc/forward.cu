@@ -241,6 +241,7 @@ extern "C" int devit_vit_forward(const devit_vit_desc* d, const float* images, i
       if (l + 1 < nl) { ma.xb_out = y; ma.stats_out = stats; }
       rc = devit_mlp_fused(&ma, stream);
       if (rc) return rc;
+      parts = 4;  // the fused kernel emits one partial row sum per 96 columns
       if ((rc = sync_debug("fused mlp", l, stream))) return rc;
       continue;
     }

@@ -13,9 +13,12 @@
 //   * GEMM2 chunk c: acc2 (128 x 384 fp32, TMEM columns [0, 384)) += H_c W2_c^T with the A operand
 //     read from tensor memory (two N = 192 UMMAs per K = 16 step).  GEMM1 of chunk c+1 is issued
 //     before GEMM2 of chunk c, so the tensor pipe works while the GELU of chunk c runs.
-//   * Final epilogue: acc2 + b2 + residual -> x (fp32, through shared-memory slots carved out of
-//     the dead Y buffer, residual TMA-prefetched as soon as the last GEMM1 retired), plus the
-//     bf16 copy and the partial row sums the next layer's LayerNorm-folded QKV GEMM consumes.
+//   * Final epilogue: acc2 + b2 + residual -> x (fp32).  At the end of a tile Y and both weight
+//     rings are dead: their 192 KB become 48 slots of [32 rows x 32 fp32], i.e. the WHOLE
+//     residual tile, three slots per epilogue warp, TMA-prefetched as soon as the last GEMM1
+//     (Y, W1 ring) / last GEMM2 (W2 ring) retired.  Each warp adds, stores through TMA and
+//     also emits the bf16 copy and the partial row sums the next layer's LayerNorm-folded QKV
+//     GEMM consumes.  The loaders resume only when every slot has been drained (all_free).
 // TMEM: 384 + 2 x 64 = 512 columns.  smem: Y 96 KB + W1 ring 48 KB + W2 ring 48 KB.
 #include <cstdlib>
 
@@ -28,7 +31,7 @@ constexpr int kMlpDim = 384;
 // warps: 0 = Y + W1 loads, 1 = MMA issue, 2..17 = epilogue (four per TMEM lane quarter: every
 // hidden chunk is split 4 x 16 columns, because GEMM1 of chunk c+1 has to wait for the GELU of
 // chunk c-1 -- two accumulator buffers -- so the GELU LATENCY of a chunk is what bounds the loop;
-// the first two warps of each quarter also run the final epilogue), 18 = W2 loads
+// all sixteen also run the final epilogue, 96 output columns each), 18 = W2 loads
 constexpr int kMlpThreads = 19 * 32;
 constexpr int kW2Warp = 18;
 constexpr int kYBytes = 6 * 16384;    // 6 K-atoms of [128 rows x 128 B]
@@ -36,8 +39,10 @@ constexpr int kW1Slot = 6 * 4096;     // 6 K-atoms of [32 rows x 128 B]  (this C
 constexpr int kW2Slot = 2 * 12288;    // 2 N-halves of [96 rows x 128 B]
 constexpr int kOffW1 = kYBytes;
 constexpr int kOffW2 = kOffW1 + 2 * kW1Slot;
-constexpr int kOffBarM = kOffW2 + 2 * kW2Slot;
-constexpr int kMlpSmem = kOffBarM + 64 * 8 + 1024;
+constexpr int kOffXb = kOffW2 + 2 * kW2Slot;  // bf16-copy staging: 16 warps x [32 rows x 64 B]
+constexpr int kOffBarM = kOffXb + 16 * 2048;
+constexpr int kMlpSmem = kOffBarM + 1024 + 1024;
+static_assert(kMlpSmem <= 227 * 1024, "fused MLP shared memory budget");
 constexpr int kAcc1Col = 384;
 
 extern long long* g_attn_trace;  // devit_debug_set_trace buffer (shared)
@@ -79,13 +84,13 @@ __device__ __forceinline__ int mlp_off(int r, int j) { return r * 128 + ((j ^ (r
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1)
 mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmW1,
                  const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmX,
-                 const __grid_constant__ MlpParams p) {
+                 const __grid_constant__ CUtensorMap tmXB, const __grid_constant__ MlpParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBarM);
   uint64_t* y_full = bars + 0;
   uint64_t* y_empty = bars + 1;     // last GEMM1 of the tile retired (Y is dead)
-  uint64_t* y_free = bars + 2;      // final epilogue done with the Y-buffer slots (8 arrivals)
+  uint64_t* y_free = bars + 2;      // "all_free": every final-epilogue slot drained (16 arrivals)
   uint64_t* w1_full = bars + 3;     // [2]
   uint64_t* w1_empty = bars + 5;    // [2]
   uint64_t* w2_full = bars + 7;     // [2]
@@ -93,9 +98,9 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
   uint64_t* acc1_full = bars + 11;  // [2]
   uint64_t* h_ready = bars + 13;    // [2]  (leader: 32 warp arrivals)
   uint64_t* acc2_full = bars + 15;
-  uint64_t* acc2_empty = bars + 16;  // (leader: 16 warp arrivals)
-  uint64_t* rfull = bars + 17;       // [8 warps][3 slots]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 41);
+  uint64_t* acc2_empty = bars + 16;  // (leader: 32 warp arrivals)
+  uint64_t* rfull = bars + 17;       // [16 warps][3 slots]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 65);
 
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
@@ -111,9 +116,10 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
     tma_prefetch_desc(&tmW1);
     tma_prefetch_desc(&tmW2);
     tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmXB);
     mbar_init(y_full, 1);
     mbar_init(y_empty, 1);
-    mbar_init(y_free, 8);
+    mbar_init(y_free, 16);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&w1_full[i], 1);
       mbar_init(&w1_empty[i], 1);
@@ -123,8 +129,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
       mbar_init(&h_ready[i], 32);
     }
     mbar_init(acc2_full, 1);
-    mbar_init(acc2_empty, 16);
-    for (int i = 0; i < 24; ++i) mbar_init(&rfull[i], 1);
+    mbar_init(acc2_empty, 32);
+    for (int i = 0; i < 48; ++i) mbar_init(&rfull[i], 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -172,7 +178,9 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
   } else if (warp == kW2Warp) {
     // ------------------------------------------------------------ loads: the W2 ring
     uint32_t g2 = 0;
-    for (int pt = cluster_id; pt < num_pairs; pt += num_clusters) {
+    int it = 0;
+    for (int pt = cluster_id; pt < num_pairs; pt += num_clusters, ++it) {
+      if (it >= 1) mbar_wait_warp(y_free, (it - 1) & 1);  // ring memory served as slots
       for (int c = 0; c < NC; ++c, ++g2) {
         const int s = g2 & 1;
         mbar_wait_warp(&w2_empty[s], ((g2 >> 1) & 1) ^ 1);
@@ -258,16 +266,20 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
   } else {
     // ------------------------------------------------------------ epilogue warps
     const int quarter = warp & 3;        // TMEM lane quarter
-    const int sub = (warp - 2) >> 2;     // 16-column slice of every hidden chunk (0..3)
-    const int half = sub & 1;            // final epilogue (sub < 2 only): columns [192 half, +192)
-    const int ew = half * 4 + quarter;   // final-epilogue slot owner index (0..7)
+    const int sub = (warp - 2) >> 2;     // 16-column slice of every hidden chunk; final epilogue:
+                                         // output columns [96 sub, +96)
+    const int ew = sub * 4 + quarter;    // slot owner index (0..15)
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
-    uint8_t* slots = smem + ew * (3 * 4096);  // final-epilogue slots inside the Y buffer
+    // slots 3 ew .. 3 ew + 2 of the 48: [0,24) in Y, [24,36) in the W1 ring, [36,48) in the W2
+    // ring (contiguous in shared memory, so the slot address is simply 4 KB x index)
+    uint8_t* slots = smem + ew * (3 * 4096);
+    const bool slots_in_w2 = ew >= 12;   // usable only once the last GEMM2 has retired
     uint64_t* rbar = rfull + ew * 3;
+    uint8_t* xb_stg = smem + kOffXb + ew * 2048;  // [32 rows x 32 bf16], rows of 64 B, 64B swizzle
     const uint32_t h_ready_leader0 = mapa_u32(smem_u32(&h_ready[0]), 0);
     const uint32_t h_ready_leader1 = mapa_u32(smem_u32(&h_ready[1]), 0);
     const uint32_t acc2_empty_leader = mapa_u32(smem_u32(acc2_empty), 0);
-    uint32_t ecnt = 0, rphase = 0;
+    uint32_t ecnt = 0;
     int it = 0;
     for (int pt = cluster_id; pt < num_pairs; pt += num_clusters, ++it) {
       const int m0 = (pt * 2 + cta_rank) * 128;
@@ -289,6 +301,12 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         const float var = fmaxf(fmaf(s2, p.ln_inv_dim, -mean * mean), 0.f);
         rstd = rsqrtf(var + p.ln_eps);
         nmr = -rstd * mean;
+      }
+      // The residual of this tile is needed only in the final epilogue, and its slots do not
+      // exist until then: pull it into L2 now, so that the late TMA loads are L2 hits.
+      if (row0 < p.M && elect_one()) {
+#pragma unroll
+        for (int s = 0; s < 3; ++s) tma_prefetch_l2_2d(&tmX, sub * 96 + s * 32, row0);
       }
       // ---- hidden chunks: acc1 -> H (bf16, in TMEM).  Slice `sub` of chunk c: neurons
       //      [64c + 16 sub, +16) = acc1 columns [16 sub, +16) -> H columns [16 sub, +8).
@@ -336,17 +354,21 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         }
         if (warp == 2) MLP_TRACE(11, ecnt);
       }
-      if (sub >= 2) continue;  // the other eight warps go straight to the next tile's chunks
-      // ---- final epilogue (warps with sub < 2): x += acc2 + b2, bf16 copy, partial row sums.
-      // Once the tile's last GEMM1 has retired (y_empty) the Y buffer is dead: its 96 KB become
-      // 24 residual slots and the first three chunks of every warp are requested right away.
-      mbar_wait_warp(y_empty, it & 1);
+      // ---- final epilogue: x += acc2 + b2, bf16 copy, partial row sums (96 columns per warp)
+      if (slots_in_w2) mbar_wait_warp(acc2_full, it & 1);
+      else mbar_wait_warp(y_empty, it & 1);
       if (elect_one()) {
 #pragma unroll
         for (int s = 0; s < 3; ++s) {
           mbar_expect_tx(&rbar[s], 4096);
-          tma_load_2d(slots + s * 4096, &tmX, &rbar[s], half * 192 + s * 32, row0);
+          tma_load_2d(slots + s * 4096, &tmX, &rbar[s], sub * 96 + s * 32, row0);
         }
+      }
+      // ... and the next tile's Y (loaded only after every slot has been drained) likewise
+      if (warp == 2 && pt + num_clusters < num_pairs && elect_one()) {
+        const int m_next = ((pt + num_clusters) * 2 + cta_rank) * 128;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) tma_prefetch_l2_2d(&tmY, a * 64, m_next);
       }
       if (warp == 2) MLP_TRACE(12, it);
       mbar_wait_warp(acc2_full, it & 1);
@@ -354,21 +376,30 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
       tc_fence_after();
       float st1 = 0.f, st2 = 0.f;
 #pragma unroll 1
-      for (int j = 0; j < 6; ++j) {
-        const int s = j % 3;
-        const int col0 = half * 192 + j * 32;
+      for (int j = 0; j < 3; ++j) {
+        const int col0 = sub * 96 + j * 32;
         uint32_t r[32];
         tmem_ld_x32(tmem_base + lane_off + col0, r);
         tmem_ld_wait();
+        if (j == 2) {
+          // acc2 is in registers: release it before the memory work of the last chunk
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (leader) mbar_arrive(acc2_empty);
+            else mbar_arrive_cluster(acc2_empty_leader);
+          }
+        }
         float* v = reinterpret_cast<float*>(r);
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
           const float4 t = __ldg(reinterpret_cast<const float4*>(p.b2 + col0) + g);
           v[4 * g] += t.x; v[4 * g + 1] += t.y; v[4 * g + 2] += t.z; v[4 * g + 3] += t.w;
         }
-        mbar_wait_warp(&rbar[s], (rphase >> s) & 1u);
-        rphase ^= 1u << s;
-        uint8_t* bsl = slots + s * 4096;
+        if (warp == 2) MLP_TRACE(15, it * 4 + j);
+        mbar_wait_warp(&rbar[j], it & 1);
+        if (warp == 2) MLP_TRACE(16, it * 4 + j);
+        uint8_t* bsl = slots + j * 4096;
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
           const float4 t = *reinterpret_cast<const float4*>(bsl + mlp_off(lane, g));
@@ -378,22 +409,14 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         for (int g = 0; g < 8; ++g)
           *reinterpret_cast<float4*>(bsl + mlp_off(lane, g)) =
               make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
-        fence_proxy_async_smem();
-        if (elect_one()) {
-          tma_store_2d(&tmX, bsl, col0, row0);
-          bulk_commit();
-          if (j >= 1 && j <= 3) {
-            // the PREVIOUS chunk's store has drained its slot: refill it with the residual of
-            // the chunk three positions further on (slot of chunk j-1 serves chunk j+2)
-            bulk_wait_read<1>();
-            const int sp = (j - 1) % 3;
-            mbar_expect_tx(&rbar[sp], 4096);
-            tma_load_2d(slots + sp * 4096, &tmX, &rbar[sp], col0 + 64, row0);
+        if (p.xb_out) {
+          // bf16 copy through a 64B-swizzled staging tile + TMA store (scattered 16-byte global stores
+          // from 16 warps were the slowest part of this phase).  The previous chunk's stores
+          // have to have read the staging tile first.
+          if (j > 0) {
+            if (elect_one()) bulk_wait_read<0>();
+            __syncwarp();
           }
-        }
-        __syncwarp();
-        if (p.xb_out && row < p.M) {
-          uint4* o = reinterpret_cast<uint4*>(p.xb_out + static_cast<long long>(row) * kMlpDim + col0);
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             uint4 t;
@@ -401,31 +424,30 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
             t.y = pack_bf16x2(v[8 * g + 2], v[8 * g + 3]);
             t.z = pack_bf16x2(v[8 * g + 4], v[8 * g + 5]);
             t.w = pack_bf16x2(v[8 * g + 6], v[8 * g + 7]);
-            o[g] = t;
+            *reinterpret_cast<uint4*>(xb_stg + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4)) = t;
           }
         }
+        fence_proxy_async_smem();
+        if (elect_one()) {
+          tma_store_2d(&tmX, bsl, col0, row0);
+          if (p.xb_out) tma_store_2d(&tmXB, xb_stg, col0, row0);
+          bulk_commit();
+        }
+        __syncwarp();
         if (p.stats_out) {
 #pragma unroll
           for (int k = 0; k < 32; ++k) {
             st1 += v[k];
             st2 = fmaf(v[k], v[k], st2);
           }
-          if (j & 1) {  // a 64-column part is complete: part index = (192 half + 32 (j-1)) / 64
-            if (row < p.M)
-              reinterpret_cast<float2*>(p.stats_out)[static_cast<long long>(3 * half + (j >> 1)) * p.M + row] =
-                  make_float2(st1, st2);
-            st1 = 0.f;
-            st2 = 0.f;
-          }
         }
+        if (warp == 2) MLP_TRACE(17, it * 4 + j);
       }
-      // acc2 has been read: release it; the Y buffer is free once our stores have drained it
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (leader) mbar_arrive(acc2_empty);
-        else mbar_arrive_cluster(acc2_empty_leader);
-      }
+      // partial row sums of this warp's 96 columns: part index = sub (4 parts per row)
+      if (p.stats_out && row < p.M)
+        reinterpret_cast<float2*>(p.stats_out)[static_cast<long long>(sub) * p.M + row] =
+            make_float2(st1, st2);
+      // the loaders may reuse Y and the rings once every warp's stores have drained its slots
       if (elect_one()) {
         bulk_wait_read<0>();
         mbar_arrive(y_free);
@@ -473,7 +495,7 @@ extern "C" int devit_mlp_fused(const devit_mlp_args* a, void* stream_v) {
                                        kMlpSmem));
     attr_done[dev & 63] = true;
   }
-  CUtensorMap tY, tW1, tW2, tX;
+  CUtensorMap tY, tW1, tW2, tX, tXB;
   rc = encode_tmap_2d(&tY, a->xb, 2, kMlpDim, a->m, kMlpDim, 64, 128, false);
   if (rc) return rc;
   rc = encode_tmap_2d(&tW1, a->w1, 2, kMlpDim, a->hidden_ld, kMlpDim, 64, 32, true);
@@ -482,6 +504,11 @@ extern "C" int devit_mlp_fused(const devit_mlp_args* a, void* stream_v) {
   if (rc) return rc;
   rc = encode_tmap_2d(&tX, a->x, 4, kMlpDim, a->m, kMlpDim, 32, 32, false);
   if (rc) return rc;
+  tXB = tX;
+  if (a->xb_out) {
+    rc = encode_tmap_2d_sw64(&tXB, a->xb_out, 2, kMlpDim, a->m, kMlpDim, 32, 32);
+    if (rc) return rc;
+  }
   MlpParams p;
   p.M = a->m;
   p.F_ld = a->hidden_ld;
@@ -501,7 +528,7 @@ extern "C" int devit_mlp_fused(const devit_mlp_args* a, void* stream_v) {
   if (clusters > num_pairs) clusters = num_pairs;
   {
     ProfScope ps(kTagGemmFc2, stream);
-    mlp_fused_kernel<<<clusters * 2, kMlpThreads, kMlpSmem, stream>>>(tY, tW1, tW2, tX, p);
+    mlp_fused_kernel<<<clusters * 2, kMlpThreads, kMlpSmem, stream>>>(tY, tW1, tW2, tX, tXB, p);
   }
   DEVIT_CUDA_OK(cudaGetLastError());
   count_launch();

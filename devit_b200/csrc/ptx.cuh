@@ -109,6 +109,13 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// L2 prefetch of a 2D tile (no shared-memory destination, no completion tracking)
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* m, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1)
+               : "memory");
+}
+
 // CTA-pair variant (cta_group::2): data lands in THIS CTA's shared memory, the completion is
 // signalled on an mbarrier given by its shared::cluster address (the leader CTA's barrier).
 __device__ __forceinline__ void tma_load_2d_cg2(void* smem_dst, const CUtensorMap* m,

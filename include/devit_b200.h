@@ -178,7 +178,7 @@ int devit_layernorm(const float* x, const float* gamma, const float* beta, void*
  * sums / folded bias [hidden_ld] (zero beyond the kept neurons), `ln_stats` the partial row sums
  * [ln_parts][m][2].  `w2` is [dim, hidden_ld] (zero columns beyond the kept neurons).
  * Outputs: x (fp32, in place), optionally the bf16 copy of the new x (`xb_out`, may alias `xb`)
- * and its partial row sums `stats_out` [6][m][2] (one part per 64 columns) for the next layer.
+ * and its partial row sums `stats_out` [4][m][2] (one part per 96 columns) for the next layer.
  * ------------------------------------------------------------------------------------- */
 typedef struct devit_mlp_args {
   int32_t m;

@@ -13,7 +13,7 @@ xb, stats = L.rowstats(x)
 w1 = (torch.randn(F, D, device="cuda", generator=g) * .05).bfloat16()
 w2 = (torch.randn(D, F, device="cuda", generator=g) * .05).bfloat16()
 c1, c2, b2 = (torch.randn(n, device="cuda", generator=g) * .1 for n in (F, F, D))
-so = torch.empty(6, M, 2, device="cuda")
+so = torch.empty(4, M, 2, device="cuda")
 def run():
     L.mlp_fused(x, xb, stats, w1, c1, c2, w2, b2, 1e-6, xb_out=xb, stats_out=so)
 for _ in range(3):
@@ -37,5 +37,7 @@ NC = (F + 63) // 64
 def r(s, i): return int(t[s, i]) - t0
 for it in range(3):
     print(f"tile {it}: mma wait Y {r(7,it)} got {r(8,it)} | epi wait acc2 {r(12,it)} got {r(13,it)} final done {r(14,it)}")
+    print("   final chunks [before resid wait, resid landed, chunk done]: " + "  ".join(
+        f"j{j}: {r(15, it * 4 + j)} {r(16, it * 4 + j)} {r(17, it * 4 + j)}" for j in range(3)))
     for c in range(it * NC, it * NC + NC):
         print(f"   c{c - it * NC:2d}: G1 [wait {r(0,c)} got {r(1,c)} issued {r(2,c)}]  G2 [wait {r(3,c)} h {r(4,c)} w2 {r(5,c)} issued {r(6,c)}]  epi [wait {r(9,c)} got {r(10,c)} done {r(11,c)}]")

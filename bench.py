@@ -353,35 +353,50 @@ def main():
     fam = {k: {"ms_per_step": v[0] / nprof, "launches_per_step": v[1] // nprof}
            for k, v in prof.items()}
 
-    # ---- roofline of the dominant kernel (the tcgen05 GEMM family) on THIS rank's shard
+    # ---- roofline of the dominant kernel on THIS rank's shard.  The fused MLP kernel
+    #      (fc1 + GELU + fc2, csrc/mlp.cu) is ~45 % of the step and 60 % of its FLOPs; the
+    #      aggregate over every tcgen05 GEMM launch and the attention kernel are given beside it.
     peaks = load_peaks()
-    gemm_fl = attn_fl = 0
+    gemm_fl = attn_fl = mlp_fl = 0
     for s in plan.subs:
         g, a = submodel_flops(*kept[s])
         gemm_fl += g * Bg
         attn_fl += a * Bg
+        mlp_fl += sum(4 * TOKENS * D * f for f in kept[s][1]) * Bg
     gemm_fl += fusion_flops() * Bg
     gemm_ms = sum(v["ms_per_step"] for k, v in fam.items() if k.startswith("gemm"))
     gemm_launches = sum(v["launches_per_step"] for k, v in fam.items() if k.startswith("gemm"))
     attn_ms = fam.get("attention", {}).get("ms_per_step", 0.0)
-    achieved = gemm_fl / (gemm_ms / 1e3) / 1e12 if gemm_ms else None
     total_fl = sum(sum(submodel_flops(*kept[s])) for s in range(N_SUB)) * BATCH \
         + fusion_flops() * BATCH
     traffic = None
-    tfile = ROOT / "profiles" / "gemm_traffic.json"
+    tfile = ROOT / "profiles" / "dominant_kernel_traffic.json"
     if tfile.exists():
         try:
-            traffic = json.loads(tfile.read_text()).get("dram_bytes_per_launch")
+            traffic = json.loads(tfile.read_text()).get(
+                "dense_dram_bytes_per_launch" if args.dense else "shrunk_dram_bytes_per_launch")
         except Exception:  # noqa: BLE001
             traffic = None
+    mlp = fam.get("gemm_mlp_fused")
+    if mlp and mlp["launches_per_step"]:
+        dom_name = "devit::mlp_fused_kernel (tcgen05 cta_group::2: LN-folded fc1 + GELU + fc2 + residual)"
+        dom_fl, dom_ms, dom_n = mlp_fl, mlp["ms_per_step"], mlp["launches_per_step"]
+    else:  # fp32 mode / fused kernel switched off: the GEMM family as a whole
+        dom_name = "devit::gemm_kernel<BN> (tcgen05, all GEMM launches of a step)"
+        dom_fl, dom_ms, dom_n = gemm_fl, gemm_ms, gemm_launches
+    achieved = dom_fl / (dom_ms / 1e3) / 1e12 if dom_ms else None
+    gemm_tf = gemm_fl / (gemm_ms / 1e3) / 1e12 if gemm_ms else None
     roofline = {
-        "kernel": "devit::gemm_kernel<BN,bf16> (tcgen05, all GEMM launches of a step)",
+        "kernel": dom_name,
         "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_sustained"],
         "unit": "TFLOP/s", "frac": (achieved / peaks["bf16_sustained"]) if achieved else None,
         "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a step)",
-        "flops_per_launch": gemm_fl / gemm_launches if gemm_launches else None,
-        "ms_per_launch": gemm_ms / gemm_launches if gemm_launches else None,
-        "launches_per_step": gemm_launches, "traffic": traffic,
+        "flops_per_launch": dom_fl / dom_n if dom_n else None,
+        "ms_per_launch": dom_ms / dom_n if dom_n else None,
+        "launches_per_step": dom_n, "traffic": traffic,
+        "share_of_step": dom_ms / sum(v["ms_per_step"] for v in fam.values()) if fam else None,
+        "all_gemm": {"tflops": gemm_tf, "frac": gemm_tf / peaks["bf16_sustained"] if gemm_tf else None,
+                     "ms_per_step": gemm_ms, "launches_per_step": gemm_launches},
         "whole_step": {"tflops": total_fl / (ms_step / 1e3) / 1e12,
                        "frac_of_bf16_burst": total_fl / (ms_step / 1e3) / 1e12
                        / (peaks["bf16_burst"] * world),

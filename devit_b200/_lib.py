@@ -247,7 +247,7 @@ def gemm(a, b, *, precision=DEVIT_BF16, m=None, n=None, segs=None, out=None,
 
 TAGS = ["gemm_other", "gemm_patch", "gemm_qkv", "gemm_proj", "gemm_fc1", "gemm_fc2",
         "gemm_fusion", "gemm_head", "attention", "layernorm", "gather_ln", "im2col",
-        "token_prefix"]
+        "token_prefix", "gemm_mlp_fused"]
 
 
 def profile_enable(on: bool) -> None:

@@ -527,7 +527,7 @@ extern "C" int devit_mlp_fused(const devit_mlp_args* a, void* stream_v) {
   int clusters = num_sms() / 2;
   if (clusters > num_pairs) clusters = num_pairs;
   {
-    ProfScope ps(kTagGemmFc2, stream);
+    ProfScope ps(kTagMlpFused, stream);
     mlp_fused_kernel<<<clusters * 2, kMlpThreads, kMlpSmem, stream>>>(tY, tW1, tW2, tX, tXB, p);
   }
   DEVIT_CUDA_OK(cudaGetLastError());

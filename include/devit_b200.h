@@ -69,7 +69,7 @@ enum {
   DEVIT_TAG_GEMM_PROJ = 3, DEVIT_TAG_GEMM_FC1 = 4, DEVIT_TAG_GEMM_FC2 = 5,
   DEVIT_TAG_GEMM_FUSION = 6, DEVIT_TAG_GEMM_HEAD = 7, DEVIT_TAG_ATTENTION = 8,
   DEVIT_TAG_LAYERNORM = 9, DEVIT_TAG_GATHER_LN = 10, DEVIT_TAG_IM2COL = 11,
-  DEVIT_TAG_PREFIX = 12, DEVIT_NUM_TAGS = 16
+  DEVIT_TAG_PREFIX = 12, DEVIT_TAG_MLP_FUSED = 13, DEVIT_NUM_TAGS = 16
 };
 int devit_profile_enable(int on);
 int devit_profile_collect(double* ms_by_tag, long long* count_by_tag);

@@ -18,7 +18,9 @@ KEYS = [
     ("launch__registers_per_thread", "regs/thread"),
     ("launch__shared_mem_per_block_dynamic", "dyn smem/block"),
     ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM throughput %"),
-    ("sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "tensor pipe active % (realtime)"),
+    ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "tensor pipe active % of elapsed"),
+    ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor pipe active % of SM-active"),
+    ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue slots busy %"),
     ("sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg", "hmma subpipe active cycles (avg/TPC)"),
     ("sm__inst_executed_pipe_uniform.sum", "uniform-pipe insts"),
     ("sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "tensor-memory (TMA/UMMA smem) active %"),

@@ -41,6 +41,15 @@ if which in ("gemm", "all"):
                ln_stats=stats, ln_colsum=c11, ln_dim=D, ln_eps=1e-6)
         L.gemm(hid, w2, bias=b2, resid=x, out=x, out_kind=L.OUT_F32, tag=5, out_bf16=xb,
                stats_out=stats)
+if which in ("mlp", "all"):
+    for F_ in (F, 1536):
+        w1, c11, c21 = rnd(F_, D, scale=.05), rnd(F_, dt=torch.float32), rnd(F_, dt=torch.float32)
+        w2, b2 = rnd(D, F_, scale=.05), rnd(D, dt=torch.float32)
+        stats6 = torch.zeros(6, M, 2, device=dev)
+        stats6[0] = stats1[0]
+        so = torch.empty(4, M, 2, device=dev)
+        for _ in range(reps):
+            L.mlp_fused(x, xb, stats6, w1, c11, c21, w2, b2, 1e-6, xb_out=xb, stats_out=so)
 if which in ("attn", "all"):
     qkv = rnd(M, 192 * H)
     for _ in range(reps):

@@ -108,6 +108,13 @@ _SIGS = {
                                   C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p]),
     "devit_im2col_patch16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                        C.c_int32, C.c_int64, C.c_void_p]),
+    "devit_im2col_tokens": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                      C.c_int32, C.c_int32, C.c_int64, C.c_void_p]),
+    "devit_token_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                   C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "devit_vit_forward_patches": (C.c_int, [C.POINTER(VitDesc), C.c_void_p, C.c_int64, C.c_int32,
+                                            C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                                            C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),
     "devit_token_prefix": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                      C.c_int32, C.c_int32, C.c_void_p]),
     "devit_gather_ln": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -260,6 +267,22 @@ def profile_collect() -> dict:
     cnt = (C.c_longlong * 16)()
     check(load().devit_profile_collect(ms, cnt))
     return {TAGS[i]: (ms[i], cnt[i]) for i in range(len(TAGS)) if cnt[i]}
+
+
+def im2col_tokens(images, num_prefix, precision=DEVIT_BF16):
+    """Token-row patch matrix of an NCHW fp32 batch (see devit_im2col_tokens): bf16
+    [B*tokens, C*256], or fp32 hi/lo planes [2, B*tokens, C*256] in the DEVIT_FP32 mode."""
+    B, Cn, H, W = images.shape
+    rows, k = B * (num_prefix + (H // 16) * (W // 16)), Cn * 256
+    if precision == DEVIT_BF16:
+        a = torch.empty(rows, k, device=images.device, dtype=torch.bfloat16)
+        kind, plane = OUT_BF16, 0
+    else:
+        a = torch.empty(2, rows, k, device=images.device, dtype=torch.float32)
+        kind, plane = OUT_F32_SPLIT, rows * k
+    check(load().devit_im2col_tokens(ptr(images), ptr(a), B, Cn, H, num_prefix, kind, plane,
+                                     stream_ptr()))
+    return a
 
 
 def rowstats(x):

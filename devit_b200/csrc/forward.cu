@@ -56,7 +56,7 @@ static int plan_layout(const devit_vit_desc* d, int batch, VitLayout* L) {
   off = align_up(off + static_cast<size_t>(L->M) * d->dim * pe, 256);
   L->off_qkv = off;
   const size_t qkv_b = static_cast<size_t>(L->M) * 3 * L->max_heads * 64 * pe;
-  const size_t patch_b = static_cast<size_t>(batch) * L->grid * L->grid * d->chans * 256 * pe;
+  const size_t patch_b = static_cast<size_t>(L->M) * d->chans * 256 * pe;  // token-row patches
   off = align_up(off + (qkv_b > patch_b ? qkv_b : patch_b), 256);
   L->off_o = off;
   off = align_up(off + static_cast<size_t>(L->M) * L->max_heads * 64 * pe, 256);
@@ -98,16 +98,17 @@ extern "C" size_t devit_vit_workspace_bytes(const devit_vit_desc* desc, int32_t 
   return L.total;
 }
 
-extern "C" int devit_vit_forward(const devit_vit_desc* d, const float* images, int32_t batch,
-                                 void* workspace, size_t workspace_bytes, float* feats_f32,
-                                 void* feats_op, int64_t feats_op_plane_stride, float* x_out,
-                                 int32_t num_layers_run, void* stream) {
+static int vit_forward_impl(const devit_vit_desc* d, const float* images, const void* patches,
+                            int64_t patches_plane_stride, int32_t batch, void* workspace,
+                            size_t workspace_bytes, float* feats_f32, void* feats_op,
+                            int64_t feats_op_plane_stride, float* x_out, int32_t num_layers_run,
+                            void* stream) {
   int rc = check_device();
   if (rc) return rc;
   VitLayout L{};
   rc = plan_layout(d, batch, &L);
   if (rc) return rc;
-  DEVIT_REQUIRE(images && workspace, "devit_vit_forward: null pointer");
+  DEVIT_REQUIRE((images || patches) && workspace, "devit_vit_forward: null pointer");
   DEVIT_REQUIRE(reinterpret_cast<uintptr_t>(workspace) % 256 == 0,
                 "devit_vit_forward: workspace must be 256-byte aligned");
   if (workspace_bytes < L.total)
@@ -127,36 +128,7 @@ extern "C" int devit_vit_forward(const devit_vit_desc* d, const float* images, i
   const int kp = d->chans * 256;
   const long long Mp = static_cast<long long>(batch) * P;
 
-  // ---- patch embedding as a GEMM; the epilogue adds bias + pos_embed and scatters patch p of
-  //      image b to token row b*tokens + num_prefix + p            (models/de_vit.py:258-264)
-  rc = devit_im2col_patch16(images, qkv, batch, d->chans, d->img, opk, Mp * kp, stream);
-  if (rc) return rc;
-  if ((rc = sync_debug("im2col", -1, stream))) return rc;
-  devit_gemm_args g;
-  base_gemm(&g, prec);
-  g.m = static_cast<int>(Mp);
-  g.n = D;
-  g.a = qkv; g.a_rows = static_cast<int>(Mp); g.a_cols = kp; g.lda = kp; g.a_plane_stride = Mp * kp;
-  g.b = d->w_patch; g.b_rows = D; g.b_cols = kp; g.ldb = kp;
-  g.b_plane_stride = static_cast<long long>(D) * kp;
-  g.segs[0] = devit_gemm_seg{0, 0, 0, kp};
-  g.out = x; g.ldo = D; g.out_kind = DEVIT_OUT_F32;
-  g.bias = d->b_patch;
-  g.rowbias = d->pos; g.ld_rowbias = D;
-  g.rowmap_period = P; g.rowmap_stride = L.tokens; g.rowmap_off = d->num_prefix;
-  g.profile_tag = DEVIT_TAG_GEMM_PATCH;
-  rc = devit_gemm(&g, stream);
-  if (rc) return rc;
-  if ((rc = sync_debug("patch gemm", -1, stream))) return rc;
-  rc = devit_token_prefix(x, d->prefix, d->pos, batch, L.tokens, D, d->num_prefix, stream);
-  if (rc) return rc;
-  if ((rc = sync_debug("prefix", -1, stream))) return rc;
-
   const int nl = (num_layers_run < 0 || num_layers_run > d->depth) ? d->depth : num_layers_run;
-  // LayerNorm folding (bf16 mode, host packed gamma-folded weights): no LayerNorm kernel and no
-  // normalised tensor at all.  `y` holds the bf16 copy of the residual stream, written by the
-  // epilogue of whichever GEMM last updated x together with the rows' partial (sum, sum^2); the
-  // QKV / fc1 GEMMs consume both and apply mean / rstd in their epilogue.
   int n_folded = 0;
   for (int l = 0; l < d->depth; ++l) n_folded += (d->layers[l].cs_qkv && d->layers[l].cs_fc1) ? 1 : 0;
   const bool fold = n_folded == d->depth;
@@ -165,16 +137,54 @@ extern "C" int devit_vit_forward(const devit_vit_desc* d, const float* images, i
   DEVIT_REQUIRE(!fold || (prec == DEVIT_BF16 && D % 128 == 0 && L.stat_parts <= 6),
                 "devit_vit_forward: LayerNorm-folded weights need DEVIT_BF16 and dim in {128, 256, "
                 "384} (got dim %d)", D);
+  float* stats = reinterpret_cast<float*>(ws + L.off_stats);
+  int parts = 1;
+
+  // ---- patch embedding as a residual GEMM over TOKEN rows (models/de_vit.py:258-264):
+  //      A = token-row patch matrix (zero rows for cls / dist), x = pos (+ cls/dist - bias),
+  //      x += A Wp^T + bias through the coalesced TMA epilogue.  With LayerNorm folding the same
+  //      epilogue also emits the bf16 copy + row sums the first QKV GEMM consumes.
+  const void* a_patch = patches;
+  long long a_plane = patches_plane_stride;
+  if (!a_patch) {
+    a_plane = M * kp;
+    rc = devit_im2col_tokens(images, qkv, batch, d->chans, d->img, d->num_prefix, opk, a_plane,
+                             stream);
+    if (rc) return rc;
+    if ((rc = sync_debug("im2col", -1, stream))) return rc;
+    a_patch = qkv;
+  }
+  rc = devit_token_init(x, d->prefix, d->pos, d->b_patch, batch, L.tokens, D, d->num_prefix,
+                        stream);
+  if (rc) return rc;
+  if ((rc = sync_debug("token init", -1, stream))) return rc;
+  devit_gemm_args g;
+  base_gemm(&g, prec);
+  g.m = static_cast<int>(M);
+  g.n = D;
+  g.a = a_patch; g.a_rows = static_cast<int>(M); g.a_cols = kp; g.lda = kp; g.a_plane_stride = a_plane;
+  g.b = d->w_patch; g.b_rows = D; g.b_cols = kp; g.ldb = kp;
+  g.b_plane_stride = static_cast<long long>(D) * kp;
+  g.segs[0] = devit_gemm_seg{0, 0, 0, kp};
+  g.out = x; g.ldo = D; g.out_kind = DEVIT_OUT_F32;
+  g.bias = d->b_patch; g.resid = x; g.ldr = D;
+  if (fold && nl > 0) {
+    g.out_bf16 = y; g.ld_out_bf16 = D; g.stats_out = stats;
+    parts = L.stat_parts;
+  }
+  g.profile_tag = DEVIT_TAG_GEMM_PATCH;
+  rc = devit_gemm(&g, stream);
+  if (rc) return rc;
+  if ((rc = sync_debug("patch gemm", -1, stream))) return rc;
+
+  // LayerNorm folding (bf16 mode, host packed gamma-folded weights): no LayerNorm kernel and no
+  // normalised tensor at all.  `y` holds the bf16 copy of the residual stream, written by the
+  // epilogue of whichever GEMM last updated x together with the rows' partial (sum, sum^2); the
+  // QKV / fc1 GEMMs consume both and apply mean / rstd in their epilogue.
   static int fused_mlp = -1;  // DEVIT_FUSED_MLP=0: separate fc1 / fc2 GEMMs (comparison)
   if (fused_mlp < 0) {
     const char* e = getenv("DEVIT_FUSED_MLP");
     fused_mlp = (e && e[0] == '0') ? 0 : 1;
-  }
-  float* stats = reinterpret_cast<float*>(ws + L.off_stats);
-  int parts = 1;
-  if (fold && nl > 0) {
-    rc = devit_rowstats(x, y, stats, M, D, stream);
-    if (rc) return rc;
   }
   for (int l = 0; l < nl; ++l) {
     const devit_layer_desc& w = d->layers[l];
@@ -293,4 +303,26 @@ extern "C" int devit_vit_forward(const devit_vit_desc* d, const float* images, i
     if (rc) return rc;
   }
   return DEVIT_OK;
+}
+
+extern "C" int devit_vit_forward(const devit_vit_desc* d, const float* images, int32_t batch,
+                                 void* workspace, size_t workspace_bytes, float* feats_f32,
+                                 void* feats_op, int64_t feats_op_plane_stride, float* x_out,
+                                 int32_t num_layers_run, void* stream) {
+  DEVIT_REQUIRE(images, "devit_vit_forward: null images");
+  return vit_forward_impl(d, images, nullptr, 0, batch, workspace, workspace_bytes, feats_f32,
+                          feats_op, feats_op_plane_stride, x_out, num_layers_run, stream);
+}
+
+extern "C" int devit_vit_forward_patches(const devit_vit_desc* d, const void* patches,
+                                         int64_t patches_plane_stride, int32_t batch,
+                                         void* workspace, size_t workspace_bytes, float* feats_f32,
+                                         void* feats_op, int64_t feats_op_plane_stride,
+                                         float* x_out, int32_t num_layers_run, void* stream) {
+  DEVIT_REQUIRE(patches, "devit_vit_forward_patches: null patches");
+  DEVIT_REQUIRE(reinterpret_cast<uintptr_t>(patches) % 16 == 0,
+                "devit_vit_forward_patches: patches must be 16-byte aligned");
+  return vit_forward_impl(d, nullptr, patches, patches_plane_stride, batch, workspace,
+                          workspace_bytes, feats_f32, feats_op, feats_op_plane_stride, x_out,
+                          num_layers_run, stream);
 }

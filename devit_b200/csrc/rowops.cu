@@ -131,10 +131,33 @@ __global__ void token_prefix_kernel(float* __restrict__ x, const float* __restri
   x[static_cast<long long>(img) * tokens * dim + r] = prefix[r] + pos[r];
 }
 
+// x[b, j, :] = pos[j, :] + (j < num_prefix ? prefix[j, :] - bias : 0): the residual-stream
+// initial value the patch-embedding GEMM (+ bias) is accumulated onto (include/devit_b200.h).
+__global__ void __launch_bounds__(256)
+token_init_kernel(float* __restrict__ x, const float* __restrict__ prefix,
+                  const float* __restrict__ pos, const float* __restrict__ bias, int batch,
+                  int tokens, int dim4, int num_prefix) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long per_img = static_cast<long long>(tokens) * dim4;
+  if (i >= batch * per_img) return;
+  const int r = static_cast<int>(i % per_img);  // (token, float4 column) inside the image
+  const int j = r / dim4, c = r - j * dim4;
+  float4 v = __ldg(reinterpret_cast<const float4*>(pos) + r);
+  if (j < num_prefix) {
+    const float4 pf = __ldg(reinterpret_cast<const float4*>(prefix) + r);
+    v.x += pf.x; v.y += pf.y; v.z += pf.z; v.w += pf.w;
+    if (bias) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + c);
+      v.x -= b.x; v.y -= b.y; v.z -= b.z; v.w -= b.w;
+    }
+  }
+  reinterpret_cast<float4*>(x)[i] = v;
+}
+
 // One thread converts 4 horizontally adjacent pixels (one float4) of one channel row.
 __global__ void __launch_bounds__(256)
 im2col16_kernel(const float* __restrict__ img, void* __restrict__ a, int batch, int chans, int hw,
-                int out_kind, long long plane) {
+                int out_kind, long long plane, int row_off, int rows_per_img) {
   const int w4 = hw >> 2;
   const long long total = static_cast<long long>(batch) * chans * hw * w4;
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -148,7 +171,8 @@ im2col16_kernel(const float* __restrict__ img, void* __restrict__ a, int batch, 
   const float4 v = __ldg(reinterpret_cast<const float4*>(img) + i);
   const int g = hw >> 4;
   const int x = x4 << 2;
-  const long long m = (static_cast<long long>(b) * g + (y >> 4)) * g + (x >> 4);
+  // patch (gy, gx) of image b -> row b * rows_per_img + row_off + gy * g + gx
+  const long long m = static_cast<long long>(b) * rows_per_img + row_off + (y >> 4) * g + (x >> 4);
   const long long k = static_cast<long long>(c) * 256 + (y & 15) * 16 + (x & 15);
   const long long o = m * (static_cast<long long>(chans) * 256) + k;
   if (out_kind == DEVIT_OUT_BF16) {
@@ -270,7 +294,58 @@ extern "C" int devit_im2col_patch16(const float* images, void* a, int32_t batch,
   {
     ProfScope ps(kTagIm2col, stream);
     im2col16_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
-        images, a, batch, chans, hw, out_kind, out_plane_stride);
+        images, a, batch, chans, hw, out_kind, out_plane_stride, 0, (hw / 16) * (hw / 16));
+  }
+  DEVIT_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return DEVIT_OK;
+}
+
+extern "C" int devit_im2col_tokens(const float* images, void* a, int32_t batch, int32_t chans,
+                                   int32_t hw, int32_t num_prefix, int32_t out_kind,
+                                   int64_t out_plane_stride, void* stream_v) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  int rc = check_device();
+  if (rc) return rc;
+  DEVIT_REQUIRE(images && a, "devit_im2col_tokens: null pointer");
+  DEVIT_REQUIRE(batch > 0 && chans > 0 && hw > 0 && hw % 16 == 0 && num_prefix >= 0,
+                "devit_im2col_tokens: image side %d must be a positive multiple of 16", hw);
+  DEVIT_REQUIRE(reinterpret_cast<uintptr_t>(images) % 16 == 0,
+                "devit_im2col_tokens: images must be 16-byte aligned");
+  const int tokens = num_prefix + (hw / 16) * (hw / 16);
+  const size_t esz = out_kind == DEVIT_OUT_BF16 ? 2 : 4;
+  const size_t k = static_cast<size_t>(chans) * 256;
+  const long long total = static_cast<long long>(batch) * chans * hw * (hw / 4);
+  {
+    ProfScope ps(kTagIm2col, stream);
+    if (num_prefix > 0) {  // zero rows for the cls / dist tokens of every image
+      DEVIT_CUDA_OK(cudaMemset2DAsync(a, tokens * k * esz, 0, num_prefix * k * esz, batch, stream));
+      if (out_kind == DEVIT_OUT_F32_SPLIT)
+        DEVIT_CUDA_OK(cudaMemset2DAsync(static_cast<float*>(a) + out_plane_stride, tokens * k * esz,
+                                        0, num_prefix * k * esz, batch, stream));
+    }
+    im2col16_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+        images, a, batch, chans, hw, out_kind, out_plane_stride, num_prefix, tokens);
+  }
+  DEVIT_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return DEVIT_OK;
+}
+
+extern "C" int devit_token_init(float* x, const float* prefix, const float* pos,
+                                const float* bias, int32_t batch, int32_t tokens, int32_t dim,
+                                int32_t num_prefix, void* stream_v) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  int rc = check_device();
+  if (rc) return rc;
+  DEVIT_REQUIRE(x && prefix && pos, "devit_token_init: null pointer");
+  DEVIT_REQUIRE(batch > 0 && num_prefix >= 0 && num_prefix <= tokens && dim > 0 && dim % 4 == 0,
+                "devit_token_init: bad shape");
+  const long long total = static_cast<long long>(batch) * tokens * (dim / 4);
+  {
+    ProfScope ps(kTagPrefix, stream);
+    token_init_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+        x, prefix, pos, bias, batch, tokens, dim / 4, num_prefix);
   }
   DEVIT_CUDA_OK(cudaGetLastError());
   count_launch();

@@ -68,12 +68,21 @@ class MultiViT(nn.Module):
             op = torch.empty(len(subs), T, B, D, device=x.device, dtype=torch.bfloat16)
         else:
             op = torch.empty(2, len(subs), T, B, D, device=x.device)
+        # every sub-model embeds the SAME images (models/ensemble_models.py:33): extract the
+        # patch matrix once when several of them run here and share the patch geometry
+        patches = None
+        if len(subs) > 1 and x.is_cuda and x.dim() == 4:
+            geo = {(bb.patch_embed.img_size, bb.patch_embed.proj.weight.shape[1:], bb.num_tokens)
+                   for bb in (self.backbones[s] for s in subs)}
+            if len(geo) == 1 and tuple(x.shape[2:]) == tuple(bb0.patch_embed.img_size):
+                patches = L.im2col_tokens(x.float().contiguous(), bb0.num_tokens, prec)
         for i, s in enumerate(subs):
             bb = self.backbones[s]
             if bb.precision != self.precision:
                 bb.set_precision(self.precision)
             bb.features_into(x, feats_f32=f32[i],
-                             feats_op=op[i] if prec == L.DEVIT_BF16 else op[:, i])
+                             feats_op=op[i] if prec == L.DEVIT_BF16 else op[:, i],
+                             patches=patches)
         return f32, op
 
     def forward(self, x):

@@ -339,17 +339,28 @@ class VisionTransformer(nn.Module):
         return x.float().contiguous()
 
     @torch.no_grad()
-    def features_into(self, x, feats_f32=None, feats_op=None, x_out=None, num_layers=-1):
+    def features_into(self, x, feats_f32=None, feats_op=None, x_out=None, num_layers=-1,
+                      patches=None):
         """Fused forward of the compacted sub-model: images -> LayerNormed cls(/dist) rows,
-        written into caller-provided slabs ([num_tokens, B, D] fp32 and/or operand format)."""
+        written into caller-provided slabs ([num_tokens, B, D] fp32 and/or operand format).
+        `patches` (optional): the token-row patch matrix of x from ``L.im2col_tokens`` -- the
+        sub-models of an ensemble embed the same images, so MultiViT extracts it once."""
         x = self._check_input(x)
         pk = self.packed(x.device)
         B = x.shape[0]
         ws = packing.workspace(x.device, pk.workspace_bytes(B))
         plane = feats_op.stride(0) if (feats_op is not None and feats_op.dim() == 4) else 0
-        L.check(L.load().devit_vit_forward(
-            C.byref(pk.desc), x.data_ptr(), B, ws.data_ptr(), ws.numel(),
-            L.ptr(feats_f32), L.ptr(feats_op), plane, L.ptr(x_out), num_layers, L.stream_ptr()))
+        if patches is None:
+            L.check(L.load().devit_vit_forward(
+                C.byref(pk.desc), x.data_ptr(), B, ws.data_ptr(), ws.numel(),
+                L.ptr(feats_f32), L.ptr(feats_op), plane, L.ptr(x_out), num_layers,
+                L.stream_ptr()))
+        else:
+            pplane = patches.stride(0) if patches.dim() == 3 else 0
+            L.check(L.load().devit_vit_forward_patches(
+                C.byref(pk.desc), patches.data_ptr(), pplane, B, ws.data_ptr(), ws.numel(),
+                L.ptr(feats_f32), L.ptr(feats_op), plane, L.ptr(x_out), num_layers,
+                L.stream_ptr()))
 
     def _feature_slabs(self, B, device, want_op=False):
         f32 = torch.empty(self.num_tokens, B, self.embed_dim, device=device)

@@ -235,6 +235,21 @@ int devit_im2col_patch16(const float* images, void* a, int32_t batch, int32_t ch
                          int32_t hw, int32_t out_kind, int64_t out_plane_stride, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * devit_im2col_tokens / devit_token_init: the same patch embedding laid out so that it is a plain
+ * residual GEMM over TOKEN rows.  im2col_tokens writes A[batch * tokens, chans*256] with
+ * tokens = num_prefix + (hw/16)^2: the first num_prefix rows of every image are zero, row
+ * num_prefix + p holds patch p.  token_init writes x[b, j, :] = pos[j, :] + (j < num_prefix ?
+ * prefix[j, :] - bias : 0), so that  x += A W^T + bias  yields cls/dist + pos on the prefix rows
+ * and patch embedding + pos on the others (timm PatchEmbed + models/de_vit.py:258-264) through the
+ * coalesced TMA epilogue, and A can be shared by every sub-model that sees the same images.
+ * ------------------------------------------------------------------------------------- */
+int devit_im2col_tokens(const float* images, void* a, int32_t batch, int32_t chans, int32_t hw,
+                        int32_t num_prefix, int32_t out_kind, int64_t out_plane_stride,
+                        void* stream);
+int devit_token_init(float* x, const float* prefix, const float* pos, const float* bias,
+                     int32_t batch, int32_t tokens, int32_t dim, int32_t num_prefix, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * devit_token_prefix: x[b, j, :] = prefix[j, :] + pos[j, :] for j < num_prefix
  * (cls / dist tokens; models/de_vit.py:259-264).  x fp32 [batch, tokens, dim].
  * ------------------------------------------------------------------------------------- */
@@ -309,6 +324,16 @@ int devit_vit_forward(const devit_vit_desc* desc, const float* images, int32_t b
                       void* workspace, size_t workspace_bytes, float* feats_f32, void* feats_op,
                       int64_t feats_op_plane_stride, float* x_out, int32_t num_layers_run,
                       void* stream);
+
+/* Same, starting from the token-row patch matrix `patches` (devit_im2col_tokens output in the
+ * descriptor's operand format; for DEVIT_FP32 the lo plane follows at patches_plane_stride
+ * elements) instead of the images: the N sub-models of an ensemble all embed the SAME images
+ * (models/ensemble_models.py:33), so the host extracts the patches once per batch. */
+int devit_vit_forward_patches(const devit_vit_desc* desc, const void* patches,
+                              int64_t patches_plane_stride, int32_t batch, void* workspace,
+                              size_t workspace_bytes, float* feats_f32, void* feats_op,
+                              int64_t feats_op_plane_stride, float* x_out, int32_t num_layers_run,
+                              void* stream);
 
 /* In DEVIT_FP32 every weight matrix pointer in the descriptors addresses the hi plane and the
  * lo plane follows at + rows*cols elements (plane stride = rows * ld). */

@@ -338,6 +338,7 @@ attn_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
+  griddep_launch_dependents();
 
   if (warp == 8) {
     if (lane == 0) {
@@ -363,6 +364,7 @@ attn_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   const int first = blockIdx.x, step = gridDim.x;
+  griddep_wait();  // qkv is the previous kernel's output
 
   if (warp == 8) {
     // ------------------------------------------------------------ control: TMA + MMA issue
@@ -739,9 +741,20 @@ static int launch_attn_persist(const void* qkv, void* out, int batch, int tokens
   const int grid = items < num_sms() ? items : num_sms();
   {
     ProfScope ps(kTagAttention, stream);
-    attn_persist_kernel<KVP><<<grid, kPersistThreads, Cfg::kSmemBytes, stream>>>(
-        tq, tkv, static_cast<__nv_bfloat16*>(out), tokens, heads, items,
-        scale * 1.4426950408889634f, getenv("DEVIT_ATTN_LOCKSTEP") ? 0 : 1, g_attn_trace);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kPersistThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    DEVIT_CUDA_OK(cudaLaunchKernelEx(&cfg, attn_persist_kernel<KVP>, tq, tkv,
+                                     static_cast<__nv_bfloat16*>(out), tokens, heads, items,
+                                     scale * 1.4426950408889634f,
+                                     getenv("DEVIT_ATTN_LOCKSTEP") ? 0 : 1, g_attn_trace));
   }
   DEVIT_CUDA_OK(cudaGetLastError());
   count_launch();

@@ -1,3 +1,5 @@
+#include <cstdlib>
+
 #include "common.cuh"
 
 #include <atomic>
@@ -17,6 +19,15 @@ int set_error(int code, const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
   return code;
+}
+
+int pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("DEVIT_PDL");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on;
 }
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }

@@ -28,6 +28,9 @@ struct ProfScope {
   ~ProfScope();
 };
 
+// 1 unless DEVIT_PDL=0: launch the layer-loop kernels with programmatic stream serialization
+int pdl_enabled();
+
 #define DEVIT_CUDA_OK(expr)                                                              \
   do {                                                                                   \
     cudaError_t _e = (expr);                                                             \

@@ -274,6 +274,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
   const int num_clusters = gridDim.x / CL;
   const bool leader = cta_rank == 0;
 
+  griddep_launch_dependents();  // the next kernel's prologue may overlap this kernel
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);
     tma_prefetch_desc(&tmB0);
@@ -311,6 +312,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   const int total_kb = p.total_kb;
+  griddep_wait();  // operands / residual come from (and outputs may alias buffers of) earlier kernels
 
   const int num_m = (p.M + kBlockM - 1) / kBlockM;
   const int num_n = (p.N + BN - 1) / BN;
@@ -827,13 +829,22 @@ static int launch_gemm(const CUtensorMap* tm, const GemmKParams& p, cudaStream_t
   cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CL;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (CL > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = CL;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = CL > 1 ? 1 : 0;
+  cfg.numAttrs = na;
   {
     ProfScope ps(tag, stream);
     DEVIT_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, KIND, CL, RES>, tm[0], tm[1], tm[2], tm[3],

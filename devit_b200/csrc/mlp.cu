@@ -58,6 +58,7 @@ extern long long* g_attn_trace;  // devit_debug_set_trace buffer (shared)
 
 struct MlpParams {
   long long* trace;
+  int stagger;  // clocks by which every other cluster delays its first tile (see the kernel)
   int M, F_ld, num_chunks;
   const float* c1;
   const float* c2;
@@ -111,6 +112,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
   const int num_pairs = (p.M + 255) / 256;
   const int NC = p.num_chunks;
 
+  griddep_launch_dependents();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmY);
     tma_prefetch_desc(&tmW1);
@@ -142,6 +144,16 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  griddep_wait();  // xb / x / ln_stats are outputs of the previous kernels
+
+  // Every cluster alternates a tensor-bound phase (hidden chunks, no HBM traffic to speak of)
+  // with an HBM-bound one (final epilogue + refill: ~0.6 MB per CTA).  Started together, all
+  // 148 SMs stream at the same time and compute at the same time; delaying every other cluster
+  // by about half a tile lets one half compute while the other half owns the HBM.
+  if (p.stagger > 0 && (cluster_id & 1)) {
+    const long long t0 = clock64();
+    while (clock64() - t0 < p.stagger) __nanosleep(500);
+  }
 
   // width of chunk c (multiple of 16; only the last chunk can be narrower than 64)
   auto chunk_n = [&](int c) -> int {
@@ -523,12 +535,30 @@ extern "C" int devit_mlp_fused(const devit_mlp_args* a, void* stream_v) {
   p.xb_out = static_cast<__nv_bfloat16*>(a->xb_out);
   p.stats_out = a->stats_out;
   p.trace = g_attn_trace;
+  {
+    static int stagger = -1;  // DEVIT_MLP_STAGGER=<clocks> (0 = off)
+    if (stagger < 0) {
+      const char* e = getenv("DEVIT_MLP_STAGGER");
+      stagger = e ? atoi(e) : 10000;  // measured best of {0, 10k, 18k, 26k}: -1.5 .. -3.5 %
+    }
+    p.stagger = stagger;
+  }
   const int num_pairs = (a->m + 255) / 256;
   int clusters = num_sms() / 2;
   if (clusters > num_pairs) clusters = num_pairs;
   {
     ProfScope ps(kTagMlpFused, stream);
-    mlp_fused_kernel<<<clusters * 2, kMlpThreads, kMlpSmem, stream>>>(tY, tW1, tW2, tX, tXB, p);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(clusters * 2);
+    cfg.blockDim = dim3(kMlpThreads);
+    cfg.dynamicSmemBytes = kMlpSmem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    DEVIT_CUDA_OK(cudaLaunchKernelEx(&cfg, mlp_fused_kernel, tY, tW1, tW2, tX, tXB, p));
   }
   DEVIT_CUDA_OK(cudaGetLastError());
   count_launch();

@@ -134,9 +134,9 @@ static int vit_forward_impl(const devit_vit_desc* d, const float* images, const 
   const bool fold = n_folded == d->depth;
   DEVIT_REQUIRE(n_folded == 0 || fold, "devit_vit_forward: cs_qkv / cs_fc1 must be set for all "
                 "layers or for none");
-  DEVIT_REQUIRE(!fold || (prec == DEVIT_BF16 && D % 128 == 0 && L.stat_parts <= 6),
-                "devit_vit_forward: LayerNorm-folded weights need DEVIT_BF16 and dim in {128, 256, "
-                "384} (got dim %d)", D);
+  DEVIT_REQUIRE(!fold || (prec == DEVIT_BF16 && D % 128 == 0 && L.stat_parts <= 12),
+                "devit_vit_forward: LayerNorm-folded weights need DEVIT_BF16 and dim a multiple of "
+                "128 up to 768 (got dim %d)", D);
   float* stats = reinterpret_cast<float*>(ws + L.off_stats);
   int parts = 1;
 

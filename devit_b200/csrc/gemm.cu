@@ -27,7 +27,7 @@ namespace devit {
 constexpr int kBlockM = 128;
 constexpr int kEpiWarps = 8;
 constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
-constexpr int kMaxLnParts = 6;  // partial row sums a LayerNorm-folded GEMM can combine
+constexpr int kMaxLnParts = 12;  // partial row sums a LayerNorm-folded GEMM can combine
 constexpr int kMaxKSegs = 24;  // 8 logical segments x 3 passes in the 3xTF32 mode
 
 struct KSeg {

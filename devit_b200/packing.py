@@ -92,9 +92,9 @@ class PackedVit:
             d.ln1_g, d.ln1_b = f32(blk.norm1.weight), f32(blk.norm1.bias)
             d.ln2_g, d.ln2_b = f32(blk.norm2.weight), f32(blk.norm2.bias)
             wqk, bqk = wq[rows], bq[rows]
-            # (the consumer epilogue combines at most 6 partial row sums = 2 per 128 columns of
-            #  the residual stream, so wider models -- the D=768 teacher -- keep the LN kernel)
-            if precision == L.DEVIT_BF16 and fold_ln and dim % 128 == 0 and dim <= 384:
+            # (the consumer epilogue combines at most 12 partial row sums = 2 per 128 columns of
+            #  the residual stream: dim <= 768)
+            if precision == L.DEVIT_BF16 and fold_ln and dim % 128 == 0 and dim <= 768:
                 # LayerNorm folding (include/devit_b200.h, devit_gemm_args.ln_stats):
                 # LN(x) W^T + b = rstd (x (gamma.W)^T - mean c1) + c2 with c1 = rowsum of the
                 # folded weights AS THE TENSOR CORE SEES THEM (bf16-rounded), c2 = b + W beta.

@@ -139,7 +139,7 @@ typedef struct devit_gemm_args {
    * Consumer GEMM (bf16 output): `a` is the raw residual stream rounded to bf16, `b` holds the
    * gamma-folded weights, `bias` holds c2, `ln_colsum` holds c1 and `ln_stats` the per-row
    * partial sums [ln_parts][m][2] = (sum x, sum x^2) over disjoint column ranges of the fp32
-   * stream (1 <= ln_parts <= 6); the epilogue derives mean / rstd (biased variance over ln_dim, + ln_eps) per row.
+   * stream (1 <= ln_parts <= 12); the epilogue derives mean / rstd (biased variance over ln_dim, + ln_eps) per row.
    * Producer GEMM (fp32 output with `resid`, n % 128 == 0): additionally writes the bf16 copy
    * of its output to `out_bf16` and the partial row sums of its output to `stats_out`
    * [2 * n / 128][m][2] (one part per 64 output columns). */

@@ -84,6 +84,33 @@ def test_ensemble_vs_reference_golden(precision, shrunk):
 
 
 @pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_eight_way_1000_classes_vs_oracle(precision):
+    """BASELINE config C3 at a small batch: 8-way decomposition, ImageNet-1K fusion head
+    (8 K-segments of 384 into the 768-wide mlp, 1000-class classifiers), dense gates."""
+    n_sub, n_cls, bsz = 8, 1000, 3
+    x = synth.images(bsz, seed=77)
+    sds = [synth.dedeit_state_dict(s, with_heads=False) for s in range(n_sub)]
+    esd = synth.ensmlp_state_dict(n_sub, num_class=n_cls)
+    with torch.no_grad():
+        ref, _, _ = O.ensemble_logits(sds, esd, x, None)
+    mv = ensemble.MultiViT(model='dedeit', drop=0, drop_path=0.1,
+                           num_classes_list=[n_cls // n_sub] * n_sub, num_div=n_sub)
+    fuse = ensemble.EnsMLP(model='dedeit', num_class=n_cls, sub_size=384,
+                           num_classes_list=[n_cls // n_sub] * n_sub, teacher_size=768)
+    for s in range(n_sub):
+        mv.backbones[s].load_state_dict(sds[s])
+    fuse.load_state_dict(esd)
+    mv = mv.cuda().eval().set_precision(precision)
+    fuse = fuse.cuda().eval().set_precision(precision)
+    logits = fuse(mv(x.cuda()))
+    assert logits.shape == (bsz, n_cls)
+    r = rel(logits, ref)
+    assert r < TOL[precision], r
+    if precision == 'fp32':
+        assert torch.equal(logits.argmax(-1).cpu(), ref.argmax(-1))
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
 def test_plain_list_input_to_ensmlp(precision):
     """EnsMLP must also accept ordinary lists of tensors (not views of our slab)."""
     _, fuse = make_ensemble(precision, False)

@@ -126,3 +126,82 @@ def shrink_gates(sub_idx, hidden=1536, heads=6, layer=12, shrink_ratio=0.3):
     n_masks = [shrink.keep_mask(hidden, n_ratio[i], n_rank[i]) for i in range(layer)]
     h_masks = [shrink.keep_mask(heads, h_ratio[i], h_rank[i]) for i in range(layer)]
     return n_masks, h_masks
+
+
+# ------------------------------------------------------------------------------- CCT
+def cct_shapes(dim=256, layers=7, mlp_ratio=2, n_conv=1, tokens=256, num_classes=100,
+               in_planes=64, backbone=False):
+    """Ordered {key: shape} of the reference CCT state_dict (models/cct.py:38-136): tokenizer,
+    then classifier (or `encoders` for backbone=True, which has no fc)."""
+    pre = 'encoders.' if backbone else 'classifier.'
+    chans = [3] + [in_planes] * (n_conv - 1) + [dim]
+    shapes = {}
+    for i in range(n_conv):
+        shapes[f'tokenizer.conv_layers.{i}.0.weight'] = (chans[i + 1], chans[i], 3, 3)
+    shapes[pre + 'positional_emb'] = (1, tokens, dim)
+    shapes[pre + 'attention_pool.weight'] = (1, dim)
+    shapes[pre + 'attention_pool.bias'] = (1,)
+    f = int(dim * mlp_ratio)
+    for i in range(layers):
+        b = f'{pre}blocks.{i}.'
+        shapes[b + 'pre_norm.weight'] = (dim,)
+        shapes[b + 'pre_norm.bias'] = (dim,)
+        shapes[b + 'self_attn.qkv.weight'] = (3 * dim, dim)
+        shapes[b + 'self_attn.proj.weight'] = (dim, dim)
+        shapes[b + 'self_attn.proj.bias'] = (dim,)
+        shapes[b + 'linear1.weight'] = (f, dim)
+        shapes[b + 'linear1.bias'] = (f,)
+        shapes[b + 'norm1.weight'] = (dim,)
+        shapes[b + 'norm1.bias'] = (dim,)
+        shapes[b + 'linear2.weight'] = (dim, f)
+        shapes[b + 'linear2.bias'] = (dim,)
+    shapes[pre + 'norm.weight'] = (dim,)
+    shapes[pre + 'norm.bias'] = (dim,)
+    if not backbone:
+        shapes[pre + 'fc.weight'] = (num_classes, dim)
+        shapes[pre + 'fc.bias'] = (num_classes,)
+    return shapes
+
+
+def cct_state_dict(sub_idx, **shape_kw):
+    """Seeded synthetic CCT weights with every code path live (non-zero biases, LN affine != 1/0,
+    attention_pool that is not uniform)."""
+    gen = torch.Generator().manual_seed(3000 + sub_idx)
+    sd = {}
+    for key, shape in cct_shapes(**shape_kw).items():
+        if 'conv_layers' in key:
+            fan_in = shape[1] * 9
+            t = torch.randn(shape, generator=gen) * (2.0 / fan_in) ** 0.5
+        elif key.endswith('positional_emb'):
+            t = torch.randn(shape, generator=gen) * 0.2
+        elif 'norm' in key and key.endswith('weight'):
+            t = 1.0 + 0.1 * torch.randn(shape, generator=gen)
+        elif 'norm' in key and key.endswith('bias'):
+            t = 0.1 * torch.randn(shape, generator=gen)
+        elif 'attention_pool.weight' in key:
+            t = torch.randn(shape, generator=gen) * 0.1
+        elif key.endswith('bias'):
+            t = torch.randn(shape, generator=gen) * 0.02
+        elif key.endswith('fc.weight'):
+            t = torch.randn(shape, generator=gen) * 0.16
+        else:
+            t = torch.randn(shape, generator=gen) * 0.05
+        sd[key] = t
+    return sd
+
+
+def ensemble_cct_state_dict(n_sub=4, sub_size=256, teacher_size=None, num_classes=100, seed=4000):
+    gen = torch.Generator().manual_seed(seed)
+    sd = {}
+    width = n_sub * sub_size
+    if teacher_size is not None:
+        sd['cls_mlp.weight'] = torch.randn(teacher_size, width, generator=gen) * 0.03
+        sd['cls_mlp.bias'] = torch.randn(teacher_size, generator=gen) * 0.02
+        width = teacher_size
+    sd['cls_classifier.weight'] = torch.randn(num_classes, width, generator=gen) * 0.16
+    sd['cls_classifier.bias'] = torch.randn(num_classes, generator=gen) * 0.02
+    return sd
+
+
+def cifar_images(batch, seed=4321):
+    return torch.randn(batch, 3, 32, 32, generator=torch.Generator().manual_seed(seed))

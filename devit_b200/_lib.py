@@ -19,7 +19,7 @@ LIB_PATH = _PKG / "lib" / "libdevit_b200.so"
 ABI_VERSION = 2
 DEVIT_BF16, DEVIT_FP32 = 0, 1
 OUT_BF16, OUT_F32, OUT_F32_SPLIT = 0, 1, 2
-ACT_NONE, ACT_GELU_ERF = 0, 1
+ACT_NONE, ACT_GELU_ERF, ACT_RELU = 0, 1, 2
 
 
 class DevitError(RuntimeError):
@@ -89,6 +89,18 @@ class VitDesc(C.Structure):
     ]
 
 
+class CctDesc(C.Structure):
+    _fields_ = [
+        ("precision", C.c_int32), ("dim", C.c_int32), ("depth", C.c_int32),
+        ("img", C.c_int32), ("chans", C.c_int32), ("n_conv", C.c_int32),
+        ("conv_chans", C.c_int32 * 3), ("w_conv", C.c_void_p * 3), ("conv_kpad", C.c_int32 * 3),
+        ("pos", C.c_void_p), ("ln_eps", C.c_float),
+        ("norm_g", C.c_void_p), ("norm_b", C.c_void_p),
+        ("pool_w", C.c_void_p), ("pool_b", C.c_float),
+        ("layers", C.POINTER(LayerDesc)),
+    ]
+
+
 # name -> (restype, argtypes); this table is also what tests/test_abi.py checks against the header
 _SIGS = {
     "devit_abi_version": (C.c_int, []),
@@ -115,6 +127,16 @@ _SIGS = {
     "devit_vit_forward_patches": (C.c_int, [C.POINTER(VitDesc), C.c_void_p, C.c_int64, C.c_int32,
                                             C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
                                             C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),
+    "devit_cct_workspace_bytes": (C.c_size_t, [C.POINTER(CctDesc), C.c_int32]),
+    "devit_cct_forward": (C.c_int, [C.POINTER(CctDesc), C.c_void_p, C.c_int32, C.c_void_p,
+                                    C.c_size_t, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "devit_im2col3x3": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                  C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
+                                  C.c_int32, C.c_int64, C.c_void_p]),
+    "devit_maxpool3x3s2_cl": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
+                                        C.c_int32, C.c_int32, C.c_void_p]),
+    "devit_seqpool": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int32,
+                                C.c_int32, C.c_int32, C.c_void_p]),
     "devit_token_prefix": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                      C.c_int32, C.c_int32, C.c_void_p]),
     "devit_gather_ln": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

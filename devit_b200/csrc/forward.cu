@@ -98,6 +98,142 @@ extern "C" size_t devit_vit_workspace_bytes(const devit_vit_desc* desc, int32_t 
   return L.total;
 }
 
+// The transformer blocks (models/de_vit.py:103-121; models/utils/transformers.py:104-113 has the
+// same pre-norm structure) over a residual stream x [M, D] that already holds the embedded
+// tokens.  In `fold` mode y / stats must hold the bf16 copy of x and `parts` partial row sums.
+struct BlockBuffers {
+  float* x;
+  void* y;
+  void* qkv;
+  void* o;
+  void* hid;
+  float* stats;
+};
+
+static int run_blocks(const devit_layer_desc* layers, int nl, int prec, int D, float ln_eps,
+                      int batch, int tokens, long long M, const BlockBuffers& bufs, bool fold,
+                      int parts, int stat_parts, void* stream) {
+  int rc = DEVIT_OK;
+  const int opk = prec == DEVIT_BF16 ? DEVIT_OUT_BF16 : DEVIT_OUT_F32_SPLIT;
+  float* x = bufs.x;
+  void* y = bufs.y;
+  void* qkv = bufs.qkv;
+  void* o = bufs.o;
+  void* hid = bufs.hid;
+  float* stats = bufs.stats;
+  devit_gemm_args g;
+  static int fused_mlp = -1;  // DEVIT_FUSED_MLP=0: separate fc1 / fc2 GEMMs (comparison)
+  if (fused_mlp < 0) {
+    const char* e = getenv("DEVIT_FUSED_MLP");
+    fused_mlp = (e && e[0] == '0') ? 0 : 1;
+  }
+  for (int l = 0; l < nl; ++l) {
+    const devit_layer_desc& w = layers[l];
+    const int hd = w.heads * 64;
+    // x -> LN1 -> y                                              (models/de_vit.py:113)
+    if (!fold) {
+      rc = devit_layernorm(x, w.ln1_g, w.ln1_b, y, M, D, ln_eps, opk, M * D, stream);
+      if (rc) return rc;
+    }
+    // qkv = y Wqkv^T + b                                         (:67)
+    base_gemm(&g, prec);
+    g.m = static_cast<int>(M); g.n = 3 * hd;
+    g.a = y; g.a_rows = static_cast<int>(M); g.a_cols = D; g.lda = D; g.a_plane_stride = M * D;
+    g.b = w.w_qkv; g.b_rows = 3 * hd; g.b_cols = D; g.ldb = D;
+    g.b_plane_stride = static_cast<long long>(3 * hd) * D;
+    g.segs[0] = devit_gemm_seg{0, 0, 0, D};
+    g.out = qkv; g.ldo = 3 * hd; g.out_kind = opk; g.out_plane_stride = M * 3 * hd;
+    if ((rc = sync_debug("ln1", l, stream))) return rc;
+    g.bias = w.b_qkv;
+    if (fold) {
+      g.ln_stats = stats; g.ln_parts = parts; g.ln_dim = D; g.ln_eps = ln_eps;
+      g.ln_colsum = w.cs_qkv;
+    }
+    g.profile_tag = DEVIT_TAG_GEMM_QKV;
+    rc = devit_gemm(&g, stream);
+    if (rc) return rc;
+    if ((rc = sync_debug("qkv gemm", l, stream))) return rc;
+    // o = softmax(q k^T / 8) v  per kept head                    (:70-74)
+    rc = devit_attention(prec, qkv, M * 3 * hd, o, M * hd, batch, tokens, w.heads, 0.125f,
+                         stream);
+    if (rc) return rc;
+    if ((rc = sync_debug("attention", l, stream))) return rc;
+    // x += o Wproj^T + b                                         (:81, :114)
+    base_gemm(&g, prec);
+    g.m = static_cast<int>(M); g.n = D;
+    g.a = o; g.a_rows = static_cast<int>(M); g.a_cols = hd; g.lda = hd; g.a_plane_stride = M * hd;
+    g.b = w.w_proj; g.b_rows = D; g.b_cols = hd; g.ldb = hd;
+    g.b_plane_stride = static_cast<long long>(D) * hd;
+    g.segs[0] = devit_gemm_seg{0, 0, 0, hd};
+    g.out = x; g.ldo = D; g.out_kind = DEVIT_OUT_F32;
+    g.bias = w.b_proj; g.resid = x; g.ldr = D;
+    if (fold) {
+      g.out_bf16 = y; g.ld_out_bf16 = D; g.stats_out = stats;
+      parts = stat_parts;
+    }
+    g.profile_tag = DEVIT_TAG_GEMM_PROJ;
+    rc = devit_gemm(&g, stream);
+    if (rc) return rc;
+    if ((rc = sync_debug("proj gemm", l, stream))) return rc;
+    // x -> LN2 -> y                                              (:115)
+    if (!fold) {
+      rc = devit_layernorm(x, w.ln2_g, w.ln2_b, y, M, D, ln_eps, opk, M * D, stream);
+      if (rc) return rc;
+    }
+    const int F = w.hidden_ld;
+    if (fold && fused_mlp && D == 384) {
+      // x += gelu(LN2(x) W1^T + b1) W2^T + b2 in one kernel, hidden kept on chip   (:35-47, :115)
+      devit_mlp_args ma;
+      std::memset(&ma, 0, sizeof(ma));
+      ma.m = static_cast<int>(M); ma.dim = D; ma.hidden_ld = F;
+      ma.xb = y; ma.w1 = w.w_fc1; ma.c1 = w.cs_fc1; ma.c2 = w.b_fc1;
+      ma.ln_stats = stats; ma.ln_parts = parts; ma.ln_eps = ln_eps;
+      ma.w2 = w.w_fc2; ma.b2 = w.b_fc2; ma.x = x;
+      if (l + 1 < nl) { ma.xb_out = y; ma.stats_out = stats; }
+      rc = devit_mlp_fused(&ma, stream);
+      if (rc) return rc;
+      parts = 4;  // the fused kernel emits one partial row sum per 96 columns
+      if ((rc = sync_debug("fused mlp", l, stream))) return rc;
+      continue;
+    }
+    // hid = gelu(y W1^T + b1), kept neurons only                 (:36-37)
+    base_gemm(&g, prec);
+    g.m = static_cast<int>(M); g.n = F;
+    g.a = y; g.a_rows = static_cast<int>(M); g.a_cols = D; g.lda = D; g.a_plane_stride = M * D;
+    g.b = w.w_fc1; g.b_rows = F; g.b_cols = D; g.ldb = D;
+    g.b_plane_stride = static_cast<long long>(F) * D;
+    g.segs[0] = devit_gemm_seg{0, 0, 0, D};
+    g.out = hid; g.ldo = F; g.out_kind = opk; g.out_plane_stride = M * F;
+    if ((rc = sync_debug("ln2", l, stream))) return rc;
+    g.bias = w.b_fc1; g.act = DEVIT_ACT_GELU_ERF;
+    if (fold) {
+      g.ln_stats = stats; g.ln_parts = parts; g.ln_dim = D; g.ln_eps = ln_eps;
+      g.ln_colsum = w.cs_fc1;
+    }
+    g.profile_tag = DEVIT_TAG_GEMM_FC1;
+    rc = devit_gemm(&g, stream);
+    if (rc) return rc;
+    if ((rc = sync_debug("fc1 gemm", l, stream))) return rc;
+    // x += hid W2^T + b2                                         (:45, :115)
+    base_gemm(&g, prec);
+    g.m = static_cast<int>(M); g.n = D;
+    g.a = hid; g.a_rows = static_cast<int>(M); g.a_cols = F; g.lda = F; g.a_plane_stride = M * F;
+    g.b = w.w_fc2; g.b_rows = D; g.b_cols = F; g.ldb = F;
+    g.b_plane_stride = static_cast<long long>(D) * F;
+    g.segs[0] = devit_gemm_seg{0, 0, 0, F};
+    g.out = x; g.ldo = D; g.out_kind = DEVIT_OUT_F32;
+    g.bias = w.b_fc2; g.resid = x; g.ldr = D;
+    if (fold && l + 1 < nl) {  // the next layer's norm1 input (the final norm reads x itself)
+      g.out_bf16 = y; g.ld_out_bf16 = D; g.stats_out = stats;
+    }
+    g.profile_tag = DEVIT_TAG_GEMM_FC2;
+    rc = devit_gemm(&g, stream);
+    if (rc) return rc;
+    if ((rc = sync_debug("fc2 gemm", l, stream))) return rc;
+  }
+  return DEVIT_OK;
+}
+
 static int vit_forward_impl(const devit_vit_desc* d, const float* images, const void* patches,
                             int64_t patches_plane_stride, int32_t batch, void* workspace,
                             size_t workspace_bytes, float* feats_f32, void* feats_op,
@@ -181,114 +317,11 @@ static int vit_forward_impl(const devit_vit_desc* d, const float* images, const 
   // normalised tensor at all.  `y` holds the bf16 copy of the residual stream, written by the
   // epilogue of whichever GEMM last updated x together with the rows' partial (sum, sum^2); the
   // QKV / fc1 GEMMs consume both and apply mean / rstd in their epilogue.
-  static int fused_mlp = -1;  // DEVIT_FUSED_MLP=0: separate fc1 / fc2 GEMMs (comparison)
-  if (fused_mlp < 0) {
-    const char* e = getenv("DEVIT_FUSED_MLP");
-    fused_mlp = (e && e[0] == '0') ? 0 : 1;
-  }
-  for (int l = 0; l < nl; ++l) {
-    const devit_layer_desc& w = d->layers[l];
-    const int hd = w.heads * 64;
-    // x -> LN1 -> y                                              (models/de_vit.py:113)
-    if (!fold) {
-      rc = devit_layernorm(x, w.ln1_g, w.ln1_b, y, M, D, d->ln_eps, opk, M * D, stream);
-      if (rc) return rc;
-    }
-    // qkv = y Wqkv^T + b                                         (:67)
-    base_gemm(&g, prec);
-    g.m = static_cast<int>(M); g.n = 3 * hd;
-    g.a = y; g.a_rows = static_cast<int>(M); g.a_cols = D; g.lda = D; g.a_plane_stride = M * D;
-    g.b = w.w_qkv; g.b_rows = 3 * hd; g.b_cols = D; g.ldb = D;
-    g.b_plane_stride = static_cast<long long>(3 * hd) * D;
-    g.segs[0] = devit_gemm_seg{0, 0, 0, D};
-    g.out = qkv; g.ldo = 3 * hd; g.out_kind = opk; g.out_plane_stride = M * 3 * hd;
-    if ((rc = sync_debug("ln1", l, stream))) return rc;
-    g.bias = w.b_qkv;
-    if (fold) {
-      g.ln_stats = stats; g.ln_parts = parts; g.ln_dim = D; g.ln_eps = d->ln_eps;
-      g.ln_colsum = w.cs_qkv;
-    }
-    g.profile_tag = DEVIT_TAG_GEMM_QKV;
-    rc = devit_gemm(&g, stream);
+  {
+    BlockBuffers bufs{x, y, qkv, o, hid, stats};
+    rc = run_blocks(d->layers, nl, prec, D, d->ln_eps, batch, L.tokens, M, bufs, fold, parts,
+                    L.stat_parts, stream);
     if (rc) return rc;
-    if ((rc = sync_debug("qkv gemm", l, stream))) return rc;
-    // o = softmax(q k^T / 8) v  per kept head                    (:70-74)
-    rc = devit_attention(prec, qkv, M * 3 * hd, o, M * hd, batch, L.tokens, w.heads, 0.125f,
-                         stream);
-    if (rc) return rc;
-    if ((rc = sync_debug("attention", l, stream))) return rc;
-    // x += o Wproj^T + b                                         (:81, :114)
-    base_gemm(&g, prec);
-    g.m = static_cast<int>(M); g.n = D;
-    g.a = o; g.a_rows = static_cast<int>(M); g.a_cols = hd; g.lda = hd; g.a_plane_stride = M * hd;
-    g.b = w.w_proj; g.b_rows = D; g.b_cols = hd; g.ldb = hd;
-    g.b_plane_stride = static_cast<long long>(D) * hd;
-    g.segs[0] = devit_gemm_seg{0, 0, 0, hd};
-    g.out = x; g.ldo = D; g.out_kind = DEVIT_OUT_F32;
-    g.bias = w.b_proj; g.resid = x; g.ldr = D;
-    if (fold) {
-      g.out_bf16 = y; g.ld_out_bf16 = D; g.stats_out = stats;
-      parts = L.stat_parts;
-    }
-    g.profile_tag = DEVIT_TAG_GEMM_PROJ;
-    rc = devit_gemm(&g, stream);
-    if (rc) return rc;
-    if ((rc = sync_debug("proj gemm", l, stream))) return rc;
-    // x -> LN2 -> y                                              (:115)
-    if (!fold) {
-      rc = devit_layernorm(x, w.ln2_g, w.ln2_b, y, M, D, d->ln_eps, opk, M * D, stream);
-      if (rc) return rc;
-    }
-    const int F = w.hidden_ld;
-    if (fold && fused_mlp && D == 384) {
-      // x += gelu(LN2(x) W1^T + b1) W2^T + b2 in one kernel, hidden kept on chip   (:35-47, :115)
-      devit_mlp_args ma;
-      std::memset(&ma, 0, sizeof(ma));
-      ma.m = static_cast<int>(M); ma.dim = D; ma.hidden_ld = F;
-      ma.xb = y; ma.w1 = w.w_fc1; ma.c1 = w.cs_fc1; ma.c2 = w.b_fc1;
-      ma.ln_stats = stats; ma.ln_parts = parts; ma.ln_eps = d->ln_eps;
-      ma.w2 = w.w_fc2; ma.b2 = w.b_fc2; ma.x = x;
-      if (l + 1 < nl) { ma.xb_out = y; ma.stats_out = stats; }
-      rc = devit_mlp_fused(&ma, stream);
-      if (rc) return rc;
-      parts = 4;  // the fused kernel emits one partial row sum per 96 columns
-      if ((rc = sync_debug("fused mlp", l, stream))) return rc;
-      continue;
-    }
-    // hid = gelu(y W1^T + b1), kept neurons only                 (:36-37)
-    base_gemm(&g, prec);
-    g.m = static_cast<int>(M); g.n = F;
-    g.a = y; g.a_rows = static_cast<int>(M); g.a_cols = D; g.lda = D; g.a_plane_stride = M * D;
-    g.b = w.w_fc1; g.b_rows = F; g.b_cols = D; g.ldb = D;
-    g.b_plane_stride = static_cast<long long>(F) * D;
-    g.segs[0] = devit_gemm_seg{0, 0, 0, D};
-    g.out = hid; g.ldo = F; g.out_kind = opk; g.out_plane_stride = M * F;
-    if ((rc = sync_debug("ln2", l, stream))) return rc;
-    g.bias = w.b_fc1; g.act = DEVIT_ACT_GELU_ERF;
-    if (fold) {
-      g.ln_stats = stats; g.ln_parts = parts; g.ln_dim = D; g.ln_eps = d->ln_eps;
-      g.ln_colsum = w.cs_fc1;
-    }
-    g.profile_tag = DEVIT_TAG_GEMM_FC1;
-    rc = devit_gemm(&g, stream);
-    if (rc) return rc;
-    if ((rc = sync_debug("fc1 gemm", l, stream))) return rc;
-    // x += hid W2^T + b2                                         (:45, :115)
-    base_gemm(&g, prec);
-    g.m = static_cast<int>(M); g.n = D;
-    g.a = hid; g.a_rows = static_cast<int>(M); g.a_cols = F; g.lda = F; g.a_plane_stride = M * F;
-    g.b = w.w_fc2; g.b_rows = D; g.b_cols = F; g.ldb = F;
-    g.b_plane_stride = static_cast<long long>(D) * F;
-    g.segs[0] = devit_gemm_seg{0, 0, 0, F};
-    g.out = x; g.ldo = D; g.out_kind = DEVIT_OUT_F32;
-    g.bias = w.b_fc2; g.resid = x; g.ldr = D;
-    if (fold && l + 1 < nl) {  // the next layer's norm1 input (the final norm reads x itself)
-      g.out_bf16 = y; g.ld_out_bf16 = D; g.stats_out = stats;
-    }
-    g.profile_tag = DEVIT_TAG_GEMM_FC2;
-    rc = devit_gemm(&g, stream);
-    if (rc) return rc;
-    if ((rc = sync_debug("fc2 gemm", l, stream))) return rc;
   }
   if (x_out) {
     DEVIT_CUDA_OK(cudaMemcpyAsync(x_out, x, static_cast<size_t>(M) * D * 4,
@@ -325,4 +358,181 @@ extern "C" int devit_vit_forward_patches(const devit_vit_desc* d, const void* pa
   return vit_forward_impl(d, nullptr, patches, patches_plane_stride, batch, workspace,
                           workspace_bytes, feats_f32, feats_op, feats_op_plane_stride, x_out,
                           num_layers_run, stream);
+}
+
+// ------------------------------------------------------------------------------- CCT
+namespace devit {
+
+struct CctLayout {
+  int tokens, max_hidden_ld, max_heads, stat_parts, planes, esz;
+  long long M;
+  size_t off_x, off_y, off_qkv, off_o, off_hid, off_stats, off_xn, off_a, off_c, off_p, total;
+};
+
+static int plan_cct(const devit_cct_desc* d, int batch, CctLayout* L) {
+  DEVIT_REQUIRE(d && d->layers, "devit_cct: null descriptor");
+  DEVIT_REQUIRE(d->precision == DEVIT_BF16 || d->precision == DEVIT_FP32,
+                "devit_cct: bad precision %d", d->precision);
+  DEVIT_REQUIRE(d->dim == 256 || d->dim == 384 || d->dim == 768,
+                "devit_cct: dim %d not in {256,384,768}", d->dim);
+  DEVIT_REQUIRE(d->n_conv >= 1 && d->n_conv <= 3 && d->depth > 0 && batch > 0 && d->chans > 0,
+                "devit_cct: bad geometry");
+  DEVIT_REQUIRE(d->img > 0 && d->img % (1 << d->n_conv) == 0, "devit_cct: image side %d", d->img);
+  DEVIT_REQUIRE(d->conv_chans[d->n_conv - 1] == d->dim,
+                "devit_cct: the last conv layer must produce dim channels");
+  L->planes = d->precision == DEVIT_BF16 ? 1 : 2;
+  L->esz = d->precision == DEVIT_BF16 ? 2 : 4;
+  const size_t pe = static_cast<size_t>(L->planes) * L->esz;
+  const int side = d->img >> d->n_conv;
+  L->tokens = side * side;
+  DEVIT_REQUIRE(L->tokens <= 256, "devit_cct: %d tokens exceed the attention kernel's 256", L->tokens);
+  L->M = static_cast<long long>(batch) * L->tokens;
+  L->max_heads = 0;
+  L->max_hidden_ld = 0;
+  for (int l = 0; l < d->depth; ++l) {
+    const devit_layer_desc& y = d->layers[l];
+    DEVIT_REQUIRE(y.heads >= 1 && y.heads * 64 <= d->dim, "devit_cct: layer %d heads %d", l, y.heads);
+    DEVIT_REQUIRE(y.hidden >= 1 && y.hidden_ld >= y.hidden && y.hidden_ld % 16 == 0,
+                  "devit_cct: layer %d hidden %d / ld %d", l, y.hidden, y.hidden_ld);
+    if (y.heads > L->max_heads) L->max_heads = y.heads;
+    if (y.hidden_ld > L->max_hidden_ld) L->max_hidden_ld = y.hidden_ld;
+  }
+  L->stat_parts = 2 * ((d->dim + 127) / 128);
+  size_t a_b = 0, c_b = 0, p_b = 0;
+  int hw = d->img, cin = d->chans;
+  for (int i = 0; i < d->n_conv; ++i) {
+    DEVIT_REQUIRE(d->w_conv[i] && d->conv_kpad[i] >= 9 * cin && d->conv_kpad[i] % 8 == 0 &&
+                      d->conv_chans[i] % 4 == 0,
+                  "devit_cct: conv layer %d (kpad %d for %d input channels)", i, d->conv_kpad[i], cin);
+    const size_t rows = static_cast<size_t>(batch) * hw * hw;
+    const size_t ab = rows * d->conv_kpad[i] * pe;
+    const size_t cb = rows * d->conv_chans[i] * (d->precision == DEVIT_BF16 ? 2 : 4);
+    const size_t pb = rows / 4 * d->conv_chans[i] * 4;
+    if (ab > a_b) a_b = ab;
+    if (cb > c_b) c_b = cb;
+    if (i + 1 < d->n_conv && pb > p_b) p_b = pb;
+    cin = d->conv_chans[i];
+    hw >>= 1;
+  }
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    const size_t at = off;
+    off = align_up(off + bytes, 256);
+    return at;
+  };
+  L->off_x = take(static_cast<size_t>(L->M) * d->dim * 4);
+  L->off_y = take(static_cast<size_t>(L->M) * d->dim * pe);
+  L->off_qkv = take(static_cast<size_t>(L->M) * 3 * L->max_heads * 64 * pe);
+  L->off_o = take(static_cast<size_t>(L->M) * L->max_heads * 64 * pe);
+  L->off_hid = take(static_cast<size_t>(L->M) * L->max_hidden_ld * pe);
+  L->off_stats = take(static_cast<size_t>(L->M) * L->stat_parts * 2 * sizeof(float));
+  L->off_xn = take(static_cast<size_t>(L->M) * d->dim * 4);
+  L->off_a = take(a_b);
+  L->off_c = take(c_b);
+  L->off_p = take(p_b);
+  L->total = off;
+  return DEVIT_OK;
+}
+
+}  // namespace devit
+
+extern "C" size_t devit_cct_workspace_bytes(const devit_cct_desc* desc, int32_t batch) {
+  CctLayout L{};
+  if (plan_cct(desc, batch, &L)) return 0;
+  return L.total;
+}
+
+extern "C" int devit_cct_forward(const devit_cct_desc* d, const float* images, int32_t batch,
+                                 void* workspace, size_t workspace_bytes, float* pooled,
+                                 float* x_out, int32_t num_layers_run, void* stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  CctLayout L{};
+  rc = plan_cct(d, batch, &L);
+  if (rc) return rc;
+  DEVIT_REQUIRE(images && workspace, "devit_cct_forward: null pointer");
+  DEVIT_REQUIRE(reinterpret_cast<uintptr_t>(workspace) % 256 == 0,
+                "devit_cct_forward: workspace must be 256-byte aligned");
+  if (workspace_bytes < L.total)
+    return set_error(DEVIT_ERR_WORKSPACE, "devit_cct_forward: workspace %zu < required %zu",
+                     workspace_bytes, L.total);
+  const int prec = d->precision;
+  const int opk = prec == DEVIT_BF16 ? DEVIT_OUT_BF16 : DEVIT_OUT_F32_SPLIT;
+  const int ck = prec == DEVIT_BF16 ? DEVIT_OUT_BF16 : DEVIT_OUT_F32;  // conv GEMM output
+  const int D = d->dim;
+  const long long M = L.M;
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  float* x = reinterpret_cast<float*>(ws + L.off_x);
+  void* y = ws + L.off_y;
+  float* stats = reinterpret_cast<float*>(ws + L.off_stats);
+  float* xn = reinterpret_cast<float*>(ws + L.off_xn);
+  void* sa = ws + L.off_a;
+  void* sc = ws + L.off_c;
+  float* sp = reinterpret_cast<float*>(ws + L.off_p);
+
+  // ---- tokenizer: n_conv x [conv3x3 (im2col + GEMM, ReLU epilogue) -> max-pool 3/2/1]
+  //      (models/utils/tokenizer.py:23-44); the last pool adds positional_emb and writes x.
+  const float* in = images;
+  int hw = d->img, cin = d->chans;
+  long long sb = static_cast<long long>(cin) * hw * hw, scs = static_cast<long long>(hw) * hw,
+            sy = hw, sx = 1;
+  for (int i = 0; i < d->n_conv; ++i) {
+    const long long rows = static_cast<long long>(batch) * hw * hw;
+    const int kpad = d->conv_kpad[i], cout = d->conv_chans[i];
+    rc = devit_im2col3x3(in, sa, batch, cin, hw, sb, scs, sy, sx, kpad, opk, rows * kpad, stream);
+    if (rc) return rc;
+    devit_gemm_args g;
+    base_gemm(&g, prec);
+    g.m = static_cast<int>(rows); g.n = cout;
+    g.a = sa; g.a_rows = g.m; g.a_cols = kpad; g.lda = kpad; g.a_plane_stride = rows * kpad;
+    g.b = d->w_conv[i]; g.b_rows = cout; g.b_cols = kpad; g.ldb = kpad;
+    g.b_plane_stride = static_cast<long long>(cout) * kpad;
+    g.segs[0] = devit_gemm_seg{0, 0, 0, kpad};
+    g.out = sc; g.ldo = cout; g.out_kind = ck;
+    g.act = DEVIT_ACT_RELU;
+    g.profile_tag = DEVIT_TAG_GEMM_PATCH;
+    rc = devit_gemm(&g, stream);
+    if (rc) return rc;
+    const bool last = i + 1 == d->n_conv;
+    rc = devit_maxpool3x3s2_cl(sc, ck, last ? x : sp, last ? d->pos : nullptr, batch, hw, cout,
+                               stream);
+    if (rc) return rc;
+    if ((rc = sync_debug("cct conv layer", i, stream))) return rc;
+    hw >>= 1;
+    cin = cout;
+    in = sp;  // channels-last [B, hw, hw, cout]
+    sb = static_cast<long long>(hw) * hw * cout; scs = 1; sy = static_cast<long long>(hw) * cout; sx = cout;
+  }
+
+  // ---- transformer blocks (shared with the ViT path)
+  const int nl = (num_layers_run < 0 || num_layers_run > d->depth) ? d->depth : num_layers_run;
+  int n_folded = 0;
+  for (int l = 0; l < d->depth; ++l) n_folded += (d->layers[l].cs_qkv && d->layers[l].cs_fc1) ? 1 : 0;
+  const bool fold = n_folded == d->depth;
+  DEVIT_REQUIRE(n_folded == 0 || fold, "devit_cct_forward: cs_qkv / cs_fc1 must be set for all "
+                "layers or for none");
+  DEVIT_REQUIRE(!fold || (prec == DEVIT_BF16 && D % 128 == 0 && L.stat_parts <= 12),
+                "devit_cct_forward: LayerNorm-folded weights need DEVIT_BF16 and dim %% 128 == 0");
+  if (fold && nl > 0) {
+    rc = devit_rowstats(x, y, stats, M, D, stream);
+    if (rc) return rc;
+  }
+  {
+    BlockBuffers bufs{x, y, ws + L.off_qkv, ws + L.off_o, ws + L.off_hid, stats};
+    rc = run_blocks(d->layers, nl, prec, D, d->ln_eps, batch, L.tokens, M, bufs, fold, 1,
+                    L.stat_parts, stream);
+    if (rc) return rc;
+  }
+  if (x_out)
+    DEVIT_CUDA_OK(cudaMemcpyAsync(x_out, x, static_cast<size_t>(M) * D * 4,
+                                  cudaMemcpyDeviceToDevice,
+                                  reinterpret_cast<cudaStream_t>(stream)));
+  // ---- final norm over every token + sequence pooling (models/utils/transformers.py:470-475)
+  if (pooled) {
+    rc = devit_layernorm(x, d->norm_g, d->norm_b, xn, M, D, d->ln_eps, DEVIT_OUT_F32, 0, stream);
+    if (rc) return rc;
+    rc = devit_seqpool(xn, d->pool_w, d->pool_b, pooled, batch, L.tokens, D, stream);
+    if (rc) return rc;
+  }
+  return DEVIT_OK;
 }

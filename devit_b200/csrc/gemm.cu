@@ -122,6 +122,9 @@ __device__ __forceinline__ void epilogue_store(const GemmKParams& p, float* v, i
   if (p.act == DEVIT_ACT_GELU_ERF) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+  } else if (p.act == DEVIT_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
   }
   if (p.rowbias) {
     const float* rb = p.rowbias + (long long)rb_row * p.ld_rowbias + col0;
@@ -215,6 +218,9 @@ __device__ __forceinline__ void bias_act32(const GemmKParams& p, float* v, const
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
     }
+  } else if (p.act == DEVIT_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
   }
 }
 

@@ -51,7 +51,7 @@ enum {
   DEVIT_OUT_F32_SPLIT = 2  /* fp32 hi plane at out, lo plane at out + plane_stride */
 };
 
-enum { DEVIT_ACT_NONE = 0, DEVIT_ACT_GELU_ERF = 1 };
+enum { DEVIT_ACT_NONE = 0, DEVIT_ACT_GELU_ERF = 1, DEVIT_ACT_RELU = 2 };
 
 int devit_abi_version(void);
 const char* devit_last_error(void);
@@ -334,6 +334,50 @@ int devit_vit_forward_patches(const devit_vit_desc* desc, const void* patches,
                               size_t workspace_bytes, float* feats_f32, void* feats_op,
                               int64_t feats_op_plane_stride, float* x_out, int32_t num_layers_run,
                               void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * CCT (Compact Convolutional Transformer) sub-models: models/cct.py:138-157 +
+ * models/utils/tokenizer.py:23-44 + models/utils/transformers.py:104-113, :441-477.
+ *   tokenizer : n_conv x [conv k3 s1 p1 (no bias) -> ReLU -> maxpool 3/2/1], each conv as
+ *               im2col (K order (ky, kx, c), zero-padded to a multiple of 8) + devit_gemm with a
+ *               ReLU epilogue, then a channels-last max-pool; the last pool adds positional_emb
+ *               and writes the fp32 residual stream [batch * tokens, dim];
+ *   blocks    : the same pre-norm blocks as the ViT path (QKV without bias, LN eps 1e-5);
+ *   head      : LayerNorm over every token, sequence pooling
+ *               pooled[b] = softmax_t(x[b,t,:] . pool_w + pool_b)^T x[b]   (:473).
+ * `pooled` is fp32 [batch, dim] (the backbone output / the input of the fc or fusion GEMM).
+ * ------------------------------------------------------------------------------------- */
+typedef struct devit_cct_desc {
+  int32_t precision;   /* DEVIT_BF16 | DEVIT_FP32 */
+  int32_t dim;         /* 256 (cct_7) */
+  int32_t depth;
+  int32_t img, chans;  /* 32, 3 */
+  int32_t n_conv;      /* 1 or 2 */
+  int32_t conv_chans[3]; /* output channels of conv layer i (last == dim) */
+  const void* w_conv[3]; /* [conv_chans[i], kpad_i] operand format, K order (ky, kx, c_in) */
+  int32_t conv_kpad[3];  /* 9 * c_in rounded up to a multiple of 8 */
+  const float* pos;    /* [tokens, dim] or NULL */
+  float ln_eps;
+  const float* norm_g;
+  const float* norm_b;
+  const float* pool_w; /* [dim] */
+  float pool_b;
+  const devit_layer_desc* layers; /* HOST pointer; b_qkv may be NULL (no QKV bias) */
+} devit_cct_desc;
+
+size_t devit_cct_workspace_bytes(const devit_cct_desc* desc, int32_t batch);
+int devit_cct_forward(const devit_cct_desc* desc, const float* images, int32_t batch,
+                      void* workspace, size_t workspace_bytes, float* pooled, float* x_out,
+                      int32_t num_layers_run, void* stream);
+
+/* Building blocks of the above (exposed for the parity tests). */
+int devit_im2col3x3(const float* in, void* a, int32_t batch, int32_t chans, int32_t hw,
+                    int64_t stride_b, int64_t stride_c, int64_t stride_y, int64_t stride_x,
+                    int32_t kpad, int32_t out_kind, int64_t out_plane_stride, void* stream);
+int devit_maxpool3x3s2_cl(const void* in, int32_t in_kind, float* out, const float* pos,
+                          int32_t batch, int32_t hw, int32_t chans, void* stream);
+int devit_seqpool(const float* xn, const float* w, float b, float* pooled, int32_t batch,
+                  int32_t tokens, int32_t dim, void* stream);
 
 /* In DEVIT_FP32 every weight matrix pointer in the descriptors addresses the hi plane and the
  * lo plane follows at + rows*cols elements (plane stride = rows * ld). */

@@ -279,8 +279,8 @@ attn_bf16_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 }
 
 // ------------------------------------------------------------------ persistent bf16 path
-// attn_persist_kernel: one CTA per SM loops over (image, kept head) items; used when every key
-// of a head fits 208 columns (ViT: 197/198 tokens).  Per item:
+// attn_persist_kernel: one CTA per SM loops over (image, kept head) items; KVP = 208 padded keys
+// (ViT: 197/198 tokens) or 256 (CCT: 256 tokens).  Per item:
 //   * TMA brings the head's Q (two 128-row tiles), K and V ONCE (the per-tile kernel above loads
 //     K and V once per query tile), double-buffered so item i+1 lands during item i;
 //   * S_t = Q_t K^T for both query tiles goes to TMEM columns [256 t, 256 t + 208);
@@ -291,8 +291,8 @@ attn_bf16_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 //     (Splitting each row over two warps -- 16 softmax warps -- was measured SLOWER: the pass
 //     is bound by the exp2 unit, 4 lanes / clock / scheduler, not by per-warp latency.)
 //   * O_t = P_t V is a tcgen05.mma with the A operand in tensor memory, accumulating into
-//     columns [192, 256) of the tile (the S tail there is dead by then); the same warps scale
-//     by 1/rowsum and store.
+//     columns [128, 192) of the tile (S there is dead by then); the same warps scale by 1/rowsum
+//     and store.
 // TMEM: 2 x 256 columns = all 512 (hence one CTA per SM); smem: 2 stages x 84 KB.
 constexpr int kPersistThreads = 9 * 32;  // 8 softmax warps + 1 control warp
 
@@ -314,8 +314,9 @@ struct AttnPersistCfg {
   static constexpr int kStageBytes = kQBytes + 2 * kKVBytes;
   static constexpr int kOffBar = 2 * kStageBytes;
   static constexpr int kSmemBytes = kOffBar + 256 + 1024;
-  static constexpr int kOCols = 192;  // O accumulator: columns [192, 256) of the tile
-  static_assert(KVP % 32 == 16 && KVP <= 208 && KVP / 2 <= kOCols, "P and O must not overlap");
+  static constexpr int kOCols = 128;  // O accumulator: columns [128, 192) of the tile (S there
+                                      // is dead once every warp has finished its second pass)
+  static_assert(KVP % 16 == 0 && KVP <= 256 && KVP / 2 <= kOCols, "P and O must not overlap");
 };
 
 template <int KVP>
@@ -463,7 +464,8 @@ attn_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const int row = t * 128 + quarter * 32 + lane;
     const bool warp_live = (t * 128 + quarter * 32) < tokens;
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + t * 256;
-    constexpr int kFull = KVP / 32;  // 32-column chunks, then one 16-column tail
+    constexpr int kFull = KVP / 32;   // 32-column chunks ...
+    constexpr int kTail = KVP % 32;   // ... then a 16-column tail (KVP = 208) or nothing (256)
     int k = 0;
     for (int item = first; item < num_items; item += step, ++k) {
       const int img = item / heads, head = item - img * heads;
@@ -475,7 +477,7 @@ attn_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       if (warp_live) {
         // Both passes are fully unrolled with the TMEM load of chunk c+1 in flight while chunk c
         // is processed (tcgen05.wait::ld waits for everything outstanding, so one load ahead).
-        uint32_t r[kFull + 1][32];
+        uint32_t r[kFull + (kTail ? 1 : 0)][32];
         // ---- pass 1: row max over the valid keys
         float mx = -INFINITY;
         tmem_ld_x32(t_row, r[0]);
@@ -483,7 +485,7 @@ attn_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         for (int c = 0; c < kFull; ++c) {
           tmem_ld_wait();
           if (c + 1 < kFull) tmem_ld_x32(t_row + (c + 1) * 32, r[c + 1]);
-          else tmem_ld_x16(t_row + kFull * 32, r[kFull]);
+          else if (kTail) tmem_ld_x16(t_row + kFull * 32, r[kFull - (kTail ? 0 : 1)]);
           if ((c + 1) * 32 <= tokens) {
 #pragma unroll
             for (int j = 0; j < 32; j += 2)
@@ -494,10 +496,13 @@ attn_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
               if (c * 32 + j < tokens) mx = fmaxf(mx, __uint_as_float(r[c][j]));
           }
         }
-        tmem_ld_wait();
+        if (kTail) {
+          tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (kFull * 32 + j < tokens) mx = fmaxf(mx, __uint_as_float(r[kFull][j]));
+          for (int j = 0; j < 16; ++j)
+            if (kFull * 32 + j < tokens)
+              mx = fmaxf(mx, __uint_as_float(r[kFull - (kTail ? 0 : 1)][j]));
+        }
         if (quarter == 0) ATTN_TRACE(10 + 6 * t, k);
         // ---- pass 2: p = exp2(s*c - max*c), row sum, P -> TMEM as packed bf16 pairs
         const float moff = mx * scale_log2e;
@@ -507,7 +512,7 @@ attn_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         for (int c = 0; c < kFull; ++c) {
           tmem_ld_wait();
           if (c + 1 < kFull) tmem_ld_x32(t_row + (c + 1) * 32, r[c + 1]);
-          else tmem_ld_x16(t_row + kFull * 32, r[kFull]);
+          else if (kTail) tmem_ld_x16(t_row + kFull * 32, r[kFull - (kTail ? 0 : 1)]);
           uint32_t pk[16];
           if ((c + 1) * 32 <= tokens) {
 #pragma unroll
@@ -533,13 +538,14 @@ attn_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           // (chunk c+1, in flight, lies above them)
           tmem_st_x16(t_row + c * 16, pk);
         }
-        {
+        if (kTail) {
+          constexpr int kT = kFull - (kTail ? 0 : 1);
           tmem_ld_wait();
           uint32_t pk[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            float e0 = fast_exp2(fmaf(__uint_as_float(r[kFull][2 * j]), scale_log2e, -moff));
-            float e1 = fast_exp2(fmaf(__uint_as_float(r[kFull][2 * j + 1]), scale_log2e, -moff));
+            float e0 = fast_exp2(fmaf(__uint_as_float(r[kT][2 * j]), scale_log2e, -moff));
+            float e1 = fast_exp2(fmaf(__uint_as_float(r[kT][2 * j + 1]), scale_log2e, -moff));
             e0 = (kFull * 32 + 2 * j < tokens) ? e0 : 0.f;
             e1 = (kFull * 32 + 2 * j + 1 < tokens) ? e1 : 0.f;
             sum += e0 + e1;
@@ -784,6 +790,8 @@ extern "C" int devit_attention(int32_t precision, const void* qkv, int64_t qkv_p
     if (kvp <= 64) return launch_attn_bf16<64>(qkv, out, batch, tokens, heads, scale, stream);
     if (kvp <= 208 && kvp > 128 && persist)
       return launch_attn_persist<208>(qkv, out, batch, tokens, heads, scale, stream);
+    if (kvp > 208 && persist)
+      return launch_attn_persist<256>(qkv, out, batch, tokens, heads, scale, stream);
     if (kvp <= 208) return launch_attn_bf16<208>(qkv, out, batch, tokens, heads, scale, stream);
     return launch_attn_bf16<256>(qkv, out, batch, tokens, heads, scale, stream);
   }

@@ -260,9 +260,7 @@ static int vit_forward_impl(const devit_vit_desc* d, const float* images, const 
   void* qkv = ws + L.off_qkv;
   void* o = ws + L.off_o;
   void* hid = ws + L.off_hid;
-  const int P = L.grid * L.grid;
   const int kp = d->chans * 256;
-  const long long Mp = static_cast<long long>(batch) * P;
 
   const int nl = (num_layers_run < 0 || num_layers_run > d->depth) ? d->depth : num_layers_run;
   int n_folded = 0;

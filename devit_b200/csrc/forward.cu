@@ -181,7 +181,7 @@ static int run_blocks(const devit_layer_desc* layers, int nl, int prec, int D, f
       if (rc) return rc;
     }
     const int F = w.hidden_ld;
-    if (fold && fused_mlp && D == 384) {
+    if (fold && fused_mlp && (D == 384 || D == 256)) {
       // x += gelu(LN2(x) W1^T + b1) W2^T + b2 in one kernel, hidden kept on chip   (:35-47, :115)
       devit_mlp_args ma;
       std::memset(&ma, 0, sizeof(ma));

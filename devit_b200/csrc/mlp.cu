@@ -11,15 +11,16 @@
 //     into the epilogue, see devit_gemm_args.ln_stats) and write it back INTO TMEM as packed
 //     bf16 pairs over columns they have already consumed.
 //   * GEMM2 chunk c: acc2 (128 x 384 fp32, TMEM columns [0, 384)) += H_c W2_c^T with the A operand
-//     read from tensor memory (two N = 192 UMMAs per K = 16 step).  GEMM1 of chunk c+1 is issued
+//     read from tensor memory (two N = D/2 UMMAs per K = 16 step).  GEMM1 of chunk c+1 is issued
 //     before GEMM2 of chunk c, so the tensor pipe works while the GELU of chunk c runs.
 //   * Final epilogue: acc2 + b2 + residual -> x (fp32).  At the end of a tile Y and both weight
-//     rings are dead: their 192 KB become 48 slots of [32 rows x 32 fp32], i.e. the WHOLE
+//     rings are dead: their 192 KB (D = 384) become 48 slots of [32 rows x 32 fp32], the WHOLE
 //     residual tile, three slots per epilogue warp, TMA-prefetched as soon as the last GEMM1
 //     (Y, W1 ring) / last GEMM2 (W2 ring) retired.  Each warp adds, stores through TMA and
 //     also emits the bf16 copy and the partial row sums the next layer's LayerNorm-folded QKV
 //     GEMM consumes.  The loaders resume only when every slot has been drained (all_free).
-// TMEM: 384 + 2 x 64 = 512 columns.  smem: Y 96 KB + W1 ring 48 KB + W2 ring 48 KB.
+// TMEM: D + 2 x 64 columns (all 512 at D = 384).  smem at D = 384: Y 96 KB + W1 ring 48 KB +
+// W2 ring 48 KB + 32 KB bf16 staging.  Instantiated for D = 384 (dedeit) and D = 256 (cct_7).
 #include <cstdlib>
 
 #include "common.cuh"
@@ -27,23 +28,36 @@
 
 namespace devit {
 
-constexpr int kMlpDim = 384;
 // warps: 0 = Y + W1 loads, 1 = MMA issue, 2..17 = epilogue (four per TMEM lane quarter: every
 // hidden chunk is split 4 x 16 columns, because GEMM1 of chunk c+1 has to wait for the GELU of
 // chunk c-1 -- two accumulator buffers -- so the GELU LATENCY of a chunk is what bounds the loop;
-// all sixteen also run the final epilogue, 96 output columns each), 18 = W2 loads
+// all sixteen also run the final epilogue, D/4 output columns each), 18 = W2 loads
 constexpr int kMlpThreads = 19 * 32;
 constexpr int kW2Warp = 18;
-constexpr int kYBytes = 6 * 16384;    // 6 K-atoms of [128 rows x 128 B]
-constexpr int kW1Slot = 6 * 4096;     // 6 K-atoms of [32 rows x 128 B]  (this CTA's half chunk)
-constexpr int kW2Slot = 2 * 12288;    // 2 N-halves of [96 rows x 128 B]
-constexpr int kOffW1 = kYBytes;
-constexpr int kOffW2 = kOffW1 + 2 * kW1Slot;
-constexpr int kOffXb = kOffW2 + 2 * kW2Slot;  // bf16-copy staging: 16 warps x [32 rows x 64 B]
-constexpr int kOffBarM = kOffXb + 16 * 2048;
-constexpr int kMlpSmem = kOffBarM + 1024 + 1024;
-static_assert(kMlpSmem <= 227 * 1024, "fused MLP shared memory budget");
-constexpr int kAcc1Col = 384;
+
+// Geometry for a model width D (384: dedeit, 256: cct_7): everything below is per CTA.
+template <int D>
+struct MlpCfg {
+  static_assert(D == 256 || D == 384, "fused MLP is laid out for D = 256 or 384");
+  static constexpr int kAtoms = D / 64;             // K-atoms of Y / of a W1 chunk
+  static constexpr int kYBytes = kAtoms * 16384;    // [128 rows x 128 B] per atom
+  static constexpr int kW1Slot = kAtoms * 4096;     // [32 rows x 128 B] per atom (half chunk)
+  static constexpr int kHalfN = D / 2;              // GEMM2 is issued as two N = D/2 UMMAs
+  static constexpr int kW2Rows = D / 4;             // rows of one N-half staged by this CTA
+  static constexpr int kW2Slot = 2 * kW2Rows * 128;
+  static constexpr int kOffW1 = kYBytes;
+  static constexpr int kOffW2 = kOffW1 + 2 * kW1Slot;
+  static constexpr int kOffXb = kOffW2 + 2 * kW2Slot;  // bf16-copy staging: 16 x [32 rows x 64 B]
+  static constexpr int kOffBar = kOffXb + 16 * 2048;
+  static constexpr int kSmem = kOffBar + 1024 + 1024;
+  static constexpr int kAcc1Col = D;                // acc2 = TMEM columns [0, D), acc1 behind it
+  static constexpr int kColsPerWarp = D / 4;        // final epilogue: output columns per warp
+  static constexpr int kSlots = kColsPerWarp / 32;  // 32-column residual slots per warp
+  // Y + both weight rings are exactly the 16 * kSlots slots of the fp32 residual tile
+  static_assert(kYBytes + 2 * kW1Slot + 2 * kW2Slot == 16 * kSlots * 4096, "slot carve-out");
+  static_assert(kSmem <= 227 * 1024, "fused MLP shared memory budget");
+  static_assert(D + 128 <= 512, "TMEM budget");
+};
 
 extern long long* g_attn_trace;  // devit_debug_set_trace buffer (shared)
 #ifdef DEVIT_GEMM_TRACE
@@ -82,13 +96,19 @@ __device__ __forceinline__ void umma_bf16_ts_cg2(uint32_t d_tmem, uint32_t a_tme
 
 __device__ __forceinline__ int mlp_off(int r, int j) { return r * 128 + ((j ^ (r & 7)) << 4); }
 
+template <int D>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1)
 mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmW1,
                  const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmX,
                  const __grid_constant__ CUtensorMap tmXB, const __grid_constant__ MlpParams p) {
+  using Cfg = MlpCfg<D>;
+  constexpr int kAtoms = Cfg::kAtoms, kYBytes = Cfg::kYBytes, kW1Slot = Cfg::kW1Slot,
+                kW2Slot = Cfg::kW2Slot, kOffW1 = Cfg::kOffW1, kOffW2 = Cfg::kOffW2,
+                kOffXb = Cfg::kOffXb, kAcc1Col = Cfg::kAcc1Col, kHalfN = Cfg::kHalfN,
+                kW2Rows = Cfg::kW2Rows, kColsPerWarp = Cfg::kColsPerWarp, kSlots = Cfg::kSlots;
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBarM);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBar);
   uint64_t* y_full = bars + 0;
   uint64_t* y_empty = bars + 1;     // last GEMM1 of the tile retired (Y is dead)
   uint64_t* y_free = bars + 2;      // "all_free": every final-epilogue slot drained (16 arrivals)
@@ -100,7 +120,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
   uint64_t* h_ready = bars + 13;    // [2]  (leader: 32 warp arrivals)
   uint64_t* acc2_full = bars + 15;
   uint64_t* acc2_empty = bars + 16;  // (leader: 32 warp arrivals)
-  uint64_t* rfull = bars + 17;       // [16 warps][3 slots]
+  uint64_t* rfull = bars + 17;       // [16 warps][3 slots max]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 65);
 
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
@@ -172,7 +192,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         const uint32_t bar = mapa_u32(smem_u32(y_full), 0);
         if (leader) mbar_expect_tx(y_full, 2 * kYBytes);
 #pragma unroll
-        for (int a = 0; a < 6; ++a) tma_load_2d_cg2(smem + a * 16384, &tmY, bar, a * 64, m0);
+        for (int a = 0; a < kAtoms; ++a) tma_load_2d_cg2(smem + a * 16384, &tmY, bar, a * 64, m0);
       }
       for (int c = 0; c < NC; ++c, ++g1) {
         const int s = g1 & 1;
@@ -183,7 +203,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
           const int row0 = c * 64 + cta_rank * (chunk_n(c) / 2);
           uint8_t* dst = smem + kOffW1 + s * kW1Slot;
 #pragma unroll
-          for (int a = 0; a < 6; ++a) tma_load_2d_cg2(dst + a * 4096, &tmW1, bar, a * 64, row0);
+          for (int a = 0; a < kAtoms; ++a) tma_load_2d_cg2(dst + a * 4096, &tmW1, bar, a * 64, row0);
         }
       }
     }
@@ -200,9 +220,9 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
           const uint32_t bar = mapa_u32(smem_u32(&w2_full[s]), 0);
           if (leader) mbar_expect_tx(&w2_full[s], 2 * kW2Slot);
           uint8_t* dst = smem + kOffW2 + s * kW2Slot;
-          // output columns [192 hh + 96 rank, +96) of W2, K = neurons [64c, 64c + 64)
-          tma_load_2d_cg2(dst, &tmW2, bar, c * 64, cta_rank * 96);
-          tma_load_2d_cg2(dst + 12288, &tmW2, bar, c * 64, 192 + cta_rank * 96);
+          // output columns [D/2 hh + D/4 rank, +D/4) of W2, K = neurons [64c, 64c + 64)
+          tma_load_2d_cg2(dst, &tmW2, bar, c * 64, cta_rank * kW2Rows);
+          tma_load_2d_cg2(dst + kW2Rows * 128, &tmW2, bar, c * 64, kHalfN + cta_rank * kW2Rows);
         }
       }
     }
@@ -211,7 +231,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
     if (leader) {
       uint32_t g1 = 0, g2 = 0;
       int it = 0;
-      const uint32_t idesc2 = make_idesc(kFmtBF16, 256, 192, 0, 0);
+      const uint32_t idesc2 = make_idesc(kFmtBF16, 256, kHalfN, 0, 0);
       auto gemm2 = [&](int cc, bool first_of_tile) {
         const int b = g2 & 1;
         const uint32_t par = (g2 >> 1) & 1;
@@ -230,8 +250,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
             const uint32_t a_t = tmem_base + kAcc1Col + 64 * b + 16 * j;
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
-              const uint64_t db = make_sw128_desc(sw + hh * 12288, 1024, 16) + 2 * j;
-              umma_bf16_ts_cg2(tmem_base + 192 * hh, a_t, db, idesc2,
+              const uint64_t db = make_sw128_desc(sw + hh * (kW2Rows * 128), 1024, 16) + 2 * j;
+              umma_bf16_ts_cg2(tmem_base + kHalfN * hh, a_t, db, idesc2,
                                (first_of_tile && j == 0) ? 0u : 1u);
             }
           }
@@ -255,7 +275,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
           const uint32_t sw = smem_u32(smem + kOffW1 + s * kW1Slot);
           if (elect_one()) {
 #pragma unroll
-            for (int a = 0; a < 6; ++a) {
+            for (int a = 0; a < kAtoms; ++a) {
               const uint64_t da = make_sw128_desc(sy + a * 16384, 1024, 16);
               const uint64_t db = make_sw128_desc(sw + a * 4096, 1024, 16);
 #pragma unroll
@@ -284,8 +304,9 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
     // slots 3 ew .. 3 ew + 2 of the 48: [0,24) in Y, [24,36) in the W1 ring, [36,48) in the W2
     // ring (contiguous in shared memory, so the slot address is simply 4 KB x index)
-    uint8_t* slots = smem + ew * (3 * 4096);
-    const bool slots_in_w2 = ew >= 12;   // usable only once the last GEMM2 has retired
+    uint8_t* slots = smem + ew * (kSlots * 4096);
+    // slots that lie in the W2 ring are usable only once the last GEMM2 has retired
+    const bool slots_in_w2 = (ew + 1) * kSlots * 4096 > kOffW2;
     uint64_t* rbar = rfull + ew * 3;
     uint8_t* xb_stg = smem + kOffXb + ew * 2048;  // [32 rows x 32 bf16], rows of 64 B, 64B swizzle
     const uint32_t h_ready_leader0 = mapa_u32(smem_u32(&h_ready[0]), 0);
@@ -318,7 +339,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
       // exist until then: pull it into L2 now, so that the late TMA loads are L2 hits.
       if (row0 < p.M && elect_one()) {
 #pragma unroll
-        for (int s = 0; s < 3; ++s) tma_prefetch_l2_2d(&tmX, sub * 96 + s * 32, row0);
+        for (int s = 0; s < kSlots; ++s) tma_prefetch_l2_2d(&tmX, sub * kColsPerWarp + s * 32, row0);
       }
       // ---- hidden chunks: acc1 -> H (bf16, in TMEM).  Slice `sub` of chunk c: neurons
       //      [64c + 16 sub, +16) = acc1 columns [16 sub, +16) -> H columns [16 sub, +8).
@@ -371,16 +392,16 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
       else mbar_wait_warp(y_empty, it & 1);
       if (elect_one()) {
 #pragma unroll
-        for (int s = 0; s < 3; ++s) {
+        for (int s = 0; s < kSlots; ++s) {
           mbar_expect_tx(&rbar[s], 4096);
-          tma_load_2d(slots + s * 4096, &tmX, &rbar[s], sub * 96 + s * 32, row0);
+          tma_load_2d(slots + s * 4096, &tmX, &rbar[s], sub * kColsPerWarp + s * 32, row0);
         }
       }
       // ... and the next tile's Y (loaded only after every slot has been drained) likewise
       if (warp == 2 && pt + num_clusters < num_pairs && elect_one()) {
         const int m_next = ((pt + num_clusters) * 2 + cta_rank) * 128;
 #pragma unroll
-        for (int a = 0; a < 6; ++a) tma_prefetch_l2_2d(&tmY, a * 64, m_next);
+        for (int a = 0; a < kAtoms; ++a) tma_prefetch_l2_2d(&tmY, a * 64, m_next);
       }
       if (warp == 2) MLP_TRACE(12, it);
       mbar_wait_warp(acc2_full, it & 1);
@@ -388,12 +409,12 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
       tc_fence_after();
       float st1 = 0.f, st2 = 0.f;
 #pragma unroll 1
-      for (int j = 0; j < 3; ++j) {
-        const int col0 = sub * 96 + j * 32;
+      for (int j = 0; j < kSlots; ++j) {
+        const int col0 = sub * kColsPerWarp + j * 32;
         uint32_t r[32];
         tmem_ld_x32(tmem_base + lane_off + col0, r);
         tmem_ld_wait();
-        if (j == 2) {
+        if (j == kSlots - 1) {
           // acc2 is in registers: release it before the memory work of the last chunk
           tc_fence_before();
           __syncwarp();
@@ -455,7 +476,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         }
         if (warp == 2) MLP_TRACE(17, it * 4 + j);
       }
-      // partial row sums of this warp's 96 columns: part index = sub (4 parts per row)
+      // partial row sums of this warp's D/4 columns: part index = sub (4 parts per row)
       if (p.stats_out && row < p.M)
         reinterpret_cast<float2*>(p.stats_out)[static_cast<long long>(sub) * p.M + row] =
             make_float2(st1, st2);
@@ -488,7 +509,9 @@ extern "C" int devit_mlp_fused(const devit_mlp_args* a, void* stream_v) {
   DEVIT_REQUIRE(a != nullptr, "devit_mlp_fused: null args");
   int rc = check_device();
   if (rc) return rc;
-  DEVIT_REQUIRE(a->dim == kMlpDim, "devit_mlp_fused: dim %d unsupported (built for 384)", a->dim);
+  DEVIT_REQUIRE(a->dim == 256 || a->dim == 384,
+                "devit_mlp_fused: dim %d unsupported (built for 256 and 384)", a->dim);
+  const int Dm = a->dim;
   DEVIT_REQUIRE(a->m > 0 && a->hidden_ld >= 16 && a->hidden_ld % 16 == 0,
                 "devit_mlp_fused: need m > 0 and hidden_ld a positive multiple of 16");
   DEVIT_REQUIRE(a->xb && a->w1 && a->c1 && a->c2 && a->w2 && a->b2 && a->x && a->ln_stats,
@@ -503,22 +526,26 @@ extern "C" int devit_mlp_fused(const devit_mlp_args* a, void* stream_v) {
   int dev = 0;
   DEVIT_CUDA_OK(cudaGetDevice(&dev));
   if (!attr_done[dev & 63]) {
-    DEVIT_CUDA_OK(cudaFuncSetAttribute(mlp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       kMlpSmem));
+    DEVIT_CUDA_OK(cudaFuncSetAttribute(mlp_fused_kernel<384>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       MlpCfg<384>::kSmem));
+    DEVIT_CUDA_OK(cudaFuncSetAttribute(mlp_fused_kernel<256>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       MlpCfg<256>::kSmem));
     attr_done[dev & 63] = true;
   }
   CUtensorMap tY, tW1, tW2, tX, tXB;
-  rc = encode_tmap_2d(&tY, a->xb, 2, kMlpDim, a->m, kMlpDim, 64, 128, false);
+  rc = encode_tmap_2d(&tY, a->xb, 2, Dm, a->m, Dm, 64, 128, false);
   if (rc) return rc;
-  rc = encode_tmap_2d(&tW1, a->w1, 2, kMlpDim, a->hidden_ld, kMlpDim, 64, 32, true);
+  rc = encode_tmap_2d(&tW1, a->w1, 2, Dm, a->hidden_ld, Dm, 64, 32, true);
   if (rc) return rc;
-  rc = encode_tmap_2d(&tW2, a->w2, 2, a->hidden_ld, kMlpDim, a->hidden_ld, 64, 96, true);
+  rc = encode_tmap_2d(&tW2, a->w2, 2, a->hidden_ld, Dm, a->hidden_ld, 64, Dm / 4, true);
   if (rc) return rc;
-  rc = encode_tmap_2d(&tX, a->x, 4, kMlpDim, a->m, kMlpDim, 32, 32, false);
+  rc = encode_tmap_2d(&tX, a->x, 4, Dm, a->m, Dm, 32, 32, false);
   if (rc) return rc;
   tXB = tX;
   if (a->xb_out) {
-    rc = encode_tmap_2d_sw64(&tXB, a->xb_out, 2, kMlpDim, a->m, kMlpDim, 32, 32);
+    rc = encode_tmap_2d_sw64(&tXB, a->xb_out, 2, Dm, a->m, Dm, 32, 32);
     if (rc) return rc;
   }
   MlpParams p;
@@ -530,7 +557,7 @@ extern "C" int devit_mlp_fused(const devit_mlp_args* a, void* stream_v) {
   p.b2 = a->b2;
   p.ln_stats = a->ln_stats;
   p.ln_parts = a->ln_parts;
-  p.ln_inv_dim = 1.0f / static_cast<float>(kMlpDim);
+  p.ln_inv_dim = 1.0f / static_cast<float>(Dm);
   p.ln_eps = a->ln_eps;
   p.xb_out = static_cast<__nv_bfloat16*>(a->xb_out);
   p.stats_out = a->stats_out;
@@ -551,14 +578,17 @@ extern "C" int devit_mlp_fused(const devit_mlp_args* a, void* stream_v) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(clusters * 2);
     cfg.blockDim = dim3(kMlpThreads);
-    cfg.dynamicSmemBytes = kMlpSmem;
+    cfg.dynamicSmemBytes = Dm == 384 ? MlpCfg<384>::kSmem : MlpCfg<256>::kSmem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 1 : 0;
-    DEVIT_CUDA_OK(cudaLaunchKernelEx(&cfg, mlp_fused_kernel, tY, tW1, tW2, tX, tXB, p));
+    if (Dm == 384)
+      DEVIT_CUDA_OK(cudaLaunchKernelEx(&cfg, mlp_fused_kernel<384>, tY, tW1, tW2, tX, tXB, p));
+    else
+      DEVIT_CUDA_OK(cudaLaunchKernelEx(&cfg, mlp_fused_kernel<256>, tY, tW1, tW2, tX, tXB, p));
   }
   DEVIT_CUDA_OK(cudaGetLastError());
   count_launch();

@@ -169,7 +169,8 @@ int devit_layernorm(const float* x, const float* gamma, const float* beta, void*
                     int64_t out_plane_stride, void* stream);
 
 /* ---------------------------------------------------------------------------------------
- * devit_mlp_fused:  x += gelu( LN(x) W1^T + b1 ) W2^T + b2   as ONE kernel (DEVIT_BF16, dim 384).
+ * devit_mlp_fused:  x += gelu( LN(x) W1^T + b1 ) W2^T + b2   as ONE kernel (DEVIT_BF16, dim 384
+ * or 256).
  * Replaces norm2 + Mlp.forward + the residual add, models/de_vit.py:35-47 and :115: fc1, the
  * erf-GELU, the (compacted) neuron gate and fc2 run per CTA pair on 256 token rows with the
  * hidden activation kept in tensor memory, so the [rows, hidden] tensor never exists in HBM.
@@ -178,11 +179,11 @@ int devit_layernorm(const float* x, const float* gamma, const float* beta, void*
  * sums / folded bias [hidden_ld] (zero beyond the kept neurons), `ln_stats` the partial row sums
  * [ln_parts][m][2].  `w2` is [dim, hidden_ld] (zero columns beyond the kept neurons).
  * Outputs: x (fp32, in place), optionally the bf16 copy of the new x (`xb_out`, may alias `xb`)
- * and its partial row sums `stats_out` [4][m][2] (one part per 96 columns) for the next layer.
+ * and its partial row sums `stats_out` [4][m][2] (one part per dim/4 columns) for the next layer.
  * ------------------------------------------------------------------------------------- */
 typedef struct devit_mlp_args {
   int32_t m;
-  int32_t dim;       /* must be 384 */
+  int32_t dim;       /* 384 or 256 */
   int32_t hidden_ld; /* kept neurons rounded up to a multiple of 16 */
   const void* xb;
   const void* w1;

@@ -745,6 +745,7 @@ static int launch_attn_persist(const void* qkv, void* out, int batch, int tokens
   if (rc) return rc;
   const int items = batch * heads;
   const int grid = items < num_sms() ? items : num_sms();
+  static int env_lockstep = kEnvUnread;  // debug: issue both query tiles in lock-step
   {
     ProfScope ps(kTagAttention, stream);
     cudaLaunchConfig_t cfg = {};
@@ -760,7 +761,8 @@ static int launch_attn_persist(const void* qkv, void* out, int batch, int tokens
     DEVIT_CUDA_OK(cudaLaunchKernelEx(&cfg, attn_persist_kernel<KVP>, tq, tkv,
                                      static_cast<__nv_bfloat16*>(out), tokens, heads, items,
                                      scale * 1.4426950408889634f,
-                                     getenv("DEVIT_ATTN_LOCKSTEP") ? 0 : 1, g_attn_trace));
+                                     env_int("DEVIT_ATTN_LOCKSTEP", 0, &env_lockstep) ? 0 : 1,
+                                     g_attn_trace));
   }
   DEVIT_CUDA_OK(cudaGetLastError());
   count_launch();

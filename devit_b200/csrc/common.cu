@@ -21,6 +21,14 @@ int set_error(int code, const char* fmt, ...) {
   return code;
 }
 
+int env_int(const char* name, int dflt, int* cache) {
+  if (*cache == kEnvUnread) {
+    const char* e = getenv(name);
+    *cache = e ? atoi(e) : dflt;
+  }
+  return *cache;
+}
+
 int pdl_enabled() {
   static int on = -1;
   if (on < 0) {

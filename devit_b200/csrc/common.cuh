@@ -30,6 +30,10 @@ struct ProfScope {
 
 // 1 unless DEVIT_PDL=0: launch the layer-loop kernels with programmatic stream serialization
 int pdl_enabled();
+// Integer value of a debug / tuning environment variable, read ONCE per process and cached in
+// `*cache` (which must start at kEnvUnread); `dflt` when the variable is not set.
+constexpr int kEnvUnread = -0x7fffffff;
+int env_int(const char* name, int dflt, int* cache);
 
 #define DEVIT_CUDA_OK(expr)                                                              \
   do {                                                                                   \

@@ -1011,12 +1011,14 @@ extern "C" int devit_gemm(const devit_gemm_args* a, void* stream_v) {
   if (cl == 0) {
     cl = (a->m >= 64 * kBlockM) ? 2 : 1;
     if (a->resid && total_k < 512) cl = 1;
-    if (const char* e = getenv("DEVIT_GEMM_CLUSTER")) cl = atoi(e);
+    static int env_cl = kEnvUnread;
+    if (env_int("DEVIT_GEMM_CLUSTER", 0, &env_cl)) cl = env_cl;
   }
   DEVIT_REQUIRE(cl == 1 || cl == 2, "devit_gemm: cluster_m %d unsupported", cl);
   int bn = a->block_n ? a->block_n : pick_block_n(a->n, cl);
   if (!a->block_n) {
-    if (const char* e = getenv("DEVIT_GEMM_BN")) bn = atoi(e);
+    static int env_bn = kEnvUnread;
+    if (env_int("DEVIT_GEMM_BN", 0, &env_bn)) bn = env_bn;
   }
   DEVIT_REQUIRE(bn == 128 || bn == 192 || bn == 256, "devit_gemm: block_n %d unsupported", bn);
 
@@ -1029,8 +1031,9 @@ extern "C" int devit_gemm(const devit_gemm_args* a, void* stream_v) {
   if (a->resid)
     tma_epi = tma_epi && (reinterpret_cast<uintptr_t>(a->resid) % 16 == 0) &&
               ((a->ldr * 4) % 16 == 0);
-  if (const char* e = getenv("DEVIT_GEMM_NO_TMA_EPI")) {
-    const int v = atoi(e);  // debug: 1 = never, 2 = not for residual GEMMs
+  {
+    static int env_no_tma = kEnvUnread;  // debug: 1 = never, 2 = not for residual GEMMs
+    const int v = env_int("DEVIT_GEMM_NO_TMA_EPI", 0, &env_no_tma);
     if (v == 1 || (v == 2 && a->resid)) tma_epi = false;
   }
   DEVIT_REQUIRE(!(ln_consumer || ln_producer) || tma_epi,
@@ -1061,7 +1064,8 @@ extern "C" int devit_gemm(const devit_gemm_args* a, void* stream_v) {
   p.tma_epi = tma_epi ? 1 : 0;
   p.dbg = 0;
   p.trace = g_trace;
-  if (const char* e = getenv("DEVIT_GEMM_DBG")) p.dbg = atoi(e);
+  static int env_dbg = kEnvUnread;
+  p.dbg = env_int("DEVIT_GEMM_DBG", 0, &env_dbg);
   CUtensorMap tm[7];
   tm[0] = ta0; tm[1] = ta1; tm[2] = tb0; tm[3] = tb1;
   tm[4] = ta0; tm[5] = ta0; tm[6] = ta0;  // placeholders when the direct epilogue is used

@@ -127,3 +127,91 @@ def test_split_tf32_is_exact():
     assert torch.equal(s[0] + s[1], t)
     assert (s[0].view(torch.int32) & 0x1FFF).abs().max().item() == 0
     assert ((s[1].abs() <= t.abs() * 2 ** -11 * 1.0001) | (t == 0)).all()
+
+
+# ------------------------------------------------------------------------------- LN folding
+def test_layernorm_fold_algebra_matches_layernorm_then_linear():
+    """packing._fold: LN(x) W^T + b == rstd (x (gamma.W)^T - mean c1) + c2 (fp64 check of the
+    identity the folded GEMM epilogues implement, include/devit_b200.h devit_gemm_args)."""
+    g = torch.Generator().manual_seed(11)
+    d, n, rows, eps = 384, 96, 37, 1e-6
+    x = (torch.randn(rows, d, generator=g) * 1.7 + 0.4).double()
+    norm = torch.nn.LayerNorm(d, eps=eps).double()
+    with torch.no_grad():
+        norm.weight.copy_(1 + 0.1 * torch.randn(d, generator=g))
+        norm.bias.copy_(0.1 * torch.randn(d, generator=g))
+    w = (torch.randn(n, d, generator=g) * 0.05).double()
+    b = (torch.randn(n, generator=g) * 0.1).double()
+    kept = []
+    wf, c1_ptr, c2 = packing.PackedVit._fold(w.float(), b.float(), norm.float(),
+                                             lambda t: kept.append(t) or len(kept) - 1)
+    c1 = kept[c1_ptr].double()
+    # c1 is the row sum of the bf16-ROUNDED folded weights (what the tensor core multiplies)
+    assert torch.equal(kept[c1_ptr], wf.to(torch.bfloat16).float().sum(1))
+    mean = x.mean(1, keepdim=True)
+    rstd = 1.0 / torch.sqrt(x.var(1, unbiased=False, keepdim=True) + eps)
+    wf_q = wf.to(torch.bfloat16).double()                      # operand as stored
+    folded = rstd * (x @ wf_q.t() - mean * c1[None, :]) + c2.double()[None, :]
+    ref = norm.double()(x) @ w.t() + b
+    # the only difference is the bf16 rounding of the folded weights
+    assert ((folded - ref).abs().max() / ref.abs().max()).item() < 4e-3
+    exact = rstd * (x @ wf.double().t() - mean * wf.double().sum(1)[None, :]) + c2.double()[None, :]
+    assert ((exact - ref).abs().max() / ref.abs().max()).item() < 1e-6
+
+
+# ------------------------------------------------------------------------------- CCT host side
+def test_cct_state_dict_layout_registry_and_packing_shapes():
+    from devit_b200 import cct
+    for n_conv, tokens, backbone in ((1, 256, False), (2, 64, False), (1, 256, True)):
+        m = cct.get_decct(num_classes=100, kernel_size=3, n_conv_layers=n_conv, img_size=32,
+                          backbone=backbone)
+        want = synth.cct_shapes(n_conv=n_conv, tokens=tokens, num_classes=100, backbone=backbone)
+        got = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+        assert list(got) == list(want) and got == want
+        m.load_state_dict(synth.cct_state_dict(0, n_conv=n_conv, tokens=tokens, num_classes=100,
+                                               backbone=backbone))
+    assert is_model('cct_7_3x1_32') and is_model('cct_7_3x2_32') and is_model('cct_6_3x1_32')
+    m = create_model('cct_7_3x1_32', num_classes=10)
+    assert m.classifier.sequence_length == 256 and len(m.classifier.blocks) == 7
+    multi = cct.MultiCCT('decct_7_3x2', num_classes_list=[25] * 4, num_sub_models=4, input_size=32)
+    assert len(multi.models) == 4 and multi.models[0].backbone
+    assert multi.models[0].encoders.sequence_length == 64
+    with pytest.raises(L.DevitError):   # loud failure, no CPU path
+        m.eval()(torch.zeros(1, 3, 32, 32))
+    with pytest.raises(L.DevitError):   # only the decct_*_3xN tokenizer family is built
+        cct.CCT(img_size=224, kernel_size=7, stride=2, padding=3)
+
+
+def test_conv_weight_k_order_matches_im2col_definition():
+    """PackedCCT lays conv weights out as [c_out, (ky, kx, c_in)] zero-padded to a multiple of 8:
+    check against an explicit im2col of the same definition (devit_im2col3x3)."""
+    g = torch.Generator().manual_seed(12)
+    cin, cout, hw = 3, 8, 6
+    x = torch.randn(2, cin, hw, hw, generator=g)
+    w = torch.randn(cout, cin, 3, 3, generator=g)
+    kpad = (9 * cin + 7) // 8 * 8
+    wk = torch.zeros(cout, kpad)
+    wk[:, :9 * cin] = w.permute(0, 2, 3, 1).reshape(cout, -1)
+    xp = torch.nn.functional.pad(x, (1, 1, 1, 1))
+    a = torch.zeros(2 * hw * hw, kpad)
+    for b in range(2):
+        for y in range(hw):
+            for xx in range(hw):
+                patch = xp[b, :, y:y + 3, xx:xx + 3]                 # [c, ky, kx]
+                a[(b * hw + y) * hw + xx, :9 * cin] = patch.permute(1, 2, 0).reshape(-1)
+    out = (a @ wk.t()).view(2, hw, hw, cout).permute(0, 3, 1, 2)
+    ref = torch.nn.functional.conv2d(x, w, None, 1, 1)
+    assert torch.allclose(out, ref, atol=1e-5)
+
+
+def test_shard_plan_eight_way():
+    from devit_b200 import parallel
+    for world in (1, 2, 4, 8):
+        seen = set()
+        for r in range(world):
+            p = parallel.shard_plan(world, r, 8, 1024)
+            assert p.group_batch == 1024 and p.num_groups == 1
+            seen.update(p.subs)
+        assert seen == set(range(8))
+    p = parallel.shard_plan(16, 9, 8, 1024)
+    assert p.num_groups == 2 and p.group_batch == 512 and p.subs == [1] and p.batch_lo == 512

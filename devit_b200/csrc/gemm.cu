@@ -77,11 +77,18 @@ static long long* g_trace = nullptr;
 #define DEVIT_TRACE(slot_, idx_) do { (void)(idx_); } while (0)
 #endif
 
-template <int BN, int CL, bool RES = false>
+constexpr int kMaxResidentKb = 6;  // B-resident mode: K <= 6 k-blocks (384 bf16)
+
+// BRES ("B resident"): for K <= 384 the CTA (pair) keeps ONE n-tile's weight k-blocks in shared
+// memory for the whole kernel and walks down the m-tiles of that n-tile, so only the activation
+// tile is streamed: half the operand bytes per tile of the ordinary mode, which matters because
+// these K = 384 GEMMs are bound by the bytes an SM pulls through L2.
+template <int BN, int CL, bool RES = false, bool BRES = false>
 struct GemmCfg {
   static constexpr int kStageA = kBlockM * 128;
   static constexpr int kStageB = (BN / CL) * 128;  // a CTA pair splits B's rows half / half
-  static constexpr int kStageBytes = kStageA + kStageB;
+  static constexpr int kStageBytes = BRES ? kStageA : kStageA + kStageB;
+  static constexpr int kResidentBytes = BRES ? kMaxResidentKb * kStageB : 0;
   // one [32 x 128 B] staging buffer per warp; the residual variant keeps a slot for every
   // 32x32 fp32 chunk of the tile so the NEXT tile's residual is in flight during this one
   // (+ one bf16 staging buffer per warp for the optional bf16 copy of the output)
@@ -89,12 +96,13 @@ struct GemmCfg {
   // per-warp copies of the tile's bias and (LayerNorm folding) column sums
   static constexpr int kBiasBytes = 2 * kEpiWarps * BN * 4;
   static constexpr int kBarBytes = (2 * 8 + 32 + 4) * 8 + 16 + 32;
-  static constexpr int kBudget = 227 * 1024 - 1024 - kEpiBytes - kBiasBytes - kBarBytes;
+  static constexpr int kBudget =
+      227 * 1024 - 1024 - kEpiBytes - kBiasBytes - kBarBytes - kResidentBytes;
   static constexpr int kStages = kBudget / kStageBytes > 8 ? 8 : kBudget / kStageBytes;
   static constexpr int kAccStride = BN <= 128 ? 128 : 256;
   static constexpr int kTmemCols = 2 * kAccStride;
-  static constexpr int kSmemBytes =
-      kStages * kStageBytes + kEpiBytes + kBiasBytes + kBarBytes + 1024;
+  static constexpr int kRingBytes = kStages * kStageBytes + kResidentBytes;
+  static constexpr int kSmemBytes = kRingBytes + kEpiBytes + kBiasBytes + kBarBytes + 1024;
   static_assert(kStages >= (RES ? 2 : 3), "not enough shared memory for the operand ring");
 };
 
@@ -242,13 +250,14 @@ __device__ __forceinline__ void ln_bias_act32(const GemmKParams& p, float* v, co
   }
 }
 
-template <int BN, int KIND, int CL, bool RES>
+template <int BN, int KIND, int CL, bool RES, bool BRES>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
             const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
             const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1,
             const __grid_constant__ CUtensorMap tmR, const __grid_constant__ GemmKParams p) {
-  using Cfg = GemmCfg<BN, CL, RES>;
+  using Cfg = GemmCfg<BN, CL, RES, BRES>;
+  static_assert(!(RES && BRES), "the residual and B-resident variants are exclusive");
   constexpr int kElem = KIND == 0 ? 2 : 4;
   constexpr int kBlockK = 128 / kElem;  // elements per k-block (one swizzle atom)
   constexpr int kStages = Cfg::kStages;
@@ -258,11 +267,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
   // LDS/STS of the epilogue into a slower generic LD/ST.
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
-  uint8_t* epi_smem = smem + kStages * Cfg::kStageBytes;
+  uint8_t* epi_smem = smem + Cfg::kRingBytes;
+  uint8_t* bres_smem = smem + kStages * Cfg::kStageBytes;  // resident weight k-blocks (BRES)
   float* bias_smem = reinterpret_cast<float*>(epi_smem + Cfg::kEpiBytes);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + Cfg::kEpiBytes + Cfg::kBiasBytes);
   uint64_t* empty_bar = full_bar + 8;
   uint64_t* rfull_bar = empty_bar + 8;  // [8 warps][4 slots]: residual chunk has landed
+  uint64_t* bres_full = rfull_bar;      // BRES (never together with RES): resident B has landed
   uint64_t* tmem_full = rfull_bar + 32;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
@@ -323,6 +334,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
   const int num_m = (p.M + kBlockM - 1) / kBlockM;
   const int num_n = (p.N + BN - 1) / BN;
   const int num_units = ((num_m + CL - 1) / CL) * num_n;  // unit = CL m-blocks x one n-tile
+  // This cluster's units: unit_first, unit_first + unit_step, ...  Ordinary mode: round-robin
+  // over all units (n fastest, so co-resident CTAs share A rows in L2).  BRES: the cluster owns
+  // n-tile (cluster_id % num_n) and every G-th m-block of it (G = clusters on that n-tile).
+  int unit_first = cluster_id, unit_step = num_clusters;
+  if (BRES) {
+    const int n_fixed = cluster_id % num_n;
+    const int group = (num_clusters - n_fixed + num_n - 1) / num_n;
+    unit_first = (cluster_id / num_n) * num_n + n_fixed;
+    unit_step = group * num_n;
+  }
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -330,7 +351,28 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
       int stage = 0;
       uint32_t phase = 0;
       int tr_p = 0;
-      for (int unit = cluster_id; unit < num_units; unit += num_clusters) {
+      if (BRES && unit_first < num_units) {
+        // the n-tile's weight k-blocks, once: they stay in shared memory for the whole kernel
+        const int n0 = (unit_first % num_n) * BN;
+        const int n_valid = (p.N - n0) < BN ? (p.N - n0) : BN;
+        const int n_cur = n_valid >= BN ? BN : ((n_valid + 16 * CL - 1) & ~(16 * CL - 1));
+        const KSeg sg = p.segs[0];
+        if (elect_one()) {
+          if (CL == 1) {
+            mbar_expect_tx(bres_full, sg.k_blocks * Cfg::kStageB);
+            for (int kb = 0; kb < sg.k_blocks; ++kb)
+              tma_load_2d(bres_smem + kb * Cfg::kStageB, &tmB0, bres_full,
+                          sg.b_k_off + kb * kBlockK, n0);
+          } else {
+            const uint32_t bar = mapa_u32(smem_u32(bres_full), 0);
+            if (leader) mbar_expect_tx(bres_full, 2 * sg.k_blocks * Cfg::kStageB);
+            for (int kb = 0; kb < sg.k_blocks; ++kb)
+              tma_load_2d_cg2(bres_smem + kb * Cfg::kStageB, &tmB0, bar,
+                              sg.b_k_off + kb * kBlockK, n0 + cta_rank * (n_cur / 2));
+          }
+        }
+      }
+      for (int unit = unit_first; unit < num_units; unit += unit_step) {
         const int m0 = ((unit / num_n) * CL + cta_rank) * kBlockM;
         const int n0 = (unit % num_n) * BN;
         const int n_valid = (p.N - n0) < BN ? (p.N - n0) : BN;
@@ -350,15 +392,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
                 mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
                 tma_load_2d(sa, ma, &full_bar[stage], sg.a_k_off + kb * kBlockK,
                             sg.a_row_off + m0);
-                tma_load_2d(sb, mb, &full_bar[stage], sg.b_k_off + kb * kBlockK, n0);
+                if (!BRES) tma_load_2d(sb, mb, &full_bar[stage], sg.b_k_off + kb * kBlockK, n0);
               } else {
                 // both CTAs' bytes complete on the LEADER's barrier (it issues the MMAs)
                 const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
                 if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
                 tma_load_2d_cg2(sa, ma, full_leader, sg.a_k_off + kb * kBlockK,
                                 sg.a_row_off + m0);
-                tma_load_2d_cg2(sb, mb, full_leader, sg.b_k_off + kb * kBlockK,
-                                n0 + cta_rank * (n_cur / 2));
+                if (!BRES)
+                  tma_load_2d_cg2(sb, mb, full_leader, sg.b_k_off + kb * kBlockK,
+                                  n0 + cta_rank * (n_cur / 2));
               }
             }
             DEVIT_TRACE(2, tr_p);
@@ -379,7 +422,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
       int acc = 0;
       uint32_t acc_phase = 0;
       int tr_m = 0, tr_t = 0;
-      for (int unit = cluster_id; unit < num_units; unit += num_clusters) {
+      if (BRES && unit_first < num_units) {
+        mbar_wait_warp(bres_full, 0);  // the resident weight k-blocks (of both CTAs of a pair)
+        tc_fence_after();
+      }
+      for (int unit = unit_first; unit < num_units; unit += unit_step) {
         const int n0 = (unit % num_n) * BN;
         const int n_valid = (p.N - n0) < BN ? (p.N - n0) : BN;
         const int n_cur = n_valid >= BN ? BN : ((n_valid + 16 * CL - 1) & ~(16 * CL - 1));
@@ -401,7 +448,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
           tc_fence_after();
           DEVIT_TRACE(4, tr_m);
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint32_t sb = sa + Cfg::kStageA;
+          const uint32_t sb = BRES ? smem_u32(bres_smem + kb * Cfg::kStageB) : sa + Cfg::kStageA;
           const uint64_t da = make_sw128_desc(sa, 1024, 16);
           const uint64_t db = make_sw128_desc(sb, 1024, 16);
           if (elect_one()) {
@@ -500,14 +547,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
                          : make_float2(0.f, 0.f);
       }
     };
-    if (p.tma_epi && cluster_id < num_units) epi_prefetch(cluster_id);
+    if (p.tma_epi && unit_first < num_units) epi_prefetch(unit_first);
     if constexpr (RES) {
-      if (cluster_id < num_units) {
-        cur_cnt = res_tile(cluster_id, &nxt_row0, &nxt_n0);
+      if (unit_first < num_units) {
+        cur_cnt = res_tile(unit_first, &nxt_row0, &nxt_n0);
         for (int j = 0; j < cur_cnt; ++j) res_issue(j, nxt_row0, nxt_n0);
       }
     }
-    for (int unit = cluster_id; unit < num_units; unit += num_clusters) {
+    for (int unit = unit_first; unit < num_units; unit += unit_step) {
       const int m0 = ((unit / num_n) * CL + cta_rank) * kBlockM;
       const int n0 = (unit % num_n) * BN;
       const int row0 = m0 + quarter * 32;
@@ -539,12 +586,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
           ln_rstd = rsqrtf(var + p.ln_eps);
           ln_nmr = -ln_rstd * mean;
         }
-        if (unit + num_clusters < num_units) epi_prefetch(unit + num_clusters);
+        if (unit + unit_step < num_units) epi_prefetch(unit + unit_step);
         if constexpr (RES) {
           // residual chunks of the NEXT tile whose slots this tile does not use can fly now
           nxt_cnt = 0;
-          if (unit + num_clusters < num_units)
-            nxt_cnt = res_tile(unit + num_clusters, &nxt_row0, &nxt_n0);
+          if (unit + unit_step < num_units)
+            nxt_cnt = res_tile(unit + unit_step, &nxt_row0, &nxt_n0);
           for (int j = cur_cnt; j < nxt_cnt; ++j) res_issue(j, nxt_row0, nxt_n0);
         }
         if (ew == 0 && lane == 0) DEVIT_TRACE(9, tr_e);
@@ -812,15 +859,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
   }
 }
 
-template <int BN, int KIND, int CL, bool RES = false>
+template <int BN, int KIND, int CL, bool RES = false, bool BRES = false>
 static int launch_gemm(const CUtensorMap* tm, const GemmKParams& p, cudaStream_t stream,
                        int tag) {
-  using Cfg = GemmCfg<BN, CL, RES>;
+  using Cfg = GemmCfg<BN, CL, RES, BRES>;
   static bool attr_done[64] = {};  // per device; benign race: the attribute set is idempotent
   int dev = 0;
   DEVIT_CUDA_OK(cudaGetDevice(&dev));
   if (!attr_done[dev & 63]) {
-    DEVIT_CUDA_OK(cudaFuncSetAttribute(gemm_kernel<BN, KIND, CL, RES>,
+    DEVIT_CUDA_OK(cudaFuncSetAttribute(gemm_kernel<BN, KIND, CL, RES, BRES>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg::kSmemBytes));
     attr_done[dev & 63] = true;
@@ -853,7 +900,7 @@ static int launch_gemm(const CUtensorMap* tm, const GemmKParams& p, cudaStream_t
   cfg.numAttrs = na;
   {
     ProfScope ps(tag, stream);
-    DEVIT_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, KIND, CL, RES>, tm[0], tm[1], tm[2], tm[3],
+    DEVIT_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, KIND, CL, RES, BRES>, tm[0], tm[1], tm[2], tm[3],
                                      tm[4], tm[5], tm[6], p));
   }
   DEVIT_CUDA_OK(cudaGetLastError());
@@ -1098,6 +1145,19 @@ extern "C" int devit_gemm(const devit_gemm_args* a, void* stream_v) {
     }
     if (bn == 128) return launch_gemm_cl<128, 1, true>(cl, tm, p, stream, tag);
     return launch_gemm_cl<192, 1, true>(cl, tm, p, stream, tag);
+  }
+  // B-resident mode: one K segment of <= 6 k-blocks, CTA pairs, enough m-blocks per n-tile
+  {
+    static int env_bres = kEnvUnread;  // DEVIT_GEMM_BRES=0 switches it off (comparison)
+    const int num_n = (a->n + bn - 1) / bn;
+    const int num_mp = ((a->m + kBlockM - 1) / kBlockM + 1) / 2;
+    const int clusters = num_sms() / 2;
+    if (kind == 0 && cl == 2 && (bn == 192 || bn == 256) && p.num_segs == 1 &&
+        p.total_kb <= kMaxResidentKb && !a->resid && tma_epi && num_n <= clusters &&
+        num_mp >= 4 * clusters / num_n && env_int("DEVIT_GEMM_BRES", 1, &env_bres)) {
+      if (bn == 192) return launch_gemm<192, 0, 2, false, true>(tm, p, stream, tag);
+      return launch_gemm<256, 0, 2, false, true>(tm, p, stream, tag);
+    }
   }
   if (kind == 0) {
     if (bn == 128) return launch_gemm_cl<128, 0>(cl, tm, p, stream, tag);

@@ -159,6 +159,24 @@ def test_mlp_fused(m, f, d):
     assert rel(stats_out[..., 1].t(), (cols * cols).sum(-1)) < 1e-5
 
 
+@pytest.mark.parametrize("n", [576, 690, 960, 1152, 300])
+@pytest.mark.parametrize("k", [384, 256, 200])
+def test_gemm_b_resident_large_m(n, k):
+    """Large-M, K <= 384 GEMMs take the B-resident path (each CTA pair keeps one n-tile's weights
+    in shared memory and walks its m-tiles): ragged N / K, plain and LayerNorm-folded epilogues,
+    at the bs-256 token count (odd number of m-blocks per pair group)."""
+    m = 256 * 198
+    a = _mk((m, k), 61).bfloat16()
+    w = _mk((n, k), 62, 0.05).bfloat16()
+    bias = _mk((n,), 63)
+    ref = a.float() @ w.float().t() + bias
+    for bn in (0, 192, 256):
+        out = L.gemm(a, w, bias=bias, out_kind=L.OUT_BF16, block_n=bn, cluster_m=2)
+        assert rel(out, ref) < 6e-3, (bn, rel(out, ref))
+    out32 = L.gemm(a, w, bias=bias, out_kind=L.OUT_F32, act=L.ACT_GELU_ERF, cluster_m=2)
+    assert rel(out32, torch.nn.functional.gelu(ref)) < 2e-5
+
+
 @pytest.mark.parametrize("cl", [1, 2])
 @pytest.mark.parametrize("bn", [128, 192, 256])
 def test_gemm_cta_pair(cl, bn):

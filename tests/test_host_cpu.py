@@ -215,3 +215,32 @@ def test_shard_plan_eight_way():
         assert seen == set(range(8))
     p = parallel.shard_plan(16, 9, 8, 1024)
     assert p.num_groups == 2 and p.group_batch == 512 and p.subs == [1] and p.batch_lo == 512
+
+
+def test_gemm_tile_schedules_cover_every_tile_exactly_once():
+    """Python restatement of the two persistent tile schedules of csrc/gemm.cu (round-robin and
+    B-resident): every (m-pair, n-tile) unit is visited exactly once, and in B-resident mode a
+    cluster never changes its n-tile."""
+    def units(cluster_id, num_clusters, num_units, num_n, bres):
+        first, step = cluster_id, num_clusters
+        if bres:
+            n_fixed = cluster_id % num_n
+            group = (num_clusters - n_fixed + num_n - 1) // num_n
+            first = (cluster_id // num_n) * num_n + n_fixed
+            step = group * num_n
+        return list(range(first, num_units, step))
+
+    for num_mp, num_n, clusters in [(198, 3, 74), (198, 4, 74), (198, 5, 74), (99, 3, 74),
+                                    (1024, 2, 74), (37, 6, 74), (198, 1, 74), (5, 3, 15)]:
+        num_units = num_mp * num_n
+        for bres in (False, True):
+            if bres and num_n > clusters:
+                continue
+            seen = []
+            for c in range(min(clusters, num_units) if not bres else clusters):
+                u = units(c, min(clusters, num_units) if not bres else clusters, num_units, num_n,
+                          bres)
+                if bres:
+                    assert len({x % num_n for x in u}) <= 1
+                seen += u
+            assert sorted(seen) == list(range(num_units)), (num_mp, num_n, clusters, bres)

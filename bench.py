@@ -311,6 +311,27 @@ def main():
     out_host = torch.empty(Bg, NUM_CLASS).pin_memory()
     main_stream = torch.cuda.current_stream()
 
+    # the same public call, captured once per input buffer when CUDA graphs are in use (a user
+    # serving fixed-shape batches would do the same); eager launches otherwise
+    e2e_graphs = None
+    if graph is not None:
+        try:
+            e2e_graphs = []
+            for b in range(2):
+                bufs[b].copy_(x_dev)
+                torch.cuda.synchronize()
+                gb = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gb):
+                    ob = ens(bufs[b])
+                e2e_graphs.append((gb, ob))
+            torch.cuda.synchronize()
+        except Exception as e:  # noqa: BLE001
+            if rank == 0:
+                print(f"[bench] e2e graph capture unavailable ({type(e).__name__}: {e})",
+                      file=sys.stderr)
+            e2e_graphs = None
+            torch.cuda.synchronize()
+
     def e2e_loop(n):
         for i in range(n + 1):
             if i < n:  # prefetch batch i
@@ -322,7 +343,11 @@ def main():
             if i > 0:  # compute batch i-1
                 b = (i - 1) & 1
                 main_stream.wait_event(ready[b])
-                out = ens(bufs[b])
+                if e2e_graphs is not None:
+                    e2e_graphs[b][0].replay()
+                    out = e2e_graphs[b][1]
+                else:
+                    out = ens(bufs[b])
                 freed[b].record(main_stream)
                 out_host.copy_(out, non_blocking=True)
         main_stream.synchronize()

@@ -365,6 +365,72 @@ def main():
     h2d = x_host.numel() * 4 * world      # every rank copies its group's batch slice
     d2h = out_host.numel() * 4 * world
 
+    # ---- e2e_u8: the same public call fed DECODED uint8 batches: ToTensor +
+    #      Normalize run inside the patch extraction on the device, so a step's H2D copy is a
+    #      quarter of the fp32 one, and the step's result is the device-side eval tail (loss,
+    #      correct@1, correct@5: 12 bytes D2H) instead of the logits.  Reported beside `e2e`.
+    e2e_u8 = None
+    try:
+        u8_host = synth.images_u8(BATCH)[plan.batch_lo:plan.batch_hi].contiguous().pin_memory()
+        tgt = torch.randint(0, NUM_CLASS, (Bg,), generator=torch.Generator().manual_seed(7)).to(dev)
+        bufs8 = [torch.empty(u8_host.shape, dtype=torch.uint8, device=dev) for _ in range(2)]
+        tail_host = torch.empty(3).pin_memory()
+
+        def tail_step(xb):
+            return L.eval_tail(ens(xb), tgt)
+
+        for b in range(2):
+            bufs8[b].copy_(u8_host)
+        for _ in range(2):
+            tail_step(bufs8[0])
+        torch.cuda.synchronize()
+        u8_graphs = None
+        if graph is not None:
+            u8_graphs = []
+            for b in range(2):
+                gb = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gb):
+                    ob = tail_step(bufs8[b])
+                u8_graphs.append((gb, ob))
+            torch.cuda.synchronize()
+
+        def u8_loop(n):
+            for i in range(n + 1):
+                if i < n:
+                    b = i & 1
+                    with torch.cuda.stream(copy_stream):
+                        copy_stream.wait_event(freed[b])
+                        bufs8[b].copy_(u8_host, non_blocking=True)
+                        ready[b].record(copy_stream)
+                if i > 0:
+                    b = (i - 1) & 1
+                    main_stream.wait_event(ready[b])
+                    if u8_graphs is not None:
+                        u8_graphs[b][0].replay()
+                        out = u8_graphs[b][1]
+                    else:
+                        out = tail_step(bufs8[b])
+                    freed[b].record(main_stream)
+                    tail_host.copy_(out, non_blocking=True)
+            main_stream.synchronize()
+
+        for b in range(2):
+            freed[b].record(main_stream)
+        u8_loop(3)
+        barrier()
+        e0.record()
+        u8_loop(args.steps)
+        e1.record()
+        barrier()
+        u8_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+        e2e_u8 = {"value": BATCH / (u8_ms / 1e3), "unit": "images/sec", "ms_per_step": u8_ms,
+                  "h2d_bytes_per_step": u8_host.numel() * world, "d2h_bytes_per_step": 12 * world,
+                  "input": "uint8 NCHW, normalised on the device; result = loss + top-1/top-5 "
+                           "counts of the batch (devit_eval_tail)"}
+    except Exception as e:  # noqa: BLE001  (deterministic host-side failures hit every rank alike)
+        print(f"[bench] e2e_u8 arm failed ({type(e).__name__}: {e})", file=sys.stderr)
+        torch.cuda.synchronize()
+
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- per-kernel-family device times (CUDA events around every launch, eager)
@@ -456,6 +522,7 @@ def main():
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "images/sec", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "e2e_u8": e2e_u8,
         "gpu_launches": int(launches_per_step * args.steps),
         "roofline": roofline,
         "cpu_baseline": cpu,

@@ -16,10 +16,11 @@ import torch
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "lib" / "libdevit_b200.so"
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 DEVIT_BF16, DEVIT_FP32 = 0, 1
 OUT_BF16, OUT_F32, OUT_F32_SPLIT = 0, 1, 2
 ACT_NONE, ACT_GELU_ERF, ACT_RELU = 0, 1, 2
+LAYOUT_NCHW, LAYOUT_NHWC = 0, 1
 
 
 class DevitError(RuntimeError):
@@ -122,6 +123,13 @@ _SIGS = {
                                        C.c_int32, C.c_int64, C.c_void_p]),
     "devit_im2col_tokens": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                       C.c_int32, C.c_int32, C.c_int64, C.c_void_p]),
+    "devit_im2col_tokens_u8": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_float),
+                                         C.POINTER(C.c_float), C.c_void_p, C.c_int32, C.c_int32,
+                                         C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_void_p]),
+    "devit_eval_tail_workspace_bytes": (C.c_size_t, [C.c_int32]),
+    "devit_eval_tail": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32,
+                                  C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                                  C.c_void_p]),
     "devit_token_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                    C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "devit_vit_forward_patches": (C.c_int, [C.POINTER(VitDesc), C.c_void_p, C.c_int64, C.c_int32,
@@ -276,7 +284,7 @@ def gemm(a, b, *, precision=DEVIT_BF16, m=None, n=None, segs=None, out=None,
 
 TAGS = ["gemm_other", "gemm_patch", "gemm_qkv", "gemm_proj", "gemm_fc1", "gemm_fc2",
         "gemm_fusion", "gemm_head", "attention", "layernorm", "gather_ln", "im2col",
-        "token_prefix", "gemm_mlp_fused"]
+        "token_prefix", "gemm_mlp_fused", "eval_tail"]
 
 
 def profile_enable(on: bool) -> None:
@@ -305,6 +313,52 @@ def im2col_tokens(images, num_prefix, precision=DEVIT_BF16):
     check(load().devit_im2col_tokens(ptr(images), ptr(a), B, Cn, H, num_prefix, kind, plane,
                                      stream_ptr()))
     return a
+
+
+def im2col_tokens_u8(images, mean, std, num_prefix, precision=DEVIT_BF16, layout=LAYOUT_NCHW):
+    """Token-row patch matrix of a uint8 batch ([B,C,H,W], or [B,H,W,3] with LAYOUT_NHWC) with
+    ToTensor + Normalize(mean, std) applied on the device (see devit_im2col_tokens_u8)."""
+    if images.dtype != torch.uint8 or images.dim() != 4:
+        raise DevitError("im2col_tokens_u8 takes a 4-d uint8 tensor")
+    images = images.contiguous()
+    if layout == LAYOUT_NCHW:
+        B, Cn, H, W = images.shape
+    else:
+        B, H, W, Cn = images.shape
+    if H != W or len(mean) != Cn or len(std) != Cn:
+        raise DevitError(f"im2col_tokens_u8: square images and {Cn} mean/std values expected")
+    rows, k = B * (num_prefix + (H // 16) * (W // 16)), Cn * 256
+    if precision == DEVIT_BF16:
+        a = torch.empty(rows, k, device=images.device, dtype=torch.bfloat16)
+        kind, plane = OUT_BF16, 0
+    else:
+        a = torch.empty(2, rows, k, device=images.device, dtype=torch.float32)
+        kind, plane = OUT_F32_SPLIT, rows * k
+    m = (C.c_float * Cn)(*[float(v) for v in mean])
+    s = (C.c_float * Cn)(*[float(v) for v in std])
+    check(load().devit_im2col_tokens_u8(ptr(images), layout, m, s, ptr(a), B, Cn, H, num_prefix,
+                                        kind, plane, stream_ptr()))
+    return a
+
+
+def eval_tail(logits, target, acc=None, topk=5, want_batch=True):
+    """Device-side CrossEntropy + top-1 / top-k counts of one batch (see devit_eval_tail).
+    `acc`: float64 [5] running meters updated in place.  Returns float32 [3]
+    {mean loss, #correct@1, #correct@k} of this batch (or None when want_batch is False)."""
+    if logits.dtype != torch.float32 or logits.dim() != 2 or logits.stride(1) != 1:
+        raise DevitError("eval_tail takes fp32 logits [batch, classes] with unit column stride")
+    if target.dtype != torch.int64 or target.shape != (logits.shape[0],):
+        raise DevitError("eval_tail takes int64 targets [batch]")
+    if acc is not None and (acc.dtype != torch.float64 or acc.numel() != 5):
+        raise DevitError("eval_tail: acc must be a float64 tensor of 5 elements")
+    B, Cn = logits.shape
+    lib = load()
+    ws = torch.empty(lib.devit_eval_tail_workspace_bytes(B), device=logits.device,
+                     dtype=torch.uint8)
+    out = torch.empty(3, device=logits.device, dtype=torch.float32) if want_batch else None
+    check(lib.devit_eval_tail(ptr(logits), logits.stride(0), ptr(target.contiguous()), B, Cn,
+                              topk, ptr(ws), ws.numel(), ptr(acc), ptr(out), stream_ptr()))
+    return out
 
 
 def rowstats(x):

@@ -19,7 +19,8 @@ void count_launch(int n = 1);
 enum ProfTag {
   kTagGemmOther = 0, kTagGemmPatch = 1, kTagGemmQkv = 2, kTagGemmProj = 3, kTagGemmFc1 = 4,
   kTagGemmFc2 = 5, kTagGemmFusion = 6, kTagGemmHead = 7, kTagAttention = 8, kTagLayerNorm = 9,
-  kTagGatherLn = 10, kTagIm2col = 11, kTagPrefix = 12, kTagMlpFused = 13, kNumProfTags = 16
+  kTagGatherLn = 10, kTagIm2col = 11, kTagPrefix = 12, kTagMlpFused = 13, kTagEvalTail = 14,
+  kNumProfTags = 16
 };
 struct ProfScope {
   cudaStream_t stream;

@@ -55,6 +55,12 @@ class MultiViT(nn.Module):
             b.set_precision(precision)
         return self
 
+    def set_input_norm(self, mean, std):
+        """Device-side ToTensor + Normalize for uint8 batches (see VisionTransformer)."""
+        for b in self.backbones:
+            b.set_input_norm(mean, std)
+        return self
+
     @torch.no_grad()
     def forward_slab(self, x, subs=None):
         """Runs the sub-models in `subs` (default: all) and returns (slab_f32, slab_op) with
@@ -71,11 +77,14 @@ class MultiViT(nn.Module):
         # every sub-model embeds the SAME images (models/ensemble_models.py:33): extract the
         # patch matrix once when several of them run here and share the patch geometry
         patches = None
-        if len(subs) > 1 and x.is_cuda and x.dim() == 4:
-            geo = {(bb.patch_embed.img_size, bb.patch_embed.proj.weight.shape[1:], bb.num_tokens)
-                   for bb in (self.backbones[s] for s in subs)}
-            if len(geo) == 1 and tuple(x.shape[2:]) == tuple(bb0.patch_embed.img_size):
-                patches = L.im2col_tokens(x.float().contiguous(), bb0.num_tokens, prec)
+        if (len(subs) > 1 or x.dtype == torch.uint8) and x.is_cuda and x.dim() == 4:
+            geo = {(bb.patch_embed.img_size, bb.patch_embed.proj.weight.shape[1:], bb.num_tokens,
+                    bb.input_norm) for bb in (self.backbones[s] for s in subs)}
+            if len(geo) == 1:
+                bb0._check_input(x, convert=False)
+                if bb0.precision != self.precision:
+                    bb0.set_precision(self.precision)
+                patches = bb0.patches_of(x)
         for i, s in enumerate(subs):
             bb = self.backbones[s]
             if bb.precision != self.precision:

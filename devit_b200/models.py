@@ -30,6 +30,22 @@ from . import _lib as L
 from . import packing
 from .registry import register_model
 
+# timm.data.constants, used by the reference's transforms (data/get_dataset.py:11,108)
+IMAGENET_DEFAULT_MEAN = (0.485, 0.456, 0.406)
+IMAGENET_DEFAULT_STD = (0.229, 0.224, 0.225)
+
+
+def u8_layout(x, side):
+    """DEVIT layout id of a 4-d uint8 image batch: [B,C,H,W] or [B,H,W,3]."""
+    if x.dim() != 4:
+        raise L.DevitError("uint8 image batches must be 4-d ([B,C,H,W] or [B,H,W,3])")
+    if x.shape[2] == side and x.shape[3] == side:
+        return L.LAYOUT_NCHW
+    if x.shape[1] == side and x.shape[2] == side and x.shape[3] == 3:
+        return L.LAYOUT_NHWC
+    raise L.DevitError(f"uint8 batch {tuple(x.shape)} is neither [B,C,{side},{side}] nor "
+                       f"[B,{side},{side},3]")
+
 _PREC = {'bf16': L.DEVIT_BF16, 'fp32': L.DEVIT_FP32}
 
 
@@ -266,6 +282,7 @@ class VisionTransformer(nn.Module):
             self.resize_encoder_mlp = nn.Linear(self.embed_dim, self.resize_dim)
 
         self.precision = default_precision()
+        self.input_norm = (IMAGENET_DEFAULT_MEAN, IMAGENET_DEFAULT_STD)
         self._packs = {}
         self._observers_stale = False
         self._last_input = None
@@ -325,7 +342,13 @@ class VisionTransformer(nn.Module):
             self._packs = {key: hit}  # one live pack per model
         return hit[1]
 
-    def _check_input(self, x):
+    def set_input_norm(self, mean=IMAGENET_DEFAULT_MEAN, std=IMAGENET_DEFAULT_STD):
+        """Normalisation applied on the device to uint8 inputs (ToTensor + Normalize of the
+        reference's eval transform, data/get_dataset.py:107-108)."""
+        self.input_norm = (tuple(float(v) for v in mean), tuple(float(v) for v in std))
+        return self
+
+    def _check_input(self, x, convert=True):
         if not x.is_cuda:
             raise L.DevitError("devit_b200 models run on CUDA (sm_100) tensors only; "
                                "there is no CPU fallback")
@@ -334,20 +357,39 @@ class VisionTransformer(nn.Module):
             raise L.DevitError("devit_b200 is forward/inference only: call .eval() "
                                "(dropout / drop-path are not implemented)")
         H = self.patch_embed.img_size[0]
-        assert x.shape[2] == H and x.shape[3] == H, \
-            f"Input image size ({x.shape[2]}*{x.shape[3]}) doesn't match model ({H}*{H})."
+        if x.dtype == torch.uint8:
+            nhwc = u8_layout(x, H) == L.LAYOUT_NHWC
+            h, w = (x.shape[1], x.shape[2]) if nhwc else (x.shape[2], x.shape[3])
+        else:
+            h, w = x.shape[2], x.shape[3]
+        assert h == H and w == H, f"Input image size ({h}*{w}) doesn't match model ({H}*{H})."
+        if x.dtype == torch.uint8 or not convert:
+            return x
         return x.float().contiguous()
+
+    def patches_of(self, x):
+        """Token-row patch matrix of a batch in this model's operand format: fp32 NCHW images as
+        they are, uint8 images ([B,C,H,W] or [B,H,W,3]) normalised on the device."""
+        prec = _PREC[self.precision]
+        if x.dtype == torch.uint8:
+            H = self.patch_embed.img_size[0]
+            mean, std = self.input_norm
+            return L.im2col_tokens_u8(x, mean, std, self.num_tokens, prec, u8_layout(x, H))
+        return L.im2col_tokens(x.float().contiguous(), self.num_tokens, prec)
 
     @torch.no_grad()
     def features_into(self, x, feats_f32=None, feats_op=None, x_out=None, num_layers=-1,
                       patches=None):
         """Fused forward of the compacted sub-model: images -> LayerNormed cls(/dist) rows,
         written into caller-provided slabs ([num_tokens, B, D] fp32 and/or operand format).
-        `patches` (optional): the token-row patch matrix of x from ``L.im2col_tokens`` -- the
-        sub-models of an ensemble embed the same images, so MultiViT extracts it once."""
-        x = self._check_input(x)
+        `patches` (optional): the token-row patch matrix of x from ``patches_of`` -- the
+        sub-models of an ensemble embed the same images, so MultiViT extracts it once.
+        uint8 images are normalised on the device (``set_input_norm``)."""
+        x = self._check_input(x, convert=patches is None)
         pk = self.packed(x.device)
         B = x.shape[0]
+        if patches is None and x.dtype == torch.uint8:
+            patches = self.patches_of(x)
         ws = packing.workspace(x.device, pk.workspace_bytes(B))
         plane = feats_op.stride(0) if (feats_op is not None and feats_op.dim() == 4) else 0
         if patches is None:

@@ -116,6 +116,29 @@ def images(batch, seed=1234, img=224, chans=3):
     return torch.randn(batch, chans, img, img, generator=gen)
 
 
+def images_u8(batch, seed=1234, img=224, chans=3, nhwc=False):
+    """Decoded-image stand-in: uniform uint8 pixels, [B,C,H,W] (or [B,H,W,C])."""
+    gen = torch.Generator().manual_seed(seed + 77)
+    x = torch.randint(0, 256, (batch, img, img, chans), generator=gen, dtype=torch.uint8)
+    return x.contiguous() if nhwc else x.permute(0, 3, 1, 2).contiguous()
+
+
+def eval_batches(sizes=(8, 8, 5), classes=100, seed=4242, scale=3.0):
+    """[(logits fp32 [b, classes], target int64 [b]), ...] with a ragged last batch; about half
+    of the targets are the arg-max so that both accuracy meters are exercised."""
+    gen = torch.Generator().manual_seed(seed)
+    out = []
+    for b in sizes:
+        logits = torch.randn(b, classes, generator=gen) * scale
+        target = torch.randint(0, classes, (b,), generator=gen)
+        top = logits.argmax(-1)
+        second = logits.topk(min(3, classes), -1).indices[:, -1]
+        pick = torch.rand(b, generator=gen)
+        target = torch.where(pick < 0.4, top, torch.where(pick < 0.7, second, target))
+        out.append((logits, target))
+    return out
+
+
 def shrink_gates(sub_idx, hidden=1536, heads=6, layer=12, shrink_ratio=0.3):
     """Sampled shrink_ratio-0.3 policy + random importance ranks -> (neuron_masks, head_masks),
     each a list of `layer` fp32 0/1 tensors, via the reference's index-selection rule."""

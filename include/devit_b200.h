@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define DEVIT_ABI_VERSION 2
+#define DEVIT_ABI_VERSION 3
 
 enum {
   DEVIT_OK = 0,
@@ -53,6 +53,9 @@ enum {
 
 enum { DEVIT_ACT_NONE = 0, DEVIT_ACT_GELU_ERF = 1, DEVIT_ACT_RELU = 2 };
 
+/* memory layout of uint8 image batches (devit_im2col_tokens_u8) */
+enum { DEVIT_LAYOUT_NCHW = 0, DEVIT_LAYOUT_NHWC = 1 };
+
 int devit_abi_version(void);
 const char* devit_last_error(void);
 /* 0 when the CURRENT cuda device is sm_100 (B200); DEVIT_ERR_DEVICE otherwise. */
@@ -69,7 +72,7 @@ enum {
   DEVIT_TAG_GEMM_PROJ = 3, DEVIT_TAG_GEMM_FC1 = 4, DEVIT_TAG_GEMM_FC2 = 5,
   DEVIT_TAG_GEMM_FUSION = 6, DEVIT_TAG_GEMM_HEAD = 7, DEVIT_TAG_ATTENTION = 8,
   DEVIT_TAG_LAYERNORM = 9, DEVIT_TAG_GATHER_LN = 10, DEVIT_TAG_IM2COL = 11,
-  DEVIT_TAG_PREFIX = 12, DEVIT_TAG_MLP_FUSED = 13, DEVIT_NUM_TAGS = 16
+  DEVIT_TAG_PREFIX = 12, DEVIT_TAG_MLP_FUSED = 13, DEVIT_TAG_EVAL_TAIL = 14, DEVIT_NUM_TAGS = 16
 };
 int devit_profile_enable(int on);
 int devit_profile_collect(double* ms_by_tag, long long* count_by_tag);
@@ -249,6 +252,42 @@ int devit_im2col_tokens(const float* images, void* a, int32_t batch, int32_t cha
                         void* stream);
 int devit_token_init(float* x, const float* prefix, const float* pos, const float* bias,
                      int32_t batch, int32_t tokens, int32_t dim, int32_t num_prefix, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * devit_im2col_tokens_u8: the same token-row patch matrix as devit_im2col_tokens, computed from
+ * the DECODED uint8 images, with the input normalisation applied on the way:
+ *     v = ((float)u8 / 255 - mean[c]) / std[c]      (fp32, IEEE division, no contraction)
+ * i.e. torchvision ToTensor + Normalize of the reference's eval transform
+ * (data/get_dataset.py:107-108) and images.to(device) (engine.py:224) folded into the patch
+ * extraction: a batch crosses PCIe as bytes (4x less than fp32) and the fp32 image tensor is never
+ * materialised.  The fp32 values are bit-identical to the CPU transform's.
+ * images: DEVIT_LAYOUT_NCHW [batch, chans, hw, hw] or DEVIT_LAYOUT_NHWC [batch, hw, hw, 3];
+ * mean / stdv: HOST pointers to `chans` floats (1 <= chans <= 4).
+ * ------------------------------------------------------------------------------------- */
+int devit_im2col_tokens_u8(const uint8_t* images, int32_t layout, const float* mean,
+                           const float* stdv, void* a, int32_t batch, int32_t chans, int32_t hw,
+                           int32_t num_prefix, int32_t out_kind, int64_t out_plane_stride,
+                           void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * devit_eval_tail: the per-batch tail of engine.evaluate / evaluate_ens_disjoint
+ * (engine.py:229-238): CrossEntropyLoss(logits, target) (mean over the batch) and timm
+ * accuracy(logits, target, topk=(1, k)), accumulated ON THE DEVICE so the evaluation loop needs
+ * one host synchronisation per epoch instead of three .item() calls per batch.
+ *   logits fp32 [batch, classes] (row stride ld), target int64 [batch];
+ *   acc (optional) double[5], updated in place:  acc[0] += mean loss of this batch, acc[1] += 1,
+ *       acc[2] += #correct@1, acc[3] += #correct@k, acc[4] += batch   -- exactly the totals /
+ *       counts the reference's MetricLogger meters receive (utils/dist_utils.py:30-33);
+ *   batch_out (optional) float[3] = {mean loss, #correct@1, #correct@k} of this batch;
+ *   workspace: devit_eval_tail_workspace_bytes(batch) bytes.
+ * A sample counts as correct@k when fewer than k classes sort before its target in descending
+ * logit order (ties: the smaller class index first).  A target outside [0, classes) gives a NaN
+ * loss and is never correct.  Deterministic (fixed reduction order, no float atomics).
+ * ------------------------------------------------------------------------------------- */
+size_t devit_eval_tail_workspace_bytes(int32_t batch);
+int devit_eval_tail(const float* logits, int64_t ld, const int64_t* target, int32_t batch,
+                    int32_t classes, int32_t topk, void* workspace, size_t workspace_bytes,
+                    double* acc, float* batch_out, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * devit_token_prefix: x[b, j, :] = prefix[j, :] + pos[j, :] for j < num_prefix

@@ -156,3 +156,46 @@ def shrink_macs(neuron_sparsity, head_sparsity, emb=384, seq_length=197, mlp_rat
 
 def to_dtype(sd, dtype):
     return {k: v.to(dtype) for k, v in sd.items()}
+
+
+# ----------------------------------------------------------------------------- either side of
+# the forward path: the eval transform's tensor part and the eval tail
+def to_tensor_normalize(images_u8, mean, std, layout='nchw'):
+    """torchvision ToTensor + Normalize as composed at data/get_dataset.py:107-108, on an
+    already decoded / resized uint8 batch: ToTensor = HWC->CHW, `.to(float32).div(255)`;
+    Normalize = `.sub_(mean[:,None,None]).div_(std[:,None,None])` with fp32 mean / std.
+    `layout`: 'nchw' [B,C,H,W] or 'nhwc' [B,H,W,C].  Returns fp32 [B,C,H,W]."""
+    x = images_u8 if layout == 'nchw' else images_u8.permute(0, 3, 1, 2)
+    x = x.to(torch.float32).div(255)
+    m = torch.as_tensor(mean, dtype=torch.float32).view(1, -1, 1, 1)
+    s = torch.as_tensor(std, dtype=torch.float32).view(1, -1, 1, 1)
+    return x.sub(m).div(s).contiguous()
+
+
+def eval_tail(logits, target, topk=5):
+    """One batch of engine.py:33-36 / 229-234: CrossEntropyLoss (mean) and timm 0.5.4
+    accuracy(output, target, topk=(1, topk)) as COUNTS.  A sample is correct@k when fewer than
+    k classes sort before its target (larger logit; equal logit and smaller index).
+    Returns (mean loss as float, #correct@1, #correct@k)."""
+    logits = logits.to(torch.float32)
+    loss = F.cross_entropy(logits, target).item()
+    lt = logits.gather(1, target.view(-1, 1))
+    idx = torch.arange(logits.shape[1]).view(1, -1)
+    ahead = ((logits > lt) | ((logits == lt) & (idx < target.view(-1, 1)))).sum(1)
+    k = min(topk, logits.shape[1])
+    return loss, int((ahead < 1).sum()), int((ahead < k).sum())
+
+
+def eval_epoch(batches, topk=5):
+    """The dict engine.evaluate returns (engine.py:39-45) for `batches` = [(logits, target), ...]:
+    MetricLogger semantics (utils/dist_utils.py:30-33,59-60) -- `loss` is updated with n = 1 per
+    batch, `acc1` / `acc5` (percent of the batch) with n = batch size."""
+    loss_total, n_batches, c1, ck, n = 0.0, 0, 0, 0, 0
+    for logits, target in batches:
+        l, a, b = eval_tail(logits, target, topk)
+        loss_total += l
+        n_batches += 1
+        c1 += a
+        ck += b
+        n += logits.shape[0]
+    return {'loss': loss_total / n_batches, 'acc1': 100.0 * c1 / n, 'acc5': 100.0 * ck / n}

@@ -148,6 +148,48 @@ def install():
         sys.path.insert(0, REFERENCE_ROOT)
 
 
+def _accuracy(output, target, topk=(1,)):
+    """timm 0.5.4 timm/utils/metrics.py accuracy(), restated: the top-max(topk) predictions of
+    every sample are compared with the target; precision@k in percent of the batch."""
+    maxk = min(max(topk), output.size()[1])
+    batch_size = target.size(0)
+    _, pred = output.topk(maxk, 1, True, True)
+    pred = pred.t()
+    correct = pred.eq(target.reshape(1, -1).expand_as(pred))
+    return [correct[:min(k, maxk)].reshape(-1).float().sum(0) * 100. / batch_size for k in topk]
+
+
+def _install_engine_shims():
+    """timm names engine.py / utils/losses.py import at module level (engine.py:11-13,
+    utils/losses.py:7).  Only `accuracy` is used by the evaluation loops; the others are
+    training-only and get inert placeholders."""
+    if 'timm.utils' in sys.modules:
+        return
+    timm = sys.modules['timm']
+    data = types.ModuleType('timm.data')
+    utils = types.ModuleType('timm.utils')
+    clip = types.ModuleType('timm.utils.clip_grad')
+    loss = types.ModuleType('timm.loss')
+    data.Mixup = type('Mixup', (), {})
+    utils.accuracy = _accuracy
+    utils.ModelEma = type('ModelEma', (), {})
+    clip.dispatch_clip_grad = lambda *a, **k: None
+    loss.SoftTargetCrossEntropy = type('SoftTargetCrossEntropy', (nn.Module,), {})
+    utils.clip_grad = clip
+    timm.data, timm.utils, timm.loss = data, utils, loss
+    for m in (data, utils, clip, loss):
+        sys.modules[m.__name__] = m
+
+
+def load_reference_engine():
+    """The reference's engine module (evaluate / evaluate_ens_disjoint with its own MetricLogger
+    and CrossEntropyLoss; timm's accuracy() restated above)."""
+    install()
+    _install_engine_shims()
+    import engine  # noqa: E402  (reference)
+    return engine
+
+
 def load_reference():
     """Returns (de_vit module, deit_vit module, ensemble_models module, create_model)."""
     install()

@@ -1,6 +1,6 @@
 """GPU parity of the two steps either side of the forward path, through
 the C ABI: uint8 images -> normalised patch matrix (bit-exact against the oracle's torchvision
-restatement) and the device-side eval tail (counts exact, loss <= 1e-6 relative), plus the
+restatement) and the device-side eval tail (counts exact, loss <= 2e-6 relative), plus the
 engine.evaluate* drop-ins against the reference's own engine.evaluate golden."""
 from pathlib import Path
 
@@ -100,7 +100,7 @@ def test_eval_tail_vs_oracle(sizes, classes):
     for lg, tg in batches:
         out = L.eval_tail(lg.cuda(), tg.cuda(), acc).cpu()
         loss, c1, ck = O.eval_tail(lg, tg)
-        assert abs(out[0].item() - loss) <= 1e-6 * abs(loss)
+        assert abs(out[0].item() - loss) <= 2e-6 * abs(loss)
         assert (int(out[1]), int(out[2])) == (c1, ck)
     ref = O.eval_epoch(batches)
     got = engine.meters_to_dict(acc.tolist())
@@ -116,13 +116,13 @@ def test_eval_tail_ties_strided_logits_and_bad_targets():
         out = L.eval_tail(logits.cuda(), tg.cuda(), None, topk=k).cpu()
         loss, c1, ck = O.eval_tail(logits, tg, topk=k)
         assert (int(out[1]), int(out[2])) == (c1, ck)
-        assert abs(out[0].item() - loss) <= 1e-6 * abs(loss)
+        assert abs(out[0].item() - loss) <= 2e-6 * abs(loss)
     # a column slice of a wider matrix (row stride > classes)
     wide = synth.eval_batches((9,), 128)[0][0]
     tg = torch.arange(9) % 100
     out = L.eval_tail(wide.cuda()[:, :100], tg.cuda()).cpu()
     loss, c1, ck = O.eval_tail(wide[:, :100].contiguous(), tg)
-    assert (int(out[1]), int(out[2])) == (c1, ck) and abs(out[0].item() - loss) <= 1e-6 * loss
+    assert (int(out[1]), int(out[2])) == (c1, ck) and abs(out[0].item() - loss) <= 2e-6 * loss
     # an out-of-range target poisons the loss and is never correct
     out = L.eval_tail(logits.cuda(), torch.tensor([0, 9]).cuda(), topk=4).cpu()
     assert torch.isnan(out[0]) and (int(out[1]), int(out[2])) == (1, 1)

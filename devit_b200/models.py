@@ -35,16 +35,16 @@ IMAGENET_DEFAULT_MEAN = (0.485, 0.456, 0.406)
 IMAGENET_DEFAULT_STD = (0.229, 0.224, 0.225)
 
 
-def u8_layout(x, side):
-    """DEVIT layout id of a 4-d uint8 image batch: [B,C,H,W] or [B,H,W,3]."""
+def u8_layout(x, side=None):
+    """DEVIT layout id of a 4-d uint8 image batch: [B,C,H,W] (C <= 4) or [B,H,W,3]."""
     if x.dim() != 4:
         raise L.DevitError("uint8 image batches must be 4-d ([B,C,H,W] or [B,H,W,3])")
-    if x.shape[2] == side and x.shape[3] == side:
+    if x.shape[2] == x.shape[3] and x.shape[1] <= 4:  # (sides are multiples of 16: no overlap)
         return L.LAYOUT_NCHW
-    if x.shape[1] == side and x.shape[2] == side and x.shape[3] == 3:
+    if x.shape[1] == x.shape[2] and x.shape[3] == 3:
         return L.LAYOUT_NHWC
-    raise L.DevitError(f"uint8 batch {tuple(x.shape)} is neither [B,C,{side},{side}] nor "
-                       f"[B,{side},{side},3]")
+    raise L.DevitError(f"uint8 batch {tuple(x.shape)} is neither [B,C,H,H] with C <= 4 nor "
+                       f"[B,H,H,3]")
 
 _PREC = {'bf16': L.DEVIT_BF16, 'fp32': L.DEVIT_FP32}
 

@@ -43,6 +43,7 @@ class GemmArgs(C.Structure):
         ("out", C.c_void_p), ("ldo", C.c_int64), ("out_kind", C.c_int32),
         ("out_plane_stride", C.c_int64),
         ("bias", C.c_void_p), ("resid", C.c_void_p), ("ldr", C.c_int64),
+        ("resid_period", C.c_int32),
         ("rowbias", C.c_void_p), ("ld_rowbias", C.c_int64),
         ("act", C.c_int32), ("alpha", C.c_float),
         ("rowmap_period", C.c_int32), ("rowmap_stride", C.c_int32), ("rowmap_off", C.c_int32),
@@ -87,6 +88,7 @@ class VitDesc(C.Structure):
         ("norm_g", C.c_void_p), ("norm_b", C.c_void_p),
         ("layers", C.POINTER(LayerDesc)),
         ("w_plane_stride_unused", C.c_int64),
+        ("tok_table", C.c_void_p),
     ]
 
 
@@ -230,7 +232,8 @@ def operand_to_f32(t: torch.Tensor, precision: int) -> torch.Tensor:
 def gemm(a, b, *, precision=DEVIT_BF16, m=None, n=None, segs=None, out=None,
          out_kind=OUT_BF16, bias=None, resid=None, rowbias=None, act=ACT_NONE, alpha=1.0,
          rowmap=(0, 0, 0), block_n=0, out_rows=None, tag=0, cluster_m=0,
-         ln_stats=None, ln_colsum=None, ln_dim=0, ln_eps=0.0, out_bf16=None, stats_out=None):
+         ln_stats=None, ln_colsum=None, ln_dim=0, ln_eps=0.0, out_bf16=None, stats_out=None,
+         resid_period=0):
     """out = epilogue(sum_s A_s B_s^T); see include/devit_b200.h (devit_gemm)."""
     lib = load()
     planes = 1 if precision == DEVIT_BF16 else 2
@@ -265,6 +268,7 @@ def gemm(a, b, *, precision=DEVIT_BF16, m=None, n=None, segs=None, out=None,
     g.bias = ptr(bias)
     g.resid = ptr(resid)
     g.ldr = resid.stride(0) if resid is not None else 0
+    g.resid_period = resid_period
     g.rowbias = ptr(rowbias)
     g.ld_rowbias = rowbias.stride(0) if rowbias is not None else 0
     g.act, g.alpha = act, alpha

@@ -52,29 +52,37 @@ __device__ __forceinline__ void store16(void* a, long long o, const float (&v)[1
 // One thread owns one 16-pixel patch-row segment (y, x0 .. x0+15).  NCHW: one 16-byte load per
 // (channel, segment) item; NHWC (3 channels): three 16-byte loads hold the 48 interleaved bytes of
 // the segment and feed three 16-element output runs.  Output runs are contiguous K ranges of a
-// patch row (32 B bf16 / 64 B fp32), consecutive threads write consecutive patches.
+// patch row (32 B bf16 / 64 B fp32).
 template <bool NHWC>
 __global__ void __launch_bounds__(256)
 im2col16_u8_kernel(const uint8_t* __restrict__ img, void* __restrict__ a, int batch, int chans,
                    int hw, NormParams np, int out_kind, long long plane, int row_off,
                    int rows_per_img) {
+  // threads are numbered in OUTPUT order (image, patch, channel, py): consecutive threads write
+  // consecutive 32-byte (bf16) runs of the patch matrix
   const int g = hw >> 4;
+  const int P = g * g;
   const int items_c = NHWC ? 1 : chans;
-  const long long total = static_cast<long long>(batch) * items_c * hw * g;
+  const long long total = static_cast<long long>(batch) * P * items_c * 16;
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
-  const int gx = static_cast<int>(i % g);
-  long long t = i / g;
-  const int y = static_cast<int>(t % hw);
-  t /= hw;
+  const int py = static_cast<int>(i) & 15;
+  long long t = i >> 4;
   const int c0 = NHWC ? 0 : static_cast<int>(t % items_c);
-  const int b = static_cast<int>(t / items_c);
-  const long long m = static_cast<long long>(b) * rows_per_img + row_off + (y >> 4) * g + gx;
+  t /= items_c;
+  const int pidx = static_cast<int>(t % P);
+  const int b = static_cast<int>(t / P);
+  const int gy = pidx / g, gx = pidx - gy * g;
+  const int y = gy * 16 + py;
+  const long long m = static_cast<long long>(b) * rows_per_img + row_off + pidx;
   const long long kdim = static_cast<long long>(chans) * 256;
-  const long long o0 = m * kdim + (y & 15) * 16;
+  const long long o0 = m * kdim + py * 16;
+  // 16-byte units: NCHW pixel offset / 16, NHWC pixel offset * 3 / 16
+  const long long src16 = NHWC ? ((static_cast<long long>(b) * hw + y) * g + gx) * 3
+                               : ((static_cast<long long>(b) * chans + c0) * hw + y) * g + gx;
   float v[16];
   if (!NHWC) {
-    const uint4 w = __ldg(reinterpret_cast<const uint4*>(img) + i);
+    const uint4 w = __ldg(reinterpret_cast<const uint4*>(img) + src16);
     const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
     // select chain instead of a dynamic index into the parameter struct (no local copy)
     const float mu = c0 == 0 ? np.mean[0] : c0 == 1 ? np.mean[1] : c0 == 2 ? np.mean[2] : np.mean[3];
@@ -84,7 +92,7 @@ im2col16_u8_kernel(const uint8_t* __restrict__ img, void* __restrict__ a, int ba
     store16(a, o0 + static_cast<long long>(c0) * 256, v, out_kind, plane);
   } else {
     // 48 bytes: pixel p, channel c at byte 3 p + c
-    const uint4* src = reinterpret_cast<const uint4*>(img) + i * 3;
+    const uint4* src = reinterpret_cast<const uint4*>(img) + src16;
     const uint4 w0 = __ldg(src), w1 = __ldg(src + 1), w2 = __ldg(src + 2);
     const uint32_t ws[12] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w,
                              w2.x, w2.y, w2.z, w2.w};

@@ -288,10 +288,15 @@ static int vit_forward_impl(const devit_vit_desc* d, const float* images, const 
     if ((rc = sync_debug("im2col", -1, stream))) return rc;
     a_patch = qkv;
   }
-  rc = devit_token_init(x, d->prefix, d->pos, d->b_patch, batch, L.tokens, D, d->num_prefix,
-                        stream);
-  if (rc) return rc;
-  if ((rc = sync_debug("token init", -1, stream))) return rc;
+  // x = pos (+ cls/dist - bias): either materialised per image (devit_token_init) and added as a
+  // plain residual, or -- when the host packed the wrapped [tokens + 31, D] table -- added by the
+  // GEMM as a periodic residual straight from L2 (no 78 MB write + read of x at bs 256)
+  if (!d->tok_table) {
+    rc = devit_token_init(x, d->prefix, d->pos, d->b_patch, batch, L.tokens, D, d->num_prefix,
+                          stream);
+    if (rc) return rc;
+    if ((rc = sync_debug("token init", -1, stream))) return rc;
+  }
   devit_gemm_args g;
   base_gemm(&g, prec);
   g.m = static_cast<int>(M);
@@ -302,6 +307,7 @@ static int vit_forward_impl(const devit_vit_desc* d, const float* images, const 
   g.segs[0] = devit_gemm_seg{0, 0, 0, kp};
   g.out = x; g.ldo = D; g.out_kind = DEVIT_OUT_F32;
   g.bias = d->b_patch; g.resid = x; g.ldr = D;
+  if (d->tok_table) { g.resid = d->tok_table; g.resid_period = L.tokens; }
   if (fold && nl > 0) {
     g.out_bf16 = y; g.ld_out_bf16 = D; g.stats_out = stats;
     parts = L.stat_parts;

@@ -47,6 +47,7 @@ struct GemmKParams {
   const float* bias;
   const float* resid;
   long long ldr;
+  int resid_period;  // > 0: the residual of row m is row (m % resid_period) of a wrapped table
   const float* rowbias;
   long long ld_rowbias;
   int act;
@@ -513,11 +514,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
       const int mine = nch - half * kResSlots;
       return mine < 0 ? 0 : (mine > kResSlots ? kResSlots : mine);
     };
+    // row of the residual tensor that holds the residual of output row r (a 32-row box never
+    // wraps: periodic tables repeat their first 31 rows at the end)
+    auto res_row = [&](int r) -> int { return p.resid_period > 0 ? r % p.resid_period : r; };
     auto res_issue = [&](int j, int row0_, int n0_) {
       if (elect_one()) {
         mbar_expect_tx(&res_bar[j], 4096);
         tma_load_2d(res_slots + j * 4096, &tmR, &res_bar[j], n0_ + (half * kResSlots + j) * 32,
-                    row0_);
+                    res_row(row0_));
       }
     };
     // ---- per-tile epilogue constants, requested one tile ahead into registers
@@ -718,7 +722,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
                   if (j - 1 < nxt_cnt) {
                     mbar_expect_tx(&res_bar[j - 1], 4096);
                     tma_load_2d(b - 4096, &tmR, &res_bar[j - 1],
-                                nxt_n0 + (half * kResSlots + j - 1) * 32, nxt_row0);
+                                nxt_n0 + (half * kResSlots + j - 1) * 32, res_row(nxt_row0));
                   }
                 }
               }
@@ -730,7 +734,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
                 const int j = cur_cnt - 1;
                 mbar_expect_tx(&res_bar[j], 4096);
                 tma_load_2d(res_slots + j * 4096, &tmR, &res_bar[j],
-                            nxt_n0 + (half * kResSlots + j) * 32, nxt_row0);
+                            nxt_n0 + (half * kResSlots + j) * 32, res_row(nxt_row0));
               }
             }
             if (p.stats_out && cur_cnt > 0 && row0 + lane < p.M) {
@@ -996,6 +1000,11 @@ extern "C" int devit_gemm(const devit_gemm_args* a, void* stream_v) {
   p.out_plane_stride = a->out_plane_stride;
   p.bias = a->bias;
   p.resid = a->resid;
+  p.resid_period = a->resid_period;
+  DEVIT_REQUIRE(a->resid_period >= 0 && !(a->resid_period > 0 && !a->resid),
+                "devit_gemm: resid_period needs resid");
+  DEVIT_REQUIRE(!(a->resid_period > 0 && static_cast<const void*>(a->resid) == a->out),
+                "devit_gemm: a periodic residual table cannot alias the output");
   p.ldr = a->ldr;
   p.rowbias = a->rowbias;
   p.ld_rowbias = a->ld_rowbias;
@@ -1132,11 +1141,14 @@ extern "C" int devit_gemm(const devit_gemm_args* a, void* stream_v) {
     }
     tm[6] = tm[4];
     if (a->resid) {
-      rc = encode_tmap_2d(&tm[6], a->resid, 4, a->n, a->m, a->ldr, 32, 32, false);
+      const int r_rows = a->resid_period > 0 ? a->resid_period + 31 : a->m;
+      rc = encode_tmap_2d(&tm[6], a->resid, 4, a->n, r_rows, a->ldr, 32, 32, false);
       if (rc) return rc;
     }
   }
 
+  DEVIT_REQUIRE(a->resid_period == 0 || tma_epi,
+                "devit_gemm: resid_period needs the TMA epilogue (aligned fp32 output, no rowmap)");
   if (tma_epi && a->resid) {
     // residual variant: whole-tile residual slots in shared memory (BN <= 192, single CTA)
     if (kind == 0) {

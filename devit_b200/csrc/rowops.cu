@@ -154,39 +154,52 @@ token_init_kernel(float* __restrict__ x, const float* __restrict__ prefix,
   reinterpret_cast<float4*>(x)[i] = v;
 }
 
-// One thread converts 4 horizontally adjacent pixels (one float4) of one channel row.
+// One thread converts 8 horizontally adjacent pixels of one patch row: two independent float4
+// loads (32 B, one full sector: enough bytes in flight to cover the HBM latency at 2048
+// threads/SM) and one 16-byte store (bf16).  Threads are numbered in OUTPUT order
+// (image, patch, channel, py, half row), so consecutive threads write consecutive 16-byte chunks
+// of the patch matrix: every warp stores 512 contiguous bytes and reads 16 x 64 B row pieces.
 __global__ void __launch_bounds__(256)
 im2col16_kernel(const float* __restrict__ img, void* __restrict__ a, int batch, int chans, int hw,
                 int out_kind, long long plane, int row_off, int rows_per_img) {
-  const int w4 = hw >> 2;
-  const long long total = static_cast<long long>(batch) * chans * hw * w4;
+  const int g = hw >> 4;
+  const int P = g * g;
+  const long long total = static_cast<long long>(batch) * P * chans * 32;
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
-  const int x4 = static_cast<int>(i % w4);
-  long long t = i / w4;
-  const int y = static_cast<int>(t % hw);
-  t /= hw;
+  const int hx = static_cast<int>(i & 1);
+  const int py = static_cast<int>(i >> 1) & 15;
+  long long t = i >> 5;
   const int c = static_cast<int>(t % chans);
-  const int b = static_cast<int>(t / chans);
-  const float4 v = __ldg(reinterpret_cast<const float4*>(img) + i);
-  const int g = hw >> 4;
-  const int x = x4 << 2;
-  // patch (gy, gx) of image b -> row b * rows_per_img + row_off + gy * g + gx
-  const long long m = static_cast<long long>(b) * rows_per_img + row_off + (y >> 4) * g + (x >> 4);
-  const long long k = static_cast<long long>(c) * 256 + (y & 15) * 16 + (x & 15);
-  const long long o = m * (static_cast<long long>(chans) * 256) + k;
+  t /= chans;
+  const int pidx = static_cast<int>(t % P);
+  const int b = static_cast<int>(t / P);
+  const int gy = pidx / g, gx = pidx - gy * g;
+  const float4* src = reinterpret_cast<const float4*>(
+      img + ((static_cast<long long>(b) * chans + c) * hw + gy * 16 + py) * hw + gx * 16 + hx * 8);
+  const float4 v0 = __ldg(src), v1 = __ldg(src + 1);
+  const long long m = static_cast<long long>(b) * rows_per_img + row_off + pidx;
+  const long long o = m * (static_cast<long long>(chans) * 256) + c * 256 + py * 16 + hx * 8;
   if (out_kind == DEVIT_OUT_BF16) {
-    uint2 pk;
-    pk.x = pack_bf16x2(v.x, v.y);
-    pk.y = pack_bf16x2(v.z, v.w);
-    *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(a) + o) = pk;
+    uint4 pk;
+    pk.x = pack_bf16x2(v0.x, v0.y);
+    pk.y = pack_bf16x2(v0.z, v0.w);
+    pk.z = pack_bf16x2(v1.x, v1.y);
+    pk.w = pack_bf16x2(v1.z, v1.w);
+    *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(a) + o) = pk;
   } else if (out_kind == DEVIT_OUT_F32) {
-    *reinterpret_cast<float4*>(static_cast<float*>(a) + o) = v;
+    float4* d = reinterpret_cast<float4*>(static_cast<float*>(a) + o);
+    d[0] = v0;
+    d[1] = v1;
   } else {
-    const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
-    *reinterpret_cast<float4*>(static_cast<float*>(a) + o) = h;
-    *reinterpret_cast<float4*>(static_cast<float*>(a) + o + plane) =
-        make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+    const float4 h0 = make_float4(tf32_hi(v0.x), tf32_hi(v0.y), tf32_hi(v0.z), tf32_hi(v0.w));
+    const float4 h1 = make_float4(tf32_hi(v1.x), tf32_hi(v1.y), tf32_hi(v1.z), tf32_hi(v1.w));
+    float4* dh = reinterpret_cast<float4*>(static_cast<float*>(a) + o);
+    float4* dl = reinterpret_cast<float4*>(static_cast<float*>(a) + o + plane);
+    dh[0] = h0;
+    dh[1] = h1;
+    dl[0] = make_float4(v0.x - h0.x, v0.y - h0.y, v0.z - h0.z, v0.w - h0.w);
+    dl[1] = make_float4(v1.x - h1.x, v1.y - h1.y, v1.z - h1.z, v1.w - h1.w);
   }
 }
 
@@ -290,7 +303,7 @@ extern "C" int devit_im2col_patch16(const float* images, void* a, int32_t batch,
                 "devit_im2col_patch16: image side %d must be a positive multiple of 16", hw);
   DEVIT_REQUIRE(reinterpret_cast<uintptr_t>(images) % 16 == 0,
                 "devit_im2col_patch16: images must be 16-byte aligned");
-  const long long total = static_cast<long long>(batch) * chans * hw * (hw / 4);
+  const long long total = static_cast<long long>(batch) * chans * hw * (hw / 8);
   {
     ProfScope ps(kTagIm2col, stream);
     im2col16_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
@@ -315,7 +328,7 @@ extern "C" int devit_im2col_tokens(const float* images, void* a, int32_t batch, 
   const int tokens = num_prefix + (hw / 16) * (hw / 16);
   const size_t esz = out_kind == DEVIT_OUT_BF16 ? 2 : 4;
   const size_t k = static_cast<size_t>(chans) * 256;
-  const long long total = static_cast<long long>(batch) * chans * hw * (hw / 4);
+  const long long total = static_cast<long long>(batch) * chans * hw * (hw / 8);
   {
     ProfScope ps(kTagIm2col, stream);
     if (num_prefix > 0) {  // zero rows for the cls / dist tokens of every image

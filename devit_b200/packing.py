@@ -17,6 +17,7 @@ gate or a parameter changes; it is not on the per-batch path.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
@@ -118,6 +119,13 @@ class PackedVit:
             prefix.append(model.dist_token.detach().reshape(1, dim))
         desc.prefix = f32(torch.cat(prefix, 0))
         desc.pos = f32(model.pos_embed.detach().reshape(-1, dim))
+        # wrapped table pos (+ cls/dist - patch bias) for the periodic-residual patch GEMM
+        # (devit_vit_desc.tok_table); DEVIT_TOK_TABLE=0 falls back to devit_token_init
+        desc.tok_table = None
+        if os.environ.get('DEVIT_TOK_TABLE', '1') != '0':
+            desc.tok_table = f32(token_table(model.pos_embed.detach().float().cpu().reshape(-1, dim),
+                                             torch.cat(prefix, 0).float().cpu(),
+                                             pe.proj.bias.detach().float().cpu()))
         desc.norm_g, desc.norm_b = f32(model.norm.weight), f32(model.norm.bias)
         desc.layers = C.cast(self.layers, C.POINTER(L.LayerDesc))
         desc.w_plane_stride_unused = 0
@@ -139,6 +147,17 @@ class PackedVit:
         if n == 0:
             L.check(1)
         return n
+
+
+def token_table(pos, prefix, patch_bias, wrap=31):
+    """[tokens + wrap, D]: row j = pos[j] + (prefix[j] - patch_bias if j < num_prefix else 0), the
+    value the residual stream holds before the patch GEMM adds `A W^T + bias`
+    (models/de_vit.py:259-264); the first `wrap` rows are repeated at the end so that a 32-row
+    box starting at any row j < tokens never wraps."""
+    t = pos.clone()
+    n = prefix.shape[0]
+    t[:n] += prefix - patch_bias[None, :]
+    return torch.cat([t, t[:wrap]], 0).contiguous()
 
 
 class PackedLinear:

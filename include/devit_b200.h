@@ -125,6 +125,10 @@ typedef struct devit_gemm_args {
   const float* bias;
   const float* resid;
   int64_t ldr;
+  int32_t resid_period; /* 0: resid is [m, n].  > 0: resid is a TABLE of resid_period + 31 rows and
+                           output row r adds table row r % resid_period; rows [period, period+31)
+                           repeat rows [0, 31).  This is how pos_embed (+ cls/dist) is added by the
+                           patch GEMM without materialising it per image.  fp32 outputs only. */
   const float* rowbias;
   int64_t ld_rowbias;
   int32_t act;
@@ -352,6 +356,11 @@ typedef struct devit_vit_desc {
   const float* norm_b;
   const devit_layer_desc* layers; /* HOST pointer to depth entries */
   int64_t w_plane_stride_unused;  /* reserved, must be 0 */
+  /* Optional [tokens + 31, dim] fp32 table: row j < tokens = pos[j] + (j < num_prefix ?
+   * prefix[j] - b_patch : 0), rows [tokens, tokens + 31) repeat rows [0, 31).  When set, the
+   * patch GEMM adds it as a periodic residual (devit_gemm_args.resid_period = tokens) and
+   * devit_token_init is not launched. */
+  const float* tok_table;
 } devit_vit_desc;
 
 size_t devit_vit_workspace_bytes(const devit_vit_desc* desc, int32_t batch);

@@ -244,3 +244,19 @@ def test_gemm_tile_schedules_cover_every_tile_exactly_once():
                     assert len({x % num_n for x in u}) <= 1
                 seen += u
             assert sorted(seen) == list(range(num_units)), (num_mp, num_n, clusters, bres)
+
+
+def test_token_table_wraps_and_matches_token_assembly():
+    """packing.token_table: row j = pos[j] + (cls/dist - patch bias on the prefix rows), first 31
+    rows repeated, so that `table[j] + (patch_row W^T + bias)` is models/de_vit.py:258-264."""
+    sd = synth.dedeit_state_dict(0, with_heads=False)
+    pos = sd['pos_embed'].reshape(-1, 384)
+    prefix = torch.cat([sd['cls_token'].reshape(1, -1), sd['dist_token'].reshape(1, -1)], 0)
+    bias = sd['patch_embed.proj.bias']
+    t = packing.token_table(pos, prefix, bias)
+    assert t.shape == (198 + 31, 384) and torch.equal(t[198:], t[:31])
+    x = synth.images(1)
+    emb = O.embed_tokens(sd, x)[0]                       # reference token assembly
+    patches = O.patch_embed(sd, x)[0]                    # A W^T + bias on the patch rows
+    assert torch.allclose(t[:2] + bias, emb[:2], atol=1e-6)          # zero patch row + bias
+    assert torch.allclose(t[2:198] + patches, emb[2:], atol=1e-5)

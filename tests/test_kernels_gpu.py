@@ -300,3 +300,31 @@ def test_attention_fp32(batch, tokens, heads):
     out = L.attention(L.split_tf32(qkv), batch, tokens, heads, 0.125, precision=L.DEVIT_FP32)
     ref = _attn_ref(qkv, batch, tokens, heads, 0.125)
     assert rel(out[0] + out[1], ref) < 3e-6
+
+
+@pytest.mark.parametrize("period,m", [(198, 198 * 5), (198, 198 * 256), (65, 700), (31, 400)])
+@pytest.mark.parametrize("precision", [L.DEVIT_BF16, L.DEVIT_FP32])
+def test_gemm_periodic_residual_table(period, m, precision):
+    """resid_period: out[r] = A[r] W^T + bias + table[r % period] with the table's first 31 rows
+    repeated at its end (how the patch GEMM adds pos_embed + cls/dist), also as a LayerNorm-fold
+    producer (bf16 copy + partial row sums of the result)."""
+    n, k = 384, 768
+    a32, w32 = _mk((m, k), 71), _mk((n, k), 72, 0.05)
+    bias = _mk((n,), 73)
+    table = _mk((period, n), 74)
+    wrapped = torch.cat([table, table[:31]], 0).contiguous()
+    a, w = L.to_operand(a32, precision), L.to_operand(w32, precision)
+    ref = L.operand_to_f32(a, precision) @ L.operand_to_f32(w, precision).t() + bias + \
+        table[torch.arange(m, device="cuda") % period]
+    out = L.gemm(a, w, precision=precision, bias=bias, resid=wrapped, resid_period=period,
+                 out_kind=L.OUT_F32)
+    assert rel(out, ref) < 2e-5, rel(out, ref)
+    if precision == L.DEVIT_BF16:
+        xb = torch.zeros(m, n, device="cuda", dtype=torch.bfloat16)
+        st = torch.zeros(2 * n // 128, m, 2, device="cuda")
+        out2 = L.gemm(a, w, bias=bias, resid=wrapped, resid_period=period, out_kind=L.OUT_F32,
+                      out_bf16=xb, stats_out=st)
+        assert torch.equal(out2, out) and torch.equal(xb, out.bfloat16())
+        assert rel(st[..., 0].sum(0), out.sum(-1)) < 1e-5
+    with pytest.raises(L.DevitError):  # a period without a table
+        L.gemm(a, w, precision=precision, resid_period=period, out_kind=L.OUT_F32)

@@ -21,90 +21,114 @@ __device__ __forceinline__ float norm_px(uint32_t byte, float mean, float stdv) 
   return __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(byte), 255.0f), mean), stdv);
 }
 
+// 32-byte global store (STG.256, sm_100): one full sector per lane and instruction -- two
+// 16-byte stores at a 32-byte lane stride would each write half sectors.
+__device__ __forceinline__ void st_global_256(void* p, uint32_t a0, uint32_t a1, uint32_t a2,
+                                              uint32_t a3, uint32_t a4, uint32_t a5, uint32_t a6,
+                                              uint32_t a7) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"l"(p), "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(a4), "r"(a5), "r"(a6), "r"(a7)
+               : "memory");
+}
+__device__ __forceinline__ void st_global_256f(float* p, const float* v) {
+  st_global_256(p, __float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]),
+                __float_as_uint(v[3]), __float_as_uint(v[4]), __float_as_uint(v[5]),
+                __float_as_uint(v[6]), __float_as_uint(v[7]));
+}
+
 __device__ __forceinline__ void store16(void* a, long long o, const float (&v)[16], int out_kind,
                                         long long plane) {
   if (out_kind == DEVIT_OUT_BF16) {
-    uint4 p0, p1;
-    p0.x = pack_bf16x2(v[0], v[1]);   p0.y = pack_bf16x2(v[2], v[3]);
-    p0.z = pack_bf16x2(v[4], v[5]);   p0.w = pack_bf16x2(v[6], v[7]);
-    p1.x = pack_bf16x2(v[8], v[9]);   p1.y = pack_bf16x2(v[10], v[11]);
-    p1.z = pack_bf16x2(v[12], v[13]); p1.w = pack_bf16x2(v[14], v[15]);
-    uint4* d = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(a) + o);
-    d[0] = p0;
-    d[1] = p1;
+    st_global_256(static_cast<__nv_bfloat16*>(a) + o, pack_bf16x2(v[0], v[1]),
+                  pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]),
+                  pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]),
+                  pack_bf16x2(v[14], v[15]));
   } else if (out_kind == DEVIT_OUT_F32) {
-    float4* d = reinterpret_cast<float4*>(static_cast<float*>(a) + o);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) d[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    st_global_256f(static_cast<float*>(a) + o, v);
+    st_global_256f(static_cast<float*>(a) + o + 8, v + 8);
   } else {
-    float4* dh = reinterpret_cast<float4*>(static_cast<float*>(a) + o);
-    float4* dl = reinterpret_cast<float4*>(static_cast<float*>(a) + o + plane);
+    float h[16], l[16];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float4 f = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-      const float4 h = make_float4(tf32_hi(f.x), tf32_hi(f.y), tf32_hi(f.z), tf32_hi(f.w));
-      dh[i] = h;
-      dl[i] = make_float4(f.x - h.x, f.y - h.y, f.z - h.z, f.w - h.w);
+    for (int i = 0; i < 16; ++i) {
+      h[i] = tf32_hi(v[i]);
+      l[i] = v[i] - h[i];
     }
+    st_global_256f(static_cast<float*>(a) + o, h);
+    st_global_256f(static_cast<float*>(a) + o + 8, h + 8);
+    st_global_256f(static_cast<float*>(a) + o + plane, l);
+    st_global_256f(static_cast<float*>(a) + o + plane + 8, l + 8);
   }
 }
 
-// One thread owns one 16-pixel patch-row segment (y, x0 .. x0+15).  NCHW: one 16-byte load per
+// One item = one 16-pixel patch-row segment (y, x0 .. x0+15).  NCHW: one 16-byte load per
 // (channel, segment) item; NHWC (3 channels): three 16-byte loads hold the 48 interleaved bytes of
 // the segment and feed three 16-element output runs.  Output runs are contiguous K ranges of a
-// patch row (32 B bf16 / 64 B fp32).
+// patch row (32 B bf16 / 64 B fp32); items are numbered in OUTPUT order (image, patch, channel,
+// py), so consecutive threads write consecutive runs of the patch matrix.
+// The two IEEE divisions per pixel made a first version compute-bound (30 % of the HBM
+// roofline): a pixel can only take 256 values per channel, so every block first builds the
+// chans x 256 table of normalised values in shared memory with exactly those operations and then
+// only looks bytes up; kU8ItemsPerThread items per thread amortise the table.
+constexpr int kU8ItemsPerThread = 4;
+
 template <bool NHWC>
 __global__ void __launch_bounds__(256)
 im2col16_u8_kernel(const uint8_t* __restrict__ img, void* __restrict__ a, int batch, int chans,
                    int hw, NormParams np, int out_kind, long long plane, int row_off,
                    int rows_per_img) {
-  // threads are numbered in OUTPUT order (image, patch, channel, py): consecutive threads write
-  // consecutive 32-byte (bf16) runs of the patch matrix
+  __shared__ float lut[4 * 256];
+  for (int c = 0; c < chans; ++c) {
+    const float mu = c == 0 ? np.mean[0] : c == 1 ? np.mean[1] : c == 2 ? np.mean[2] : np.mean[3];
+    const float sd = c == 0 ? np.stdv[0] : c == 1 ? np.stdv[1] : c == 2 ? np.stdv[2] : np.stdv[3];
+    lut[c * 256 + threadIdx.x] = norm_px(threadIdx.x, mu, sd);
+  }
+  __syncthreads();
   const int g = hw >> 4;
   const int P = g * g;
   const int items_c = NHWC ? 1 : chans;
   const long long total = static_cast<long long>(batch) * P * items_c * 16;
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int py = static_cast<int>(i) & 15;
-  long long t = i >> 4;
-  const int c0 = NHWC ? 0 : static_cast<int>(t % items_c);
-  t /= items_c;
-  const int pidx = static_cast<int>(t % P);
-  const int b = static_cast<int>(t / P);
-  const int gy = pidx / g, gx = pidx - gy * g;
-  const int y = gy * 16 + py;
-  const long long m = static_cast<long long>(b) * rows_per_img + row_off + pidx;
   const long long kdim = static_cast<long long>(chans) * 256;
-  const long long o0 = m * kdim + py * 16;
-  // 16-byte units: NCHW pixel offset / 16, NHWC pixel offset * 3 / 16
-  const long long src16 = NHWC ? ((static_cast<long long>(b) * hw + y) * g + gx) * 3
-                               : ((static_cast<long long>(b) * chans + c0) * hw + y) * g + gx;
-  float v[16];
-  if (!NHWC) {
-    const uint4 w = __ldg(reinterpret_cast<const uint4*>(img) + src16);
-    const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
-    // select chain instead of a dynamic index into the parameter struct (no local copy)
-    const float mu = c0 == 0 ? np.mean[0] : c0 == 1 ? np.mean[1] : c0 == 2 ? np.mean[2] : np.mean[3];
-    const float sd = c0 == 0 ? np.stdv[0] : c0 == 1 ? np.stdv[1] : c0 == 2 ? np.stdv[2] : np.stdv[3];
+#pragma unroll 1
+  for (int it = 0; it < kU8ItemsPerThread; ++it) {
+    const long long i = (static_cast<long long>(blockIdx.x) * kU8ItemsPerThread + it) * 256 +
+                        threadIdx.x;
+    if (i >= total) return;
+    const int py = static_cast<int>(i) & 15;
+    long long t = i >> 4;
+    const int c0 = NHWC ? 0 : static_cast<int>(t % items_c);
+    t /= items_c;
+    const int pidx = static_cast<int>(t % P);
+    const int b = static_cast<int>(t / P);
+    const int gy = pidx / g, gx = pidx - gy * g;
+    const int y = gy * 16 + py;
+    const long long m = static_cast<long long>(b) * rows_per_img + row_off + pidx;
+    const long long o0 = m * kdim + py * 16;
+    // 16-byte units: NCHW pixel offset / 16, NHWC pixel offset * 3 / 16
+    const long long src16 = NHWC ? ((static_cast<long long>(b) * hw + y) * g + gx) * 3
+                                 : ((static_cast<long long>(b) * chans + c0) * hw + y) * g + gx;
+    float v[16];
+    if (!NHWC) {
+      const uint4 w = __ldg(reinterpret_cast<const uint4*>(img) + src16);
+      const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+      const float* tab = lut + c0 * 256;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = norm_px((ws[j >> 2] >> (8 * (j & 3))) & 0xffu, mu, sd);
-    store16(a, o0 + static_cast<long long>(c0) * 256, v, out_kind, plane);
-  } else {
-    // 48 bytes: pixel p, channel c at byte 3 p + c
-    const uint4* src = reinterpret_cast<const uint4*>(img) + src16;
-    const uint4 w0 = __ldg(src), w1 = __ldg(src + 1), w2 = __ldg(src + 2);
-    const uint32_t ws[12] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w,
-                             w2.x, w2.y, w2.z, w2.w};
+      for (int j = 0; j < 16; ++j) v[j] = tab[(ws[j >> 2] >> (8 * (j & 3))) & 0xffu];
+      store16(a, o0 + static_cast<long long>(c0) * 256, v, out_kind, plane);
+    } else {
+      // 48 bytes: pixel p, channel c at byte 3 p + c
+      const uint4* src = reinterpret_cast<const uint4*>(img) + src16;
+      const uint4 w0 = __ldg(src), w1 = __ldg(src + 1), w2 = __ldg(src + 2);
+      const uint32_t ws[12] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w,
+                               w2.x, w2.y, w2.z, w2.w};
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const float mu = np.mean[c], sd = np.stdv[c];
+      for (int c = 0; c < 3; ++c) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int byte = 3 * j + c;
-        v[j] = norm_px((ws[byte >> 2] >> (8 * (byte & 3))) & 0xffu, mu, sd);
+        for (int j = 0; j < 16; ++j) {
+          const int byte = 3 * j + c;
+          v[j] = lut[c * 256 + ((ws[byte >> 2] >> (8 * (byte & 3))) & 0xffu)];
+        }
+        store16(a, o0 + static_cast<long long>(c) * 256, v, out_kind, plane);
       }
-      store16(a, o0 + static_cast<long long>(c) * 256, v, out_kind, plane);
     }
   }
 }
@@ -223,8 +247,11 @@ extern "C" int devit_im2col_tokens_u8(const uint8_t* images, int32_t layout, con
   DEVIT_REQUIRE(layout == DEVIT_LAYOUT_NCHW || chans == 3,
                 "devit_im2col_tokens_u8: the NHWC layout is implemented for 3 channels");
   DEVIT_REQUIRE(out_kind >= 0 && out_kind <= 2, "devit_im2col_tokens_u8: bad out_kind %d", out_kind);
-  DEVIT_REQUIRE(reinterpret_cast<uintptr_t>(images) % 16 == 0,
-                "devit_im2col_tokens_u8: images must be 16-byte aligned");
+  DEVIT_REQUIRE(reinterpret_cast<uintptr_t>(images) % 16 == 0 &&
+                    reinterpret_cast<uintptr_t>(a) % 32 == 0 &&
+                    (out_kind != DEVIT_OUT_F32_SPLIT || (out_plane_stride * 4) % 32 == 0),
+                "devit_im2col_tokens_u8: images must be 16-byte, the patch matrix (and its plane "
+                "stride) 32-byte aligned");
   NormParams np;
   for (int c = 0; c < 4; ++c) {
     np.mean[c] = c < chans ? mean[c] : 0.f;
@@ -236,7 +263,8 @@ extern "C" int devit_im2col_tokens_u8(const uint8_t* images, int32_t layout, con
   const size_t k = static_cast<size_t>(chans) * 256;
   const bool nhwc = layout == DEVIT_LAYOUT_NHWC;
   const long long total = static_cast<long long>(batch) * (nhwc ? 1 : chans) * hw * (hw / 16);
-  const unsigned grid = static_cast<unsigned>((total + 255) / 256);
+  const long long per_block = 256LL * kU8ItemsPerThread;
+  const unsigned grid = static_cast<unsigned>((total + per_block - 1) / per_block);
   {
     ProfScope ps(kTagIm2col, stream);
     if (num_prefix > 0) {  // zero rows for the cls / dist tokens of every image

@@ -92,6 +92,10 @@ class VitDesc(C.Structure):
     ]
 
 
+class VitExports(C.Structure):
+    _fields_ = [("qkv", C.c_void_p * 32)]
+
+
 class CctDesc(C.Structure):
     _fields_ = [
         ("precision", C.c_int32), ("dim", C.c_int32), ("depth", C.c_int32),
@@ -137,6 +141,10 @@ _SIGS = {
     "devit_vit_forward_patches": (C.c_int, [C.POINTER(VitDesc), C.c_void_p, C.c_int64, C.c_int32,
                                             C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
                                             C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),
+    "devit_vit_forward_ex": (C.c_int, [C.POINTER(VitDesc), C.c_void_p, C.c_void_p, C.c_int64,
+                                       C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                                       C.c_int64, C.c_void_p, C.c_int32, C.POINTER(VitExports),
+                                       C.c_void_p]),
     "devit_cct_workspace_bytes": (C.c_size_t, [C.POINTER(CctDesc), C.c_int32]),
     "devit_cct_forward": (C.c_int, [C.POINTER(CctDesc), C.c_void_p, C.c_int32, C.c_void_p,
                                     C.c_size_t, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),

@@ -108,6 +108,7 @@ struct BlockBuffers {
   void* o;
   void* hid;
   float* stats;
+  void* const* qkv_export = nullptr;  // per layer: caller buffer that receives q/k/v (or NULL)
 };
 
 static int run_blocks(const devit_layer_desc* layers, int nl, int prec, int D, float ln_eps,
@@ -127,9 +128,13 @@ static int run_blocks(const devit_layer_desc* layers, int nl, int prec, int D, f
     const char* e = getenv("DEVIT_FUSED_MLP");
     fused_mlp = (e && e[0] == '0') ? 0 : 1;
   }
+  void* const qkv_ws = qkv;
   for (int l = 0; l < nl; ++l) {
     const devit_layer_desc& w = layers[l];
     const int hd = w.heads * 64;
+    // an exported layer's QKV GEMM writes straight into the caller's buffer and the attention
+    // kernel reads it from there: the export costs no copy
+    qkv = (bufs.qkv_export && bufs.qkv_export[l]) ? bufs.qkv_export[l] : qkv_ws;
     // x -> LN1 -> y                                              (models/de_vit.py:113)
     if (!fold) {
       rc = devit_layernorm(x, w.ln1_g, w.ln1_b, y, M, D, ln_eps, opk, M * D, stream);
@@ -238,7 +243,7 @@ static int vit_forward_impl(const devit_vit_desc* d, const float* images, const 
                             int64_t patches_plane_stride, int32_t batch, void* workspace,
                             size_t workspace_bytes, float* feats_f32, void* feats_op,
                             int64_t feats_op_plane_stride, float* x_out, int32_t num_layers_run,
-                            void* stream) {
+                            void* stream, const devit_vit_exports* exports = nullptr) {
   int rc = check_device();
   if (rc) return rc;
   VitLayout L{};
@@ -323,6 +328,14 @@ static int vit_forward_impl(const devit_vit_desc* d, const float* images, const 
   // QKV / fc1 GEMMs consume both and apply mean / rstd in their epilogue.
   {
     BlockBuffers bufs{x, y, qkv, o, hid, stats};
+    if (exports) {
+      DEVIT_REQUIRE(d->depth <= DEVIT_MAX_DEPTH, "devit_vit_forward_ex: depth %d > %d", d->depth,
+                    DEVIT_MAX_DEPTH);
+      for (int l = 0; l < nl; ++l)
+        DEVIT_REQUIRE(reinterpret_cast<uintptr_t>(exports->qkv[l]) % 256 == 0,
+                      "devit_vit_forward_ex: qkv export buffers must be 256-byte aligned");
+      bufs.qkv_export = exports->qkv;
+    }
     rc = run_blocks(d->layers, nl, prec, D, d->ln_eps, batch, L.tokens, M, bufs, fold, parts,
                     L.stat_parts, stream);
     if (rc) return rc;
@@ -362,6 +375,22 @@ extern "C" int devit_vit_forward_patches(const devit_vit_desc* d, const void* pa
   return vit_forward_impl(d, nullptr, patches, patches_plane_stride, batch, workspace,
                           workspace_bytes, feats_f32, feats_op, feats_op_plane_stride, x_out,
                           num_layers_run, stream);
+}
+
+extern "C" int devit_vit_forward_ex(const devit_vit_desc* d, const float* images,
+                                    const void* patches, int64_t patches_plane_stride,
+                                    int32_t batch, void* workspace, size_t workspace_bytes,
+                                    float* feats_f32, void* feats_op,
+                                    int64_t feats_op_plane_stride, float* x_out,
+                                    int32_t num_layers_run, const devit_vit_exports* exports,
+                                    void* stream) {
+  DEVIT_REQUIRE((images != nullptr) != (patches != nullptr),
+                "devit_vit_forward_ex: pass exactly one of images / patches");
+  DEVIT_REQUIRE(!patches || reinterpret_cast<uintptr_t>(patches) % 16 == 0,
+                "devit_vit_forward_ex: patches must be 16-byte aligned");
+  return vit_forward_impl(d, images, patches, patches_plane_stride, batch, workspace,
+                          workspace_bytes, feats_f32, feats_op, feats_op_plane_stride, x_out,
+                          num_layers_run, stream, exports);
 }
 
 // ------------------------------------------------------------------------------- CCT

@@ -283,6 +283,7 @@ class VisionTransformer(nn.Module):
 
         self.precision = default_precision()
         self.input_norm = (IMAGENET_DEFAULT_MEAN, IMAGENET_DEFAULT_STD)
+        self.export_qkv_layers = None  # layers whose q/k/v output_qkv=True keeps (None = all)
         self._packs = {}
         self._observers_stale = False
         self._last_input = None
@@ -431,8 +432,62 @@ class VisionTransformer(nn.Module):
                 return (tokens, [], [], [])
             return {'output': tokens, 'qkv': [None] * depth, 'attention': [None] * depth,
                     'encoder': [None] * depth}
+        if output_qkv and not (output_att or output_emb or output_encoders) and \
+                self.resize_dim is None and x.is_cuda and self._all_heads_kept(x.device):
+            return self._forward_features_qkv_export(x)
         return self._forward_features_layerwise(x, output_qkv, output_att, output_emb,
                                                 output_encoders)
+
+    # ------------------------------------------------------------------ fused path + q/k/v export
+    def _all_heads_kept(self, device):
+        pk = self.packed(device)
+        return all(int(k.numel()) == blk.attn.num_heads
+                   for k, blk in zip(pk.kept_heads, self.blocks))
+
+    def _forward_features_qkv_export(self, x):
+        """output_qkv=True on the FUSED path: every selected layer's QKV
+        GEMM writes into an export buffer that the attention kernel reads back, so the per-layer
+        (q, k, v) tuples the training-side consumers read (the teacher's q/k/v in
+        feature_relation_loss, engine.py:70-95) come out of the same 10 ms forward instead of the
+        layer-wise path.  `export_qkv_layers` (None = all layers) limits which layers are kept;
+        the others are None.  Used when no head is gated off (q/k/v of gated heads do not exist
+        in a compacted model).  q, k, v: [B, H, N, hd] views like the reference's
+        (models/de_vit.py:67-68), bf16 in the bf16 mode, fp32 (hi + lo) in the fp32 mode."""
+        x = self._check_input(x)
+        B = x.shape[0]
+        pk = self.packed(x.device)
+        depth = len(self.blocks)
+        H = self.blocks[0].attn.num_heads
+        prec = _PREC[self.precision]
+        want = range(depth) if self.export_qkv_layers is None else \
+            sorted({int(l) % depth for l in self.export_qkv_layers})
+        ex = L.VitExports()
+        bufs = {}
+        for l in want:
+            shape = (B * pk.tokens, 3 * H * 64)
+            bufs[l] = torch.empty(shape, device=x.device, dtype=torch.bfloat16) \
+                if prec == L.DEVIT_BF16 else torch.empty((2,) + shape, device=x.device)
+            ex.qkv[l] = bufs[l].data_ptr()
+        f32, _ = self._feature_slabs(B, x.device)
+        patches = self.patches_of(x) if x.dtype == torch.uint8 else None
+        ws = packing.workspace(x.device, pk.workspace_bytes(B))
+        L.check(L.load().devit_vit_forward_ex(
+            C.byref(pk.desc), None if patches is not None else x.data_ptr(),
+            None if patches is None else patches.data_ptr(),
+            patches.stride(0) if (patches is not None and patches.dim() == 3) else 0,
+            B, ws.data_ptr(), ws.numel(), L.ptr(f32), None, 0, None, -1, C.byref(ex),
+            L.stream_ptr()))
+        self._last_input, self._observers_stale = x, True
+        qkvs = [None] * depth
+        for l, t in bufs.items():
+            t = t if prec == L.DEVIT_BF16 else t[0] + t[1]
+            q, k, v = t.view(B, pk.tokens, 3, H, 64).permute(2, 0, 3, 1, 4).unbind(0)
+            qkvs[l] = (q, k, v)
+        tokens = self._pre_logits(f32[0]) if self.dist_token is None else (f32[0], f32[1])
+        if self.tuple_api:  # models/deit_vit.py:232-240: one entry per layer when asked for
+            return (tokens, qkvs, [], [])
+        return {'output': tokens, 'qkv': qkvs, 'attention': [None] * depth,
+                'encoder': [None] * depth}
 
     def _pre_logits(self, t):
         if isinstance(self.pre_logits, nn.Identity):

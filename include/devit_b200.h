@@ -384,6 +384,27 @@ int devit_vit_forward_patches(const devit_vit_desc* desc, const void* patches,
                               int64_t feats_op_plane_stride, float* x_out, int32_t num_layers_run,
                               void* stream);
 
+/* Same as devit_vit_forward / devit_vit_forward_patches (pass exactly one of `images` /
+ * `patches`) with per-layer exports for the training-side consumers of this forward
+ * (VisionTransformer.forward(..., output_qkv=True), models/de_vit.py:268-284; the teacher's
+ * q/k/v feed feature_relation_loss, engine.py:70-95, utils/losses.py:307-327):
+ * exports->qkv[l] (or NULL) receives layer l's QKV Linear output [batch * tokens, 3 * heads_l * 64]
+ * in the descriptor's operand format, column (which * heads_l + h) * 64 + d (the reference's
+ * reshape(B, N, 3, H, hd), models/de_vit.py:67) -- bf16, or fp32 hi plane followed by the lo
+ * plane at + batch * tokens * 3 * heads_l * 64 elements.  The GEMM writes there directly and the
+ * attention kernel reads it back, so an export costs no copy.  Only KEPT heads exist in a
+ * compacted sub-model; the host uses this path when no head is gated off. */
+#define DEVIT_MAX_DEPTH 32
+typedef struct devit_vit_exports {
+  void* qkv[DEVIT_MAX_DEPTH];
+} devit_vit_exports;
+
+int devit_vit_forward_ex(const devit_vit_desc* desc, const float* images, const void* patches,
+                         int64_t patches_plane_stride, int32_t batch, void* workspace,
+                         size_t workspace_bytes, float* feats_f32, void* feats_op,
+                         int64_t feats_op_plane_stride, float* x_out, int32_t num_layers_run,
+                         const devit_vit_exports* exports, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * CCT (Compact Convolutional Transformer) sub-models: models/cct.py:138-157 +
  * models/utils/tokenizer.py:23-44 + models/utils/transformers.py:104-113, :441-477.

@@ -274,3 +274,61 @@ def test_full_size_batch_is_image_independent(precision):
     c = out[0].view(bsz // B, B, 384)
     assert rel(c[0], G['shrunk_cls'][0]) < TOL[precision]
     assert torch.equal(c, c[:1].expand_as(c)), "copies of the same image must agree bit-for-bit"
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_output_qkv_on_the_fused_path(precision):
+    """output_qkv=True with no head gated off runs the fused forward with per-layer q/k/v exports
+    (devit_vit_forward_ex): same logits as the plain forward bit for bit, q/k/v equal to the
+    layer-wise path's and to the oracle's, uint8 input included; gated heads fall back."""
+    sd = synth.dedeit_state_dict(0)
+    m = make_sub(0, precision)
+    x = synth.images(2)
+    tol = TOL[precision]
+    with torch.no_grad():
+        xe = O.embed_tokens(sd, x)
+        ln = torch.nn.functional.layer_norm(xe, (384,), sd['blocks.0.norm1.weight'],
+                                            sd['blocks.0.norm1.bias'], 1e-6)
+        _, _, (q, k, v) = O.attention(sd, 'blocks.0.attn.', ln, 6, None, True)
+        feats, blocks = O.forward_features(sd, x, 6, None, None, return_blocks=True)
+        ln5 = torch.nn.functional.layer_norm(blocks[5], (384,), sd['blocks.5.norm1.weight'],
+                                             sd['blocks.5.norm1.bias'], 1e-6)
+        _, _, (q5, k5, v5) = O.attention(sd, 'blocks.5.attn.', ln5, 6, None, True)
+    before = L.load().devit_launch_count()
+    out = m(x.cuda(), output_qkv=True)
+    fused_launches = L.load().devit_launch_count() - before
+    assert rel(out['output'], m(x.cuda())) < 1e-6
+    assert len(out['qkv']) == 12 and all(t is not None for t in out['qkv'])
+    gq, gk, gv = out['qkv'][0]
+    assert gq.shape == (2, 6, 198, 64)
+    assert rel(gq, q) < tol and rel(gk, k) < tol and rel(gv, v) < tol
+    g5 = out['qkv'][5]
+    assert rel(g5[0], q5) < tol and rel(g5[1], k5) < tol and rel(g5[2], v5) < tol
+    # the layer-wise path (any other flag) gives the same tensors within the mode's rounding
+    before = L.load().devit_launch_count()
+    lw = m(x.cuda(), output_qkv=True, output_att=True)
+    assert L.load().devit_launch_count() - before > fused_launches
+    assert rel(lw['qkv'][5][2], g5[2].float()) < tol
+    # selected layers only
+    m.export_qkv_layers = [5]
+    sel = m(x.cuda(), output_qkv=True)['qkv']
+    assert [t is not None for t in sel] == [i == 5 for i in range(12)]
+    assert torch.equal(sel[5][1], g5[1])
+    m.export_qkv_layers = None
+    # a gated head -> layer-wise path (dense q/k/v like the reference)
+    gates = synth.shrink_gates(0)
+    mg = make_sub(0, precision, gates)
+    og = mg(x.cuda(), output_qkv=True)
+    assert og['qkv'][0][0].shape == (2, 6, 198, 64) and rel(og['qkv'][0][0], q) < tol
+
+
+def test_teacher_output_qkv_fused_tuple_api():
+    t = create_model('deit_base_distilled_patch16_224', num_classes=100)
+    t.load_state_dict(synth.teacher_state_dict())
+    t = t.cuda().eval().set_precision('bf16')
+    x = synth.images(2).cuda()
+    feats, qkvs, att, enc = t.forward_features(x, output_qkv=True)
+    assert len(qkvs) == 12 and att == [] and enc == []
+    assert qkvs[5][0].shape == (2, 12, 198, 64) and qkvs[5][0].dtype == torch.bfloat16
+    lw = t.forward_features(x, output_qkv=True, output_att=True)[1]
+    assert rel(qkvs[5][0], lw[5][0]) < 2e-2 and rel(qkvs[11][2], lw[11][2]) < 2e-2

@@ -108,7 +108,7 @@ class CctDesc(C.Structure):
     ]
 
 
-# name -> (restype, argtypes); this table is also what tests/test_abi.py checks against the header
+# name -> (restype, argtypes); this table is also what tests/test_host_cpu.py checks against the header
 _SIGS = {
     "devit_abi_version": (C.c_int, []),
     "devit_last_error": (C.c_char_p, []),

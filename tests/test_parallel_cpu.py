@@ -79,3 +79,42 @@ def test_gloo_gather_matches_stack_order(world, n_sub):
         p.join(120)
         assert p.exitcode == 0
     assert ret.get(timeout=10) == 1
+
+
+def _meters_worker(rank, world, port, ret):
+    """Each rank evaluates its own shard of the batches (the reference's DistributedSampler
+    split); the all-reduced meters must equal the single-process result over all batches
+    (utils/dist_utils.py:35-46: count and total are summed over ranks)."""
+    from devit_b200 import engine, synth
+    from oracle import devit_oracle as O
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        batches = synth.eval_batches((8, 8, 5, 3), 100)
+        meters = engine.EvalMeters(torch.device('cpu'))
+        for lg, tg in batches[rank::world]:           # host stand-in for devit_eval_tail
+            loss, c1, ck = O.eval_tail(lg, tg)
+            meters.acc += torch.tensor([loss, 1, c1, ck, lg.shape[0]], dtype=torch.float64)
+        meters.synchronize_between_processes()
+        got = meters.result()
+        want = O.eval_epoch(batches)
+        ok = all(abs(got[k] - want[k]) <= 1e-9 * max(1.0, abs(want[k])) for k in want)
+        flag = torch.tensor([1 if ok else 0])
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            ret.put(int(flag.item()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_eval_meters_reduce_like_metric_logger():
+    ctx = mp.get_context('spawn')
+    ret = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_meters_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert ret.get(timeout=10) == 1

@@ -65,7 +65,8 @@ def shard_plan(world: int, rank: int, n_sub: int, batch: int) -> ShardPlan:
 
 def make_groups(plan: ShardPlan):
     """Creates every model-parallel process group (collective over all ranks) and returns the
-    one this rank belongs to (None when a group is a single rank)."""
+    one this rank belongs to (None when a group is a single rank).  Call it twice to get a
+    second, independent communicator over the same ranks (ShardedEnsemble.stage_group)."""
     mine = None
     if plan.group_size == 1:
         return None
@@ -88,13 +89,48 @@ def gather_blocks(local: torch.Tensor, plan: ShardPlan, group) -> torch.Tensor:
     return out.view((plan.group_size,) + tuple(local.shape))
 
 
+def stage_slice(plan: ShardPlan, rows: int):
+    """(lo, hi) rows of a group batch of `rows` images that model rank `plan.model_rank` uploads
+    in `ShardedEnsemble.stage_batch`; None when the batch does not split evenly."""
+    g = plan.group_size
+    if g <= 1 or rows % g:
+        return None
+    per = rows // g
+    return plan.model_rank * per, (plan.model_rank + 1) * per
+
+
 class ShardedEnsemble:
     """MultiViT + EnsMLP across the ranks of a ShardPlan.  `multi` holds (at least) this rank's
     sub-models; `fuse` is replicated on every rank."""
 
-    def __init__(self, multi, fuse, plan: ShardPlan, group=None):
+    def __init__(self, multi, fuse, plan: ShardPlan, group=None, stage_group=None):
         self.multi, self.fuse, self.plan, self.group = multi, fuse, plan, group
         self.order = plan.gathered_order()
+        # a second communicator over the same ranks for the input exchange, so that the upload
+        # of batch i+1 never queues in front of the feature all-gather of batch i
+        self.stage_group = stage_group
+        self._stage_buf = None
+
+    @torch.no_grad()
+    def stage_batch(self, host_batch: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+        """Brings the group's batch from (pinned) HOST memory into `out` on this rank's GPU.
+        Every sub-model consumes the same images (models/ensemble_models.py:33), so instead of
+        all G model ranks pulling the whole batch over PCIe, rank r uploads rows
+        [r B/G, (r+1) B/G) and one all-gather over NVLink assembles the batch on every rank:
+        1/G of the host->device bytes per rank.  Runs on the current stream; falls back to a plain
+        full copy for a single rank or an uneven split.  Returns `out`."""
+        sl = stage_slice(self.plan, host_batch.shape[0])
+        if sl is None or self.stage_group is None:
+            out.copy_(host_batch, non_blocking=True)
+            return out
+        lo, hi = sl
+        shape = (hi - lo,) + tuple(host_batch.shape[1:])
+        if self._stage_buf is None or self._stage_buf.shape != shape or \
+                self._stage_buf.dtype != host_batch.dtype or self._stage_buf.device != out.device:
+            self._stage_buf = torch.empty(shape, dtype=host_batch.dtype, device=out.device)
+        self._stage_buf.copy_(host_batch[lo:hi], non_blocking=True)
+        dist.all_gather_into_tensor(out, self._stage_buf, group=self.stage_group)
+        return out
 
     @torch.no_grad()
     def __call__(self, x_group: torch.Tensor) -> torch.Tensor:

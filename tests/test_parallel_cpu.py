@@ -118,3 +118,57 @@ def test_gloo_eval_meters_reduce_like_metric_logger():
         p.join(120)
         assert p.exitcode == 0
     assert ret.get(timeout=10) == 1
+
+
+def _stage_worker(rank, world, port, n_sub, batch, ret):
+    """stage_batch: every rank uploads 1/G of its group's batch and the all-gather over the
+    second communicator rebuilds the whole group batch on every rank (uint8 and fp32)."""
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        plan = parallel.shard_plan(world, rank, n_sub, batch)
+        group = parallel.make_groups(plan)
+        stage_group = parallel.make_groups(plan)
+        ens = parallel.ShardedEnsemble(None, None, plan, group, stage_group)
+        gen = torch.Generator().manual_seed(11)
+        full = torch.randn(batch, 3, 4, 4, generator=gen)
+        full8 = torch.randint(0, 256, (batch, 4, 4, 3), generator=gen, dtype=torch.uint8)
+        ok = True
+        for src in (full, full8):
+            host = src[plan.batch_lo:plan.batch_hi].contiguous()
+            out = torch.zeros_like(host)
+            ens.stage_batch(host, out)
+            ok = ok and torch.equal(out, host)
+        # an uneven split falls back to the plain copy
+        odd = full[:plan.group_size + 1].contiguous()
+        ok = ok and parallel.stage_slice(plan, odd.shape[0]) is None
+        ok = ok and torch.equal(ens.stage_batch(odd, torch.zeros_like(odd)), odd)
+        flag = torch.tensor([1 if ok else 0])
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            ret.put(int(flag.item()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world,n_sub,batch', [(2, 4, 8), (4, 2, 8)])
+def test_gloo_stage_batch_rebuilds_the_group_batch(world, n_sub, batch):
+    ctx = mp.get_context('spawn')
+    ret = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_stage_worker, args=(r, world, port, n_sub, batch, ret))
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert ret.get(timeout=10) == 1
+
+
+def test_stage_slice():
+    p = parallel.shard_plan(4, 2, 4, 256)
+    assert parallel.stage_slice(p, 256) == (128, 192) and parallel.stage_slice(p, 255) is None
+    assert parallel.stage_slice(parallel.shard_plan(1, 0, 4, 256), 256) is None
+    p = parallel.shard_plan(8, 5, 4, 256)          # 2 data-parallel groups of 4 model ranks
+    assert p.group_batch == 128 and parallel.stage_slice(p, 128) == (32, 64)

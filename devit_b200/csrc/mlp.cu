@@ -72,7 +72,8 @@ extern long long* g_attn_trace;  // devit_debug_set_trace buffer (shared)
 
 struct MlpParams {
   long long* trace;
-  int stagger;  // clocks by which every other cluster delays its first tile (see the kernel)
+  int stagger;  // clocks by which some clusters delay their first tile (see the kernel)
+  int stagger_mode;  // 0: every other cluster; 1: only the clusters with a tile less than the rest
   int M, F_ld, num_chunks;
   const float* c1;
   const float* c2;
@@ -170,7 +171,15 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
   // with an HBM-bound one (final epilogue + refill: ~0.6 MB per CTA).  Started together, all
   // 148 SMs stream at the same time and compute at the same time; delaying every other cluster
   // by about half a tile lets one half compute while the other half owns the HBM.
-  if (p.stagger > 0 && (cluster_id & 1)) {
+  // Mode 1 (DEVIT_MLP_STAGGER_MODE=1, not yet measured): delay only the clusters that own one
+  // tile fewer than the busiest ones -- they have a whole tile time of slack, so the delay is free
+  // for the kernel's end time (198 pair-tiles over 74 clusters: 24 such clusters; 99 tiles at
+  // N = 8: 49).
+  const bool delayed = p.stagger_mode == 1
+      ? (num_pairs > num_clusters && cluster_id >= num_pairs % num_clusters &&
+         num_pairs % num_clusters != 0)
+      : (cluster_id & 1) != 0;
+  if (p.stagger > 0 && delayed) {
     const long long t0 = clock64();
     while (clock64() - t0 < p.stagger) __nanosleep(500);
   }
@@ -569,6 +578,8 @@ extern "C" int devit_mlp_fused(const devit_mlp_args* a, void* stream_v) {
       stagger = e ? atoi(e) : 10000;  // measured best of {0, 10k, 18k, 26k}: -1.5 .. -3.5 %
     }
     p.stagger = stagger;
+    static int mode_cache = kEnvUnread;
+    p.stagger_mode = env_int("DEVIT_MLP_STAGGER_MODE", 0, &mode_cache);
   }
   const int num_pairs = (a->m + 255) / 256;
   int clusters = num_sms() / 2;

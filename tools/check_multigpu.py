@@ -1,6 +1,7 @@
 """N-rank sharded ensemble vs the same ensemble on one GPU (run under torchrun, 1 rank per GPU):
 logits of every data-parallel group must equal the single-GPU logits of that batch slice
-(same kernels, fixed K-segment order in the fusion head -> bit-identical), argmax included.
+(same kernels, fixed K-segment order in the fusion head -> bit-identical), argmax included; the
+staged host batch (ShardedEnsemble.stage_batch) must equal the plain device copy.
    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/check_multigpu.py
 """
 import os
@@ -49,6 +50,13 @@ def main():
         single_plan = parallel.shard_plan(1, 0, N_SUB, B)
         single = parallel.ShardedEnsemble(multi, fuse, single_plan, None)(xs)
         same = torch.equal(sharded, single)
+        # host batch staged as 1/G per rank + NVLink all-gather must rebuild xs exactly
+        stage_group = parallel.make_groups(plan)
+        ens = parallel.ShardedEnsemble(multi, fuse, plan, group, stage_group)
+        host = x[plan.batch_lo:plan.batch_hi].contiguous().pin_memory()
+        staged = ens.stage_batch(host, torch.empty_like(xs))
+        torch.cuda.synchronize()
+        same = same and torch.equal(staged, xs)
         amax = torch.equal(sharded.argmax(-1), single.argmax(-1))
         err = ((sharded.float() - single.float()).abs().max() / single.float().abs().max()).item()
         flag = torch.tensor([int(same), int(amax)], device=dev)

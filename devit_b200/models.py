@@ -35,7 +35,7 @@ IMAGENET_DEFAULT_MEAN = (0.485, 0.456, 0.406)
 IMAGENET_DEFAULT_STD = (0.229, 0.224, 0.225)
 
 
-def u8_layout(x, side=None):
+def u8_layout(x):
     """DEVIT layout id of a 4-d uint8 image batch: [B,C,H,W] (C <= 4) or [B,H,W,3]."""
     if x.dim() != 4:
         raise L.DevitError("uint8 image batches must be 4-d ([B,C,H,W] or [B,H,W,3])")
@@ -359,7 +359,7 @@ class VisionTransformer(nn.Module):
                                "(dropout / drop-path are not implemented)")
         H = self.patch_embed.img_size[0]
         if x.dtype == torch.uint8:
-            nhwc = u8_layout(x, H) == L.LAYOUT_NHWC
+            nhwc = u8_layout(x) == L.LAYOUT_NHWC
             h, w = (x.shape[1], x.shape[2]) if nhwc else (x.shape[2], x.shape[3])
         else:
             h, w = x.shape[2], x.shape[3]
@@ -373,9 +373,8 @@ class VisionTransformer(nn.Module):
         they are, uint8 images ([B,C,H,W] or [B,H,W,3]) normalised on the device."""
         prec = _PREC[self.precision]
         if x.dtype == torch.uint8:
-            H = self.patch_embed.img_size[0]
             mean, std = self.input_norm
-            return L.im2col_tokens_u8(x, mean, std, self.num_tokens, prec, u8_layout(x, H))
+            return L.im2col_tokens_u8(x, mean, std, self.num_tokens, prec, u8_layout(x))
         return L.im2col_tokens(x.float().contiguous(), self.num_tokens, prec)
 
     @torch.no_grad()

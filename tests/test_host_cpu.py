@@ -260,3 +260,14 @@ def test_token_table_wraps_and_matches_token_assembly():
     patches = O.patch_embed(sd, x)[0]                    # A W^T + bias on the patch rows
     assert torch.allclose(t[:2] + bias, emb[:2], atol=1e-6)          # zero patch row + bias
     assert torch.allclose(t[2:198] + patches, emb[2:], atol=1e-5)
+
+
+def test_u8_layout_detection():
+    z = lambda *s: torch.zeros(*s, dtype=torch.uint8)  # noqa: E731
+    assert models.u8_layout(z(2, 3, 224, 224)) == L.LAYOUT_NCHW
+    assert models.u8_layout(z(2, 1, 32, 32)) == L.LAYOUT_NCHW
+    assert models.u8_layout(z(2, 224, 224, 3)) == L.LAYOUT_NHWC
+    assert models.u8_layout(z(2, 32, 32, 3)) == L.LAYOUT_NHWC
+    for bad in (z(3, 224, 224), z(2, 224, 224, 4), z(2, 5, 32, 32)):
+        with pytest.raises(L.DevitError):
+            models.u8_layout(bad)

@@ -271,3 +271,15 @@ def test_u8_layout_detection():
     for bad in (z(3, 224, 224), z(2, 224, 224, 4), z(2, 5, 32, 32)):
         with pytest.raises(L.DevitError):
             models.u8_layout(bad)
+
+
+def test_engine_has_no_cpu_fallback():
+    from devit_b200 import engine
+    m = create_model('dedeit', num_classes=10).eval()
+    loader = [(torch.zeros(1, 3, 224, 224), torch.zeros(1, dtype=torch.int64))]
+    with pytest.raises(L.DevitError):
+        engine.evaluate(loader, m, torch.device('cpu'))
+    with pytest.raises(L.DevitError):
+        L.eval_tail(torch.zeros(2, 10), torch.zeros(2, dtype=torch.int64))
+    with pytest.raises(L.DevitError):
+        L.im2col_tokens_u8(torch.zeros(1, 3, 32, 32, dtype=torch.uint8), (0.5,) * 3, (0.5,) * 3, 0)

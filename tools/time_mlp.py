@@ -1,10 +1,12 @@
-"""Times devit_mlp_fused at the bs-256 shape: python tools/time_mlp.py [hidden ...]"""
+"""Times devit_mlp_fused at the bs-256 shape (TIME_MLP_BATCH=<images> for another batch):
+   python tools/time_mlp.py [hidden ...]"""
+import os
 import sys
 from pathlib import Path
 import torch
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 from devit_b200 import _lib as L  # noqa: E402
-M, D = 256 * 198, 384
+M, D = int(os.environ.get('TIME_MLP_BATCH', '256')) * 198, 384
 g = torch.Generator(device="cuda").manual_seed(0)
 for F in [int(a) for a in sys.argv[1:]] or [928, 1536]:
     x = torch.randn(M, D, device="cuda", generator=g)

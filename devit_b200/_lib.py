@@ -16,7 +16,7 @@ import torch
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "lib" / "libdevit_b200.so"
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 DEVIT_BF16, DEVIT_FP32 = 0, 1
 OUT_BF16, OUT_F32, OUT_F32_SPLIT = 0, 1, 2
 ACT_NONE, ACT_GELU_ERF, ACT_RELU = 0, 1, 2
@@ -93,7 +93,7 @@ class VitDesc(C.Structure):
 
 
 class VitExports(C.Structure):
-    _fields_ = [("qkv", C.c_void_p * 32)]
+    _fields_ = [("qkv", C.c_void_p * 32), ("feats_kind_rows", C.c_int32)]
 
 
 class CctDesc(C.Structure):
@@ -114,6 +114,7 @@ _SIGS = {
     "devit_last_error": (C.c_char_p, []),
     "devit_device_check": (C.c_int, []),
     "devit_launch_count": (C.c_longlong, []),
+    "devit_set_sm_budget": (C.c_int, [C.c_int]),
     "devit_profile_enable": (C.c_int, [C.c_int]),
     "devit_profile_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "devit_gemm": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
@@ -159,7 +160,7 @@ _SIGS = {
                                      C.c_int32, C.c_int32, C.c_void_p]),
     "devit_gather_ln": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
-                                  C.c_int32, C.c_float, C.c_void_p]),
+                                  C.c_int32, C.c_float, C.c_int32, C.c_void_p]),
     "devit_vit_workspace_bytes": (C.c_size_t, [C.POINTER(VitDesc), C.c_int32]),
     "devit_vit_forward": (C.c_int, [C.POINTER(VitDesc), C.c_void_p, C.c_int32, C.c_void_p,
                                     C.c_size_t, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
@@ -208,8 +209,34 @@ def ptr(t: torch.Tensor | None) -> int | None:
     return t.data_ptr()
 
 
-def stream_ptr() -> int:
-    return torch.cuda.current_stream().cuda_stream
+def stream_ptr(device=None) -> int:
+    """cudaStream_t of torch's current stream on `device` (default: the current device).  The C
+    side launches on the CURRENT device, so callers whose operands may live on another device wrap
+    the call in ``torch.cuda.device(t.device)`` and pass that device here."""
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def on_operand_device(fn):
+    """Runs a wrapper with the device of its first CUDA tensor argument made current: the C ABI
+    launches on the current device and on torch's current stream OF THAT DEVICE, so a tensor on
+    cuda:1 while cuda:0 is current would otherwise be handed to device 0's stream.  Mixed-device
+    operands are rejected."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        dev = None
+        for a in list(args) + list(kwargs.values()):
+            if torch.is_tensor(a) and a.is_cuda:
+                if dev is None:
+                    dev = a.device
+                elif a.device != dev:
+                    raise DevitError(f"{fn.__name__}: operands on {dev} and {a.device}")
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapped
 
 
 # ------------------------------------------------------------------------------------------
@@ -237,6 +264,7 @@ def operand_to_f32(t: torch.Tensor, precision: int) -> torch.Tensor:
     return t[0] + t[1]
 
 
+@on_operand_device
 def gemm(a, b, *, precision=DEVIT_BF16, m=None, n=None, segs=None, out=None,
          out_kind=OUT_BF16, bias=None, resid=None, rowbias=None, act=ACT_NONE, alpha=1.0,
          rowmap=(0, 0, 0), block_n=0, out_rows=None, tag=0, cluster_m=0,
@@ -299,8 +327,18 @@ TAGS = ["gemm_other", "gemm_patch", "gemm_qkv", "gemm_proj", "gemm_fc1", "gemm_f
         "token_prefix", "gemm_mlp_fused", "eval_tail"]
 
 
+_profiling = False
+
+
+def profiling() -> bool:
+    """True while the per-launch CUDA-event profile is on (callers then keep to one stream)."""
+    return _profiling
+
+
 def profile_enable(on: bool) -> None:
+    global _profiling
     check(load().devit_profile_enable(1 if on else 0))
+    _profiling = bool(on)
 
 
 def profile_collect() -> dict:
@@ -311,6 +349,7 @@ def profile_collect() -> dict:
     return {TAGS[i]: (ms[i], cnt[i]) for i in range(len(TAGS)) if cnt[i]}
 
 
+@on_operand_device
 def im2col_tokens(images, num_prefix, precision=DEVIT_BF16):
     """Token-row patch matrix of an NCHW fp32 batch (see devit_im2col_tokens): bf16
     [B*tokens, C*256], or fp32 hi/lo planes [2, B*tokens, C*256] in the DEVIT_FP32 mode."""
@@ -327,6 +366,7 @@ def im2col_tokens(images, num_prefix, precision=DEVIT_BF16):
     return a
 
 
+@on_operand_device
 def im2col_tokens_u8(images, mean, std, num_prefix, precision=DEVIT_BF16, layout=LAYOUT_NCHW):
     """Token-row patch matrix of a uint8 batch ([B,C,H,W], or [B,H,W,3] with LAYOUT_NHWC) with
     ToTensor + Normalize(mean, std) applied on the device (see devit_im2col_tokens_u8)."""
@@ -353,6 +393,7 @@ def im2col_tokens_u8(images, mean, std, num_prefix, precision=DEVIT_BF16, layout
     return a
 
 
+@on_operand_device
 def eval_tail(logits, target, acc=None, topk=5, want_batch=True):
     """Device-side CrossEntropy + top-1 / top-k counts of one batch (see devit_eval_tail).
     `acc`: float64 [5] running meters updated in place.  Returns float32 [3]
@@ -373,6 +414,7 @@ def eval_tail(logits, target, acc=None, topk=5, want_batch=True):
     return out
 
 
+@on_operand_device
 def rowstats(x):
     """bf16 copy + per-row (sum, sum of squares) of an fp32 matrix -> (xb, stats[1, rows, 2])."""
     rows, dim = x.shape
@@ -382,6 +424,7 @@ def rowstats(x):
     return xb, stats
 
 
+@on_operand_device
 def mlp_fused(x, xb, ln_stats, w1, c1, c2, w2, b2, eps, xb_out=None, stats_out=None):
     """In-place x += gelu(LN(x) W1^T + b1) W2^T + b2 (LayerNorm folded); see devit_mlp_fused."""
     a = MlpArgs()
@@ -394,6 +437,7 @@ def mlp_fused(x, xb, ln_stats, w1, c1, c2, w2, b2, eps, xb_out=None, stats_out=N
     return x
 
 
+@on_operand_device
 def layernorm(x, gamma, beta, eps, out_kind=OUT_BF16):
     lib = load()
     rows, dim = x.shape
@@ -408,6 +452,7 @@ def layernorm(x, gamma, beta, eps, out_kind=OUT_BF16):
     return y
 
 
+@on_operand_device
 def attention(qkv, batch, tokens, heads, scale, precision=DEVIT_BF16):
     lib = load()
     rows = batch * tokens

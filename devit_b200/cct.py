@@ -254,9 +254,10 @@ class CCT(nn.Module):
         B = x.shape[0]
         ws = packing.workspace(x.device, pk.workspace_bytes(B))
         pooled = torch.empty(B, pk.dim, device=x.device)
-        L.check(L.load().devit_cct_forward(C.byref(pk.desc), x.data_ptr(), B, ws.data_ptr(),
-                                           ws.numel(), pooled.data_ptr(), L.ptr(x_out), num_layers,
-                                           L.stream_ptr()))
+        with torch.cuda.device(x.device):  # the C side launches on the current device
+            L.check(L.load().devit_cct_forward(C.byref(pk.desc), x.data_ptr(), B, ws.data_ptr(),
+                                               ws.numel(), pooled.data_ptr(), L.ptr(x_out),
+                                               num_layers, L.stream_ptr(x.device)))
         return pooled
 
     @torch.no_grad()

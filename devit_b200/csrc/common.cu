@@ -12,6 +12,7 @@ namespace devit {
 
 static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};
+static std::atomic<int> g_sm_budget{0};
 
 int set_error(int code, const char* fmt, ...) {
   va_list ap;
@@ -107,7 +108,14 @@ int check_device() {
 int num_sms() {
   DevInfo d;
   if (device_info(&d)) return 1;
-  return d.sms > 0 ? d.sms : 1;
+  // devit_set_sm_budget (or DEVIT_SM_LIMIT=<n> for experiments): size every persistent grid
+  // for n SMs so that several kernel chains share the chip; even, so CTA pairs stay whole
+  static int limit_cache = kEnvUnread;
+  int limit = g_sm_budget.load(std::memory_order_relaxed);
+  if (limit <= 0) limit = env_int("DEVIT_SM_LIMIT", 0, &limit_cache);
+  int sms = d.sms > 0 ? d.sms : 1;
+  if (limit >= 2 && limit < sms) sms = limit & ~1;
+  return sms;
 }
 
 // ------------------------------------------------------------------ tensor maps
@@ -197,6 +205,7 @@ int devit_abi_version(void) { return DEVIT_ABI_VERSION; }
 const char* devit_last_error(void) { return devit::g_err; }
 int devit_device_check(void) { return devit::check_device(); }
 long long devit_launch_count(void) { return devit::g_launches.load(); }
+int devit_set_sm_budget(int sms) { return devit::g_sm_budget.exchange(sms < 0 ? 0 : sms); }
 
 int devit_profile_enable(int on) {
   std::lock_guard<std::mutex> lk(devit::g_prof_mu);

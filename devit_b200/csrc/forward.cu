@@ -349,7 +349,7 @@ static int vit_forward_impl(const devit_vit_desc* d, const float* images, const 
   if (feats_f32 || feats_op) {
     rc = devit_gather_ln(x, d->norm_g, d->norm_b, feats_f32, feats_op, opk,
                          feats_op_plane_stride, batch, L.tokens, D, d->num_prefix, d->ln_eps,
-                         stream);
+                         exports ? exports->feats_kind_rows : 0, stream);
     if (rc) return rc;
   }
   return DEVIT_OK;

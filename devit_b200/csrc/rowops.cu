@@ -108,12 +108,12 @@ __global__ void __launch_bounds__(256)
 gather_ln_kernel(const float* __restrict__ x, const float* __restrict__ g,
                  const float* __restrict__ b, float* __restrict__ feats_f32,
                  void* __restrict__ feats_op, int out_kind, long long plane, int batch, int tokens,
-                 int num_prefix, float eps) {
+                 int num_prefix, float eps, int kind_rows) {
   constexpr int D = V * 128;
   const int idx = blockIdx.x * 8 + (threadIdx.x >> 5);  // = img * num_prefix + j
   if (idx >= batch * num_prefix) return;
   const int img = idx / num_prefix, j = idx - img * num_prefix;
-  const long long orow = static_cast<long long>(j) * batch + img;
+  const long long orow = static_cast<long long>(j) * kind_rows + img;
   const int esz = out_kind == DEVIT_OUT_BF16 ? 2 : 4;
   ln_row<V>(x + (static_cast<long long>(img) * tokens + j) * D, g, b, eps, threadIdx.x & 31,
             out_kind, feats_op ? static_cast<uint8_t*>(feats_op) + orow * D * esz : nullptr, plane,
@@ -253,18 +253,21 @@ extern "C" int devit_rowstats(const float* x, void* xb, float* stats, int64_t ro
 extern "C" int devit_gather_ln(const float* x, const float* gamma, const float* beta,
                                float* feats_f32, void* feats_op, int32_t out_kind,
                                int64_t out_plane_stride, int32_t batch, int32_t tokens,
-                               int32_t dim, int32_t num_prefix, float eps, void* stream_v) {
+                               int32_t dim, int32_t num_prefix, float eps, int32_t kind_rows,
+                               void* stream_v) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
   int rc = check_device();
   if (rc) return rc;
   DEVIT_REQUIRE(x && gamma && beta && (feats_f32 || feats_op), "devit_gather_ln: null pointer");
   DEVIT_REQUIRE(batch > 0 && num_prefix > 0 && num_prefix <= tokens, "devit_gather_ln: bad shape");
+  if (kind_rows <= 0) kind_rows = batch;
+  DEVIT_REQUIRE(kind_rows >= batch, "devit_gather_ln: kind_rows %d < batch %d", kind_rows, batch);
   const unsigned grid = static_cast<unsigned>((batch * num_prefix + 7) / 8);
   ProfScope ps(kTagGatherLn, stream);
   switch (dim) {
-    case 256: gather_ln_kernel<2><<<grid, 256, 0, stream>>>(x, gamma, beta, feats_f32, feats_op, out_kind, out_plane_stride, batch, tokens, num_prefix, eps); break;
-    case 384: gather_ln_kernel<3><<<grid, 256, 0, stream>>>(x, gamma, beta, feats_f32, feats_op, out_kind, out_plane_stride, batch, tokens, num_prefix, eps); break;
-    case 768: gather_ln_kernel<6><<<grid, 256, 0, stream>>>(x, gamma, beta, feats_f32, feats_op, out_kind, out_plane_stride, batch, tokens, num_prefix, eps); break;
+    case 256: gather_ln_kernel<2><<<grid, 256, 0, stream>>>(x, gamma, beta, feats_f32, feats_op, out_kind, out_plane_stride, batch, tokens, num_prefix, eps, kind_rows); break;
+    case 384: gather_ln_kernel<3><<<grid, 256, 0, stream>>>(x, gamma, beta, feats_f32, feats_op, out_kind, out_plane_stride, batch, tokens, num_prefix, eps, kind_rows); break;
+    case 768: gather_ln_kernel<6><<<grid, 256, 0, stream>>>(x, gamma, beta, feats_f32, feats_op, out_kind, out_plane_stride, batch, tokens, num_prefix, eps, kind_rows); break;
     default: return set_error(DEVIT_ERR_ARG, "devit_gather_ln: dim %d not in {256,384,768}", dim);
   }
   DEVIT_CUDA_OK(cudaGetLastError());

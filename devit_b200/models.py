@@ -379,30 +379,53 @@ class VisionTransformer(nn.Module):
 
     @torch.no_grad()
     def features_into(self, x, feats_f32=None, feats_op=None, x_out=None, num_layers=-1,
-                      patches=None):
+                      patches=None, rows=None):
         """Fused forward of the compacted sub-model: images -> LayerNormed cls(/dist) rows,
         written into caller-provided slabs ([num_tokens, B, D] fp32 and/or operand format).
         `patches` (optional): the token-row patch matrix of x from ``patches_of`` -- the
         sub-models of an ensemble embed the same images, so MultiViT extracts it once.
-        uint8 images are normalised on the device (``set_input_norm``)."""
+        `rows` = (b0, b1) (optional): process only images [b0, b1) of x / patches and write
+        their rows of the slabs (MultiViT runs the chunks of a batch as independent kernel chains
+        on separate streams).  uint8 images are normalised on the device (``set_input_norm``)."""
         x = self._check_input(x, convert=patches is None)
-        pk = self.packed(x.device)
-        B = x.shape[0]
-        if patches is None and x.dtype == torch.uint8:
-            patches = self.patches_of(x)
-        ws = packing.workspace(x.device, pk.workspace_bytes(B))
-        plane = feats_op.stride(0) if (feats_op is not None and feats_op.dim() == 4) else 0
-        if patches is None:
-            L.check(L.load().devit_vit_forward(
-                C.byref(pk.desc), x.data_ptr(), B, ws.data_ptr(), ws.numel(),
-                L.ptr(feats_f32), L.ptr(feats_op), plane, L.ptr(x_out), num_layers,
-                L.stream_ptr()))
-        else:
-            pplane = patches.stride(0) if patches.dim() == 3 else 0
-            L.check(L.load().devit_vit_forward_patches(
-                C.byref(pk.desc), patches.data_ptr(), pplane, B, ws.data_ptr(), ws.numel(),
-                L.ptr(feats_f32), L.ptr(feats_op), plane, L.ptr(x_out), num_layers,
-                L.stream_ptr()))
+        # the C side launches on the CURRENT device: make the operand's device current for the
+        # call (a model on cuda:1 while cuda:0 is current must not launch on device 0's stream)
+        with torch.cuda.device(x.device):
+            pk = self.packed(x.device)
+            B = x.shape[0]
+            if patches is None and x.dtype == torch.uint8:
+                patches = self.patches_of(x)
+            b0, b1 = (0, B) if rows is None else rows
+            if not (0 <= b0 < b1 <= B):
+                raise L.DevitError(f"features_into: rows {rows} outside the batch of {B}")
+            nb = b1 - b0
+            ws = packing.workspace(x.device, pk.workspace_bytes(nb))
+            T, D = self.num_tokens, self.embed_dim
+            split = feats_op is not None and feats_op.dim() == 4
+            plane = feats_op.stride(0) if split else 0
+            for t in (feats_f32, feats_op[0] if split else feats_op):
+                if t is not None and (t.shape != (T, B, D) or not t.is_contiguous()):
+                    raise L.DevitError(f"features_into: feature slabs must be contiguous "
+                                       f"[{T}, {B}, {D}], got {tuple(t.shape)}")
+            ex = L.VitExports()
+            ex.feats_kind_rows = B
+
+            def at(t, elems):  # pointer `elems` elements into a tensor (or None)
+                return None if t is None else t.data_ptr() + elems * t.element_size()
+
+            if x_out is not None and rows is not None:
+                x_out = x_out[b0:b1]
+            img_ptr = pat_ptr = None
+            pplane = 0
+            if patches is None:
+                img_ptr = at(x, b0 * x.stride(0))
+            else:
+                pplane = patches.stride(0) if patches.dim() == 3 else 0
+                pat_ptr = at(patches, b0 * pk.tokens * patches.shape[-1])
+            L.check(L.load().devit_vit_forward_ex(
+                C.byref(pk.desc), img_ptr, pat_ptr, pplane, nb, ws.data_ptr(), ws.numel(),
+                at(feats_f32, b0 * D), at(feats_op, b0 * D), plane, L.ptr(x_out), num_layers,
+                C.byref(ex), L.stream_ptr(x.device)))
 
     def _feature_slabs(self, B, device, want_op=False):
         f32 = torch.empty(self.num_tokens, B, self.embed_dim, device=device)
@@ -470,12 +493,13 @@ class VisionTransformer(nn.Module):
         f32, _ = self._feature_slabs(B, x.device)
         patches = self.patches_of(x) if x.dtype == torch.uint8 else None
         ws = packing.workspace(x.device, pk.workspace_bytes(B))
-        L.check(L.load().devit_vit_forward_ex(
-            C.byref(pk.desc), None if patches is not None else x.data_ptr(),
-            None if patches is None else patches.data_ptr(),
-            patches.stride(0) if (patches is not None and patches.dim() == 3) else 0,
-            B, ws.data_ptr(), ws.numel(), L.ptr(f32), None, 0, None, -1, C.byref(ex),
-            L.stream_ptr()))
+        with torch.cuda.device(x.device):  # the C side launches on the current device
+            L.check(L.load().devit_vit_forward_ex(
+                C.byref(pk.desc), None if patches is not None else x.data_ptr(),
+                None if patches is None else patches.data_ptr(),
+                patches.stride(0) if (patches is not None and patches.dim() == 3) else 0,
+                B, ws.data_ptr(), ws.numel(), L.ptr(f32), None, 0, None, -1, C.byref(ex),
+                L.stream_ptr(x.device)))
         self._last_input, self._observers_stale = x, True
         qkvs = [None] * depth
         for l, t in bufs.items():

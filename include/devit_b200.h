@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define DEVIT_ABI_VERSION 3
+#define DEVIT_ABI_VERSION 4
 
 enum {
   DEVIT_OK = 0,
@@ -76,6 +76,15 @@ enum {
 };
 int devit_profile_enable(int on);
 int devit_profile_collect(double* ms_by_tag, long long* count_by_tag);
+
+/* SM budget of the persistent kernels launched AFTER this call by any thread of the process
+ * (0 = the whole chip, the default).  Every GEMM / attention / fused-MLP launch is a persistent
+ * grid with one CTA per SM; when the host runs several independent kernel chains on separate
+ * streams (the sub-models of an ensemble are independent until the fusion head,
+ * models/ensemble_models.py:33) it sizes each chain's grids for a share of the chip so that two
+ * chains run side by side and the HBM-bound phases of one overlap the tensor-bound phases of the
+ * other.  Values are rounded down to an even count (CTA pairs); returns the previous budget. */
+int devit_set_sm_budget(int sms);
 
 /* ---------------------------------------------------------------------------------------
  * devit_gemm: out = epilogue( sum_s A_s[M, K_s] * B_s[N, K_s]^T )  on tcgen05/TMEM via TMA.
@@ -303,12 +312,16 @@ int devit_token_prefix(float* x, const float* prefix, const float* pos, int32_t 
 /* ---------------------------------------------------------------------------------------
  * devit_gather_ln: feats[j, b, :] = LayerNorm(x[b, j, :]) for j < num_prefix -- the final
  * norm restricted to the rows the model actually returns (models/de_vit.py:286-288).
- * feats_f32 (optional) fp32 [num_prefix, batch, dim]; feats_op (optional) the same values in
+ * feats_f32 (optional) fp32 [num_prefix, kind_rows, dim]; feats_op (optional) the same values in
  * the GEMM operand format selected by out_kind (bf16 or split fp32) for the fusion head.
+ * kind_rows (0 = batch) is the row count of one token kind in the OUTPUT slabs: a caller that
+ * runs a batch in several chunks passes the slab pointers advanced to the chunk's first image and
+ * kind_rows = the whole batch.
  * ------------------------------------------------------------------------------------- */
 int devit_gather_ln(const float* x, const float* gamma, const float* beta, float* feats_f32,
                     void* feats_op, int32_t out_kind, int64_t out_plane_stride, int32_t batch,
-                    int32_t tokens, int32_t dim, int32_t num_prefix, float eps, void* stream);
+                    int32_t tokens, int32_t dim, int32_t num_prefix, float eps,
+                    int32_t kind_rows, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * devit_vit_forward: the whole VisionTransformer.forward_features of one (compacted)
@@ -397,6 +410,9 @@ int devit_vit_forward_patches(const devit_vit_desc* desc, const void* patches,
 #define DEVIT_MAX_DEPTH 32
 typedef struct devit_vit_exports {
   void* qkv[DEVIT_MAX_DEPTH];
+  /* rows of one token kind in feats_f32 / feats_op (0 = batch): set to the whole batch when this
+   * call processes a chunk of it and the feats pointers address the chunk's first image */
+  int32_t feats_kind_rows;
 } devit_vit_exports;
 
 int devit_vit_forward_ex(const devit_vit_desc* desc, const float* images, const void* patches,

@@ -1,7 +1,8 @@
-"""Import shim that lets the UNMODIFIED reference (/root/reference) run in this container.
-
-Used only by tests/golden/make_golden.py (and optional local cross-checks); it cannot travel to
-the GPU box because /root/reference does not exist there.  Three non-invasive shims
+"""Import shim that lets the UNMODIFIED reference run outside its own (torch 1.8 / timm 0.5.4)
+environment: from /root/reference in the build container, or from the byte copy of its hot-path
+modules that oracle/make_ref.py places under the git-ignored oracle/_ref/ (which travels to the
+GPU box).  Used by tests/golden/make_*.py, the reference-vs-oracle cross-checks and the
+`--impl reference` / `cpu_baseline` legs of bench.py.  Three non-invasive shims
  -- none edits the reference:
   1. a stand-in for the parts of timm==0.5.4 the hot path imports (timm is not installed);
   2. ``builtins.partial`` / ``builtins.nn`` so models/utils/config.py:4 imports;
@@ -19,7 +20,22 @@ import types
 import torch
 import torch.nn as nn
 
-REFERENCE_ROOT = "/root/reference"
+def reference_root():
+    """/root/reference when present (build container), else oracle/_ref (GPU box), else None."""
+    import os
+    from pathlib import Path
+    forced = os.environ.get("DEVIT_REF_ROOT")  # tests: force the oracle/_ref copy
+    if forced:
+        return forced if os.path.isdir(os.path.join(forced, "models")) else None
+    if os.path.isdir("/root/reference/models"):
+        return "/root/reference"
+    ref = Path(__file__).resolve().parent / "_ref"
+    if (ref / "models" / "de_vit.py").exists():
+        return str(ref)
+    return None
+
+
+REFERENCE_ROOT = reference_root()
 
 
 class _PatchEmbed(nn.Module):
@@ -144,6 +160,9 @@ def install():
             return t.device
         _get_device._devit_shim = True
         torch.Tensor.get_device = _get_device
+    if REFERENCE_ROOT is None:
+        raise ImportError("the reference is neither at /root/reference nor under oracle/_ref "
+                          "(run oracle/make_ref.py where /root/reference exists)")
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)
 

@@ -26,7 +26,7 @@ def test_abi_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert declared == set(L.exported_symbols()), "ctypes table and header disagree"
-    assert L.load().devit_abi_version() == 3
+    assert L.load().devit_abi_version() == L.ABI_VERSION
 
 
 def test_no_cpu_fallback():

@@ -75,6 +75,7 @@ class MlpArgs(C.Structure):
         ("ln_stats", C.c_void_p), ("ln_parts", C.c_int32), ("ln_eps", C.c_float),
         ("w2", C.c_void_p), ("b2", C.c_void_p), ("x", C.c_void_p), ("xb_out", C.c_void_p),
         ("stats_out", C.c_void_p),
+        ("o", C.c_void_p), ("w_proj", C.c_void_p), ("b_proj", C.c_void_p), ("proj_k", C.c_int32),
     ]
 
 
@@ -425,14 +426,20 @@ def rowstats(x):
 
 
 @on_operand_device
-def mlp_fused(x, xb, ln_stats, w1, c1, c2, w2, b2, eps, xb_out=None, stats_out=None):
-    """In-place x += gelu(LN(x) W1^T + b1) W2^T + b2 (LayerNorm folded); see devit_mlp_fused."""
+def mlp_fused(x, xb, ln_stats, w1, c1, c2, w2, b2, eps, xb_out=None, stats_out=None,
+              o=None, w_proj=None, b_proj=None):
+    """In-place x += gelu(LN(x) W1^T + b1) W2^T + b2 (LayerNorm folded); see devit_mlp_fused.
+    With `o` / `w_proj` / `b_proj` the attention-output projection runs in front in the same
+    kernel (x1 = x + o Wp^T + bp, then the MLP on x1; `xb` / `ln_stats` are not used)."""
     a = MlpArgs()
     a.m, a.dim, a.hidden_ld = x.shape[0], x.shape[1], w1.shape[0]
     a.xb, a.w1, a.c1, a.c2 = ptr(xb), ptr(w1), ptr(c1), ptr(c2)
-    a.ln_stats, a.ln_parts, a.ln_eps = ptr(ln_stats), ln_stats.shape[0], eps
+    a.ln_stats, a.ln_parts, a.ln_eps = ptr(ln_stats), (ln_stats.shape[0] if ln_stats is not None
+                                                      else 0), eps
     a.w2, a.b2, a.x = ptr(w2), ptr(b2), ptr(x)
     a.xb_out, a.stats_out = ptr(xb_out), ptr(stats_out)
+    if o is not None:
+        a.o, a.w_proj, a.b_proj, a.proj_k = ptr(o), ptr(w_proj), ptr(b_proj), o.shape[1]
     check(load().devit_mlp_fused(C.byref(a), stream_ptr()))
     return x
 

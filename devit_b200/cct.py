@@ -240,8 +240,10 @@ class CCT(nn.Module):
         return self._pack[1]
 
     @torch.no_grad()
-    def pooled_features(self, x, x_out=None, num_layers=-1):
-        """images [B, C, H, W] -> sequence-pooled feature [B, dim] (fp32)."""
+    def pooled_features(self, x, x_out=None, num_layers=-1, out=None, rows=None):
+        """images [B, C, H, W] -> sequence-pooled feature [B, dim] (fp32).  `out` (optional): a
+        contiguous [B, dim] fp32 tensor to write into; `rows` = (b0, b1): process only that chunk
+        of the batch (MultiCCT runs chunks as independent kernel chains)."""
         if not x.is_cuda:
             raise L.DevitError("devit_b200 models run on CUDA (sm_100) tensors only; "
                                "there is no CPU fallback")
@@ -252,12 +254,21 @@ class CCT(nn.Module):
         x = x.float().contiguous()
         pk = self.packed(x.device)
         B = x.shape[0]
-        ws = packing.workspace(x.device, pk.workspace_bytes(B))
-        pooled = torch.empty(B, pk.dim, device=x.device)
+        b0, b1 = (0, B) if rows is None else rows
+        if not (0 <= b0 < b1 <= B):
+            raise L.DevitError(f"pooled_features: rows {rows} outside the batch of {B}")
+        pooled = out if out is not None else torch.empty(B, pk.dim, device=x.device)
+        if pooled.shape != (B, pk.dim) or not pooled.is_contiguous() or \
+                pooled.dtype != torch.float32:
+            raise L.DevitError("pooled_features: `out` must be a contiguous fp32 [B, dim] tensor")
+        if x_out is not None and rows is not None:
+            x_out = x_out[b0:b1]
         with torch.cuda.device(x.device):  # the C side launches on the current device
-            L.check(L.load().devit_cct_forward(C.byref(pk.desc), x.data_ptr(), B, ws.data_ptr(),
-                                               ws.numel(), pooled.data_ptr(), L.ptr(x_out),
-                                               num_layers, L.stream_ptr(x.device)))
+            ws = packing.workspace(x.device, pk.workspace_bytes(b1 - b0))
+            L.check(L.load().devit_cct_forward(
+                C.byref(pk.desc), x.data_ptr() + b0 * x.stride(0) * 4, b1 - b0, ws.data_ptr(),
+                ws.numel(), pooled.data_ptr() + b0 * pk.dim * 4, L.ptr(x_out), num_layers,
+                L.stream_ptr(x.device)))
         return pooled
 
     @torch.no_grad()
@@ -358,8 +369,32 @@ class MultiCCT(nn.Module):
         return self
 
     @torch.no_grad()
+    def forward_slab(self, x, subs=None):
+        """Runs the backbones in `subs` (default: all) as independent kernel chains and returns
+        (slab_f32, slab_op), both [len(subs), 1, B, dim] (slab_op in the GEMM operand format: bf16,
+        or [2, ...] split planes in the fp32 mode) -- the layout ShardedEnsemble all-gathers."""
+        from .ensemble import chain_tasks, run_chains
+        subs = list(range(len(self.models))) if subs is None else list(subs)
+        B, D = x.shape[0], self.models[subs[0]].tokenizer.conv_layers[-1][0].out_channels
+        f32 = torch.empty(len(subs), 1, B, D, device=x.device)
+
+        def launch(task):
+            i, s, rows = task
+            m = self.models[s]
+            if m.precision != self.precision:
+                m.set_precision(self.precision)
+            m.pooled_features(x, out=f32[i, 0], rows=rows)
+
+        run_chains(x.device, chain_tasks(subs, B, x.is_cuda), launch)
+        return f32, L.to_operand(f32, _PREC[self.precision])
+
+    @torch.no_grad()
     def forward(self, x):
-        return [m(x) for m in self.models]
+        from .ensemble import FeatureList
+        f32, op = self.forward_slab(x)
+        out = FeatureList(f32[s, 0] for s in range(f32.shape[0]))
+        out.slab_f32, out.slab_op, out.kind = f32, op, 0
+        return out
 
 
 class EnsembleCCT(nn.Module):
@@ -382,19 +417,27 @@ class EnsembleCCT(nn.Module):
         self.precision = precision
         return self
 
-    @torch.no_grad()
-    def forward(self, sub_model_features, distill=False):
+    def _first(self):
+        return self.cls_classifier if self.teacher_size is None else self.cls_mlp
+
+    def _head(self, slab, order, distill=False):
+        """slab: operand-format [n, 1, B, D] (or [2, n, 1, B, D]); entry j = sub-model order[j]."""
         prec = _PREC[self.precision]
-        n, D = len(sub_model_features), self.sub_size
-        if n != self.num_sub_models or n > 8:
-            raise L.DevitError(f"EnsembleCCT: expected {self.num_sub_models} (<= 8) feature tensors")
-        B = sub_model_features[0].shape[0]
-        slab = L.to_operand(torch.stack([f.float() for f in sub_model_features], 0)
-                            .reshape(n * B, D), prec)
-        segs = [(j * B, 0, j * D, D) for j in range(n)]
-        first = self.cls_classifier if self.teacher_size is None else self.cls_mlp
+        s4 = slab if prec == L.DEVIT_BF16 else slab[0]
+        n, kinds, B, D = s4.shape
+        if n != self.num_sub_models or n > 8 or D != self.sub_size or kinds != 1:
+            raise L.DevitError(f"EnsembleCCT: expected {self.num_sub_models} (<= 8) feature "
+                               f"tensors of width {self.sub_size}")
+        order = list(range(n)) if order is None else list(order)
+        if sorted(order) != list(range(n)):
+            raise L.DevitError(f"EnsembleCCT: slab order {order} is not a permutation")
+        a = slab.view(n * B, D) if prec == L.DEVIT_BF16 else slab.view(2, n * B, D)
+        # K-segments in SUB-MODEL order whatever the slab layout: same summation order, hence the
+        # same logits bit for bit, for every world size
+        segs = sorted(((j * B, 0, order[j] * D, D) for j in range(n)), key=lambda sg: sg[2])
+        first = self._first()
         w = L.to_operand(first.weight.float(), prec)
-        h = L.gemm(slab, w, precision=prec, m=B, segs=segs, bias=first.bias.float(),
+        h = L.gemm(a, w, precision=prec, m=B, segs=segs, bias=first.bias.float(),
                    out_kind=L.OUT_F32, tag=6)
         if self.teacher_size is None:
             return h
@@ -404,3 +447,23 @@ class EnsembleCCT(nn.Module):
         if distill and self.training:
             return h, logits
         return logits
+
+    @torch.no_grad()
+    def forward_gathered(self, slab, order=None):
+        """Fusion head straight from a gathered operand slab (ShardedEnsemble)."""
+        return self._head(slab, order)
+
+    @torch.no_grad()
+    def forward(self, sub_model_features, distill=False):
+        prec = _PREC[self.precision]
+        feats = sub_model_features
+        slab = getattr(feats, 'slab_op', None)
+        n = len(feats)
+        if slab is None or any(feats[j].data_ptr() != feats.slab_f32[j, 0].data_ptr()
+                               for j in range(n)):
+            # plain list of tensors (or a list whose entries were replaced): stack, as the
+            # reference does (models/ensemble_models.py:139)
+            B = feats[0].shape[0]
+            slab = L.to_operand(torch.stack([f.float() for f in feats], 0)
+                                .reshape(n, 1, B, -1), prec)
+        return self._head(slab, None, distill)

@@ -128,6 +128,8 @@ static int run_blocks(const devit_layer_desc* layers, int nl, int prec, int D, f
     const char* e = getenv("DEVIT_FUSED_MLP");
     fused_mlp = (e && e[0] == '0') ? 0 : 1;
   }
+  static int fused_proj_cache = kEnvUnread;  // DEVIT_FUSED_PROJ=0: separate proj GEMM (comparison)
+  const bool fused_proj = env_int("DEVIT_FUSED_PROJ", 1, &fused_proj_cache) != 0;
   void* const qkv_ws = qkv;
   for (int l = 0; l < nl; ++l) {
     const devit_layer_desc& w = layers[l];
@@ -163,6 +165,25 @@ static int run_blocks(const devit_layer_desc* layers, int nl, int prec, int D, f
                          stream);
     if (rc) return rc;
     if ((rc = sync_debug("attention", l, stream))) return rc;
+    const int F = w.hidden_ld;
+    const bool fuse_mlp = fold && fused_mlp && (D == 384 || D == 256);
+    if (fuse_mlp && fused_proj) {
+      // x1 = x + o Wproj^T + b ; x = x1 + gelu(LN2(x1) W1^T + b1) W2^T + b2 in ONE kernel: the
+      // residual stream makes one fp32 round trip per layer, x1 / its bf16 copy / its row sums
+      // stay on chip                                               (:81-82, :114, :35-47, :115)
+      devit_mlp_args ma;
+      std::memset(&ma, 0, sizeof(ma));
+      ma.m = static_cast<int>(M); ma.dim = D; ma.hidden_ld = F;
+      ma.w1 = w.w_fc1; ma.c1 = w.cs_fc1; ma.c2 = w.b_fc1; ma.ln_eps = ln_eps;
+      ma.w2 = w.w_fc2; ma.b2 = w.b_fc2; ma.x = x;
+      ma.o = o; ma.w_proj = w.w_proj; ma.b_proj = w.b_proj; ma.proj_k = hd;
+      if (l + 1 < nl) { ma.xb_out = y; ma.stats_out = stats; }
+      rc = devit_mlp_fused(&ma, stream);
+      if (rc) return rc;
+      parts = 4;  // the fused kernel emits one partial row sum per dim/4 columns
+      if ((rc = sync_debug("fused proj + mlp", l, stream))) return rc;
+      continue;
+    }
     // x += o Wproj^T + b                                         (:81, :114)
     base_gemm(&g, prec);
     g.m = static_cast<int>(M); g.n = D;
@@ -185,8 +206,7 @@ static int run_blocks(const devit_layer_desc* layers, int nl, int prec, int D, f
       rc = devit_layernorm(x, w.ln2_g, w.ln2_b, y, M, D, ln_eps, opk, M * D, stream);
       if (rc) return rc;
     }
-    const int F = w.hidden_ld;
-    if (fold && fused_mlp && (D == 384 || D == 256)) {
+    if (fuse_mlp) {
       // x += gelu(LN2(x) W1^T + b1) W2^T + b2 in one kernel, hidden kept on chip   (:35-47, :115)
       devit_mlp_args ma;
       std::memset(&ma, 0, sizeof(ma));

@@ -21,6 +21,23 @@
 //     GEMM consumes.  The loaders resume only when every slot has been drained (all_free).
 // TMEM: D + 2 x 64 columns (all 512 at D = 384).  smem at D = 384: Y 96 KB + W1 ring 48 KB +
 // W2 ring 48 KB + 32 KB bf16 staging.  Instantiated for D = 384 (dedeit) and D = 256 (cct_7).
+//
+// PROJ variant (devit_mlp_args.o != NULL): the attention-output projection and its residual add
+// (models/de_vit.py:81-82, :114) run in the SAME kernel in front of the MLP:
+//     x1 = x + o Wp^T + bp ;  x = x1 + gelu( LN(x1) W1^T + b1 ) W2^T + b2
+// so the residual stream makes ONE fp32 round trip through HBM per layer instead of two and
+// neither x1, its bf16 copy nor its row statistics ever exist in global memory.  Per pair-tile:
+//   * the attention output tile O (128 x 64h bf16 per CTA) is TMA-loaded into the Y buffer and
+//     Wp streams through the W2 ring, one 64-wide head chunk at a time;
+//   * GEMM0: acc2 = O Wp^T (A and B from shared memory, same N = D/2 UMMA pairs as GEMM2);
+//   * epilogue 0 (all sixteen epilogue warps, D/4 columns each, 32 at a time): acc2 + bp + the
+//     fp32 residual chunk (TMA-loaded into one 4 KB slot per warp that lives in the idle W1 ring
+//     / staging buffer) = x1; the warp accumulates the row's (sum, sum^2), writes bf16(x1) into
+//     the Y buffer in the K-major 128B-swizzled layout GEMM1 reads, and writes x1 + b2 BACK INTO
+//     acc2, on top of which GEMM2 then accumulates.  The four partial row sums of a row meet in
+//     shared memory (one named barrier), giving the exact LayerNorm statistics of x1;
+//   * the hidden-chunk loop is unchanged; the final epilogue has no residual to fetch: acc2 is
+//     the new x.
 #include <cstdlib>
 
 #include "common.cuh"
@@ -48,7 +65,13 @@ struct MlpCfg {
   static constexpr int kOffW1 = kYBytes;
   static constexpr int kOffW2 = kOffW1 + 2 * kW1Slot;
   static constexpr int kOffXb = kOffW2 + 2 * kW2Slot;  // bf16-copy staging: 16 x [32 rows x 64 B]
-  static constexpr int kOffBar = kOffXb + 16 * 2048;
+  // PROJ: one 4 KB residual slot per epilogue warp: as many as fit in the (then idle) W1 ring,
+  // the rest at the bottom of the staging buffer, followed by the 4 KB row-statistics exchange
+  static constexpr int kXSlotsInW1 = (2 * kW1Slot / 4096) < 16 ? (2 * kW1Slot / 4096) : 16;
+  static constexpr int kOffStat = kOffXb + (16 - kXSlotsInW1) * 4096;
+  static constexpr int kXbBytes =
+      (kOffStat + 4096 - kOffXb) > 16 * 2048 ? (kOffStat + 4096 - kOffXb) : 16 * 2048;
+  static constexpr int kOffBar = kOffXb + kXbBytes;
   static constexpr int kSmem = kOffBar + 1024 + 1024;
   static constexpr int kAcc1Col = D;                // acc2 = TMEM columns [0, D), acc1 behind it
   static constexpr int kColsPerWarp = D / 4;        // final epilogue: output columns per warp
@@ -83,6 +106,8 @@ struct MlpParams {
   float ln_inv_dim, ln_eps;
   __nv_bfloat16* xb_out;
   float* stats_out;
+  const float* bp;   // PROJ: attention-output projection bias [D]
+  int proj_chunks;   // PROJ: kept heads (64-wide K chunks of O / Wp)
 };
 
 __device__ __forceinline__ void umma_bf16_ts_cg2(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
@@ -97,11 +122,13 @@ __device__ __forceinline__ void umma_bf16_ts_cg2(uint32_t d_tmem, uint32_t a_tme
 
 __device__ __forceinline__ int mlp_off(int r, int j) { return r * 128 + ((j ^ (r & 7)) << 4); }
 
-template <int D>
+// tmY: the bf16 copy of x (plain variant) or the attention output O (PROJ); tmWp: Wp (PROJ only)
+template <int D, bool PROJ>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1)
 mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmW1,
                  const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmX,
-                 const __grid_constant__ CUtensorMap tmXB, const __grid_constant__ MlpParams p) {
+                 const __grid_constant__ CUtensorMap tmXB, const __grid_constant__ CUtensorMap tmWp,
+                 const __grid_constant__ MlpParams p) {
   using Cfg = MlpCfg<D>;
   constexpr int kAtoms = Cfg::kAtoms, kYBytes = Cfg::kYBytes, kW1Slot = Cfg::kW1Slot,
                 kW2Slot = Cfg::kW2Slot, kOffW1 = Cfg::kOffW1, kOffW2 = Cfg::kOffW2,
@@ -121,8 +148,11 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
   uint64_t* h_ready = bars + 13;    // [2]  (leader: 32 warp arrivals)
   uint64_t* acc2_full = bars + 15;
   uint64_t* acc2_empty = bars + 16;  // (leader: 32 warp arrivals)
-  uint64_t* rfull = bars + 17;       // [16 warps][3 slots max]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 65);
+  uint64_t* rfull = bars + 17;       // [16 warps][3 slots max]  (PROJ: [16 warps], one slot each)
+  uint64_t* p_full = bars + 65;      // PROJ: GEMM0 retired (acc2 = O Wp^T, O is dead)
+  uint64_t* y_ready = bars + 66;     // PROJ: bf16(x1) written to Y, x1 + b2 in acc2 (leader: 32)
+  uint64_t* x_done = bars + 67;      // PROJ: this CTA's residual slots are drained (16 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 68);
 
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
@@ -154,6 +184,10 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
     mbar_init(acc2_full, 1);
     mbar_init(acc2_empty, 32);
     for (int i = 0; i < 48; ++i) mbar_init(&rfull[i], 1);
+    mbar_init(p_full, 1);
+    mbar_init(y_ready, 32);
+    mbar_init(x_done, 16);
+    if (PROJ) tma_prefetch_desc(&tmWp);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -191,7 +225,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
   };
 
   if (warp == 0) {
-    // ------------------------------------------------------------ loads: Y and the W1 ring
+    // ------------------------------------------------------------ loads: Y (or O) and the W1 ring
     uint32_t g1 = 0;
     int it = 0;
     for (int pt = cluster_id; pt < num_pairs; pt += num_clusters, ++it) {
@@ -199,10 +233,19 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
       if (it >= 1) mbar_wait_warp(y_free, (it - 1) & 1);
       if (elect_one()) {
         const uint32_t bar = mapa_u32(smem_u32(y_full), 0);
-        if (leader) mbar_expect_tx(y_full, 2 * kYBytes);
+        if constexpr (PROJ) {
+          // the attention output tile, one 64-column atom per kept head
+          if (leader) mbar_expect_tx(y_full, 2 * p.proj_chunks * 16384);
+          for (int a = 0; a < p.proj_chunks; ++a)
+            tma_load_2d_cg2(smem + a * 16384, &tmY, bar, a * 64, m0);
+        } else {
+          if (leader) mbar_expect_tx(y_full, 2 * kYBytes);
 #pragma unroll
-        for (int a = 0; a < kAtoms; ++a) tma_load_2d_cg2(smem + a * 16384, &tmY, bar, a * 64, m0);
+          for (int a = 0; a < kAtoms; ++a) tma_load_2d_cg2(smem + a * 16384, &tmY, bar, a * 64, m0);
+        }
       }
+      // PROJ: the W1 ring holds residual slots of epilogue 0 until they are drained
+      if constexpr (PROJ) mbar_wait_warp(x_done, it & 1);
       for (int c = 0; c < NC; ++c, ++g1) {
         const int s = g1 & 1;
         mbar_wait_warp(&w1_empty[s], ((g1 >> 1) & 1) ^ 1);
@@ -218,40 +261,44 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
     }
   } else if (warp == kW2Warp) {
     // ------------------------------------------------------------ loads: the W2 ring
-    uint32_t g2 = 0;
+    uint32_t gw = 0;  // ring uses (PROJ: the Wp head chunks of a tile go through it first)
     int it = 0;
     for (int pt = cluster_id; pt < num_pairs; pt += num_clusters, ++it) {
       if (it >= 1) mbar_wait_warp(y_free, (it - 1) & 1);  // ring memory served as slots
-      for (int c = 0; c < NC; ++c, ++g2) {
-        const int s = g2 & 1;
-        mbar_wait_warp(&w2_empty[s], ((g2 >> 1) & 1) ^ 1);
+      const int n_pre = PROJ ? p.proj_chunks : 0;
+      for (int c = -n_pre; c < NC; ++c, ++gw) {
+        const int s = gw & 1;
+        mbar_wait_warp(&w2_empty[s], ((gw >> 1) & 1) ^ 1);
         if (elect_one()) {
           const uint32_t bar = mapa_u32(smem_u32(&w2_full[s]), 0);
           if (leader) mbar_expect_tx(&w2_full[s], 2 * kW2Slot);
           uint8_t* dst = smem + kOffW2 + s * kW2Slot;
-          // output columns [D/2 hh + D/4 rank, +D/4) of W2, K = neurons [64c, 64c + 64)
-          tma_load_2d_cg2(dst, &tmW2, bar, c * 64, cta_rank * kW2Rows);
-          tma_load_2d_cg2(dst + kW2Rows * 128, &tmW2, bar, c * 64, kHalfN + cta_rank * kW2Rows);
+          // output columns [D/2 hh + D/4 rank, +D/4) of W2 (Wp), K = neurons [64c, 64c + 64)
+          // (K = columns of head chunk c + n_pre)
+          const CUtensorMap* tm = c < 0 ? &tmWp : &tmW2;
+          const int k0 = (c < 0 ? c + n_pre : c) * 64;
+          tma_load_2d_cg2(dst, tm, bar, k0, cta_rank * kW2Rows);
+          tma_load_2d_cg2(dst + kW2Rows * 128, tm, bar, k0, kHalfN + cta_rank * kW2Rows);
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issue (leader only)
     if (leader) {
-      uint32_t g1 = 0, g2 = 0;
+      uint32_t g1 = 0, g2 = 0, gw = 0;  // W1 ring / hidden chunks (GEMM2) / W2 ring uses
       int it = 0;
       const uint32_t idesc2 = make_idesc(kFmtBF16, 256, kHalfN, 0, 0);
       auto gemm2 = [&](int cc, bool first_of_tile) {
-        const int b = g2 & 1;
-        const uint32_t par = (g2 >> 1) & 1;
+        const int b = g2 & 1;   // acc1 / H buffer of this hidden chunk
+        const int ws = gw & 1;  // W2 ring slot
         MLP_TRACE(3, g2);
-        mbar_wait_warp(&h_ready[b], par);
+        mbar_wait_warp(&h_ready[b], (g2 >> 1) & 1);
         MLP_TRACE(4, g2);
-        mbar_wait_warp(&w2_full[b], par);
+        mbar_wait_warp(&w2_full[ws], (gw >> 1) & 1);
         MLP_TRACE(5, g2);
-        if (first_of_tile && it >= 1) mbar_wait_warp(acc2_empty, (it - 1) & 1);
+        if (!PROJ && first_of_tile && it >= 1) mbar_wait_warp(acc2_empty, (it - 1) & 1);
         tc_fence_after();
-        const uint32_t sw = smem_u32(smem + kOffW2 + b * kW2Slot);
+        const uint32_t sw = smem_u32(smem + kOffW2 + ws * kW2Slot);
         const int ksteps = chunk_n(cc) / 16;
         if (elect_one()) {
           for (int j = 0; j < ksteps; ++j) {
@@ -260,19 +307,48 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
               const uint64_t db = make_sw128_desc(sw + hh * (kW2Rows * 128), 1024, 16) + 2 * j;
+              // PROJ: acc2 already holds x1 + b2, every GEMM2 accumulates
               umma_bf16_ts_cg2(tmem_base + kHalfN * hh, a_t, db, idesc2,
-                               (first_of_tile && j == 0) ? 0u : 1u);
+                               (!PROJ && first_of_tile && j == 0) ? 0u : 1u);
             }
           }
-          umma_commit_cg2(&w2_empty[b], 3);
+          umma_commit_cg2(&w2_empty[ws], 3);
         }
         MLP_TRACE(6, g2);
         ++g2;
+        ++gw;
       };
       for (int pt = cluster_id; pt < num_pairs; pt += num_clusters, ++it) {
         MLP_TRACE(7, it);
         mbar_wait_warp(y_full, it & 1);
         MLP_TRACE(8, it);
+        if constexpr (PROJ) {
+          // GEMM0: acc2 = O Wp^T, one 64-wide head chunk per W2-ring slot
+          if (it >= 1) mbar_wait_warp(acc2_empty, (it - 1) & 1);
+          for (int a = 0; a < p.proj_chunks; ++a, ++gw) {
+            const int ws = gw & 1;
+            mbar_wait_warp(&w2_full[ws], (gw >> 1) & 1);
+            tc_fence_after();
+            const uint64_t da = make_sw128_desc(smem_u32(smem) + a * 16384, 1024, 16);
+            const uint32_t sw = smem_u32(smem + kOffW2 + ws * kW2Slot);
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                  const uint64_t db = make_sw128_desc(sw + hh * (kW2Rows * 128), 1024, 16);
+                  umma_bf16_cg2(tmem_base + kHalfN * hh, da + 2 * k, db + 2 * k, idesc2,
+                                (a | k) ? 1u : 0u);
+                }
+              }
+              umma_commit_cg2(&w2_empty[ws], 3);
+            }
+          }
+          if (elect_one()) umma_commit_cg2(p_full, 3);
+          // epilogue 0 of both CTAs: bf16(x1) in Y, x1 + b2 in acc2
+          mbar_wait_warp(y_ready, it & 1);
+          tc_fence_after();
+        }
         for (int c = 0; c < NC; ++c) {
           const int s = g1 & 1;
           MLP_TRACE(0, g1);
@@ -321,6 +397,12 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
     const uint32_t h_ready_leader0 = mapa_u32(smem_u32(&h_ready[0]), 0);
     const uint32_t h_ready_leader1 = mapa_u32(smem_u32(&h_ready[1]), 0);
     const uint32_t acc2_empty_leader = mapa_u32(smem_u32(acc2_empty), 0);
+    // PROJ: this warp's residual slot of epilogue 0 (W1 ring first, then the staging buffer)
+    uint8_t* xslot = ew < Cfg::kXSlotsInW1 ? smem + kOffW1 + ew * 4096
+                                           : smem + kOffXb + (ew - Cfg::kXSlotsInW1) * 4096;
+    uint64_t* xbar = rfull + ew;
+    const uint32_t y_ready_leader = mapa_u32(smem_u32(y_ready), 0);
+    uint32_t xcnt = 0;
     uint32_t ecnt = 0;
     int it = 0;
     for (int pt = cluster_id; pt < num_pairs; pt += num_clusters, ++it) {
@@ -329,7 +411,105 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
       const int row = row0 + lane;
       // ---- this row's LayerNorm statistics (folded into the fc1 epilogue)
       float rstd, nmr;
-      {
+      if constexpr (PROJ) {
+        // ---- epilogue 0: x1 = acc2 (= O Wp^T) + bp + x.  Residual chunks arrive by TMA in this
+        //      warp's slot; bf16(x1) -> Y (K-major, 128B swizzle), x1 + b2 -> acc2, row sums ->
+        //      shared memory.
+        float2* stat_s = reinterpret_cast<float2*>(smem + Cfg::kOffStat);
+        if (it >= 1) mbar_wait_warp(y_free, (it - 1) & 1);  // the slot memory is dead
+        if (elect_one()) {
+          mbar_expect_tx(xbar, 4096);
+          tma_load_2d(xslot, &tmX, xbar, sub * kColsPerWarp, row0);
+        }
+        // next tile's operands -> L2 while this one computes
+        if (pt + num_clusters < num_pairs && elect_one()) {
+          const int m_next = ((pt + num_clusters) * 2 + cta_rank) * 128;
+#pragma unroll
+          for (int s2 = 0; s2 < kSlots; ++s2)
+            tma_prefetch_l2_2d(&tmX, sub * kColsPerWarp + s2 * 32, m_next + quarter * 32);
+          if (sub == 0 && quarter < 2)
+            for (int a = quarter; a < p.proj_chunks; a += 2) tma_prefetch_l2_2d(&tmY, a * 64, m_next);
+        }
+        if (warp == 2) MLP_TRACE(12, it);
+        mbar_wait_warp(p_full, it & 1);
+        if (warp == 2) MLP_TRACE(13, it);
+        tc_fence_after();
+        float st1 = 0.f, st2 = 0.f;
+        const int rr = quarter * 32 + lane;  // row inside the CTA's 128
+#pragma unroll 1
+        for (int j = 0; j < kSlots; ++j, ++xcnt) {
+          const int col0 = sub * kColsPerWarp + j * 32;
+          uint32_t r[32];
+          tmem_ld_x32(tmem_base + lane_off + col0, r);
+          tmem_ld_wait();
+          float* v = reinterpret_cast<float*>(r);
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(p.bp + col0) + g);
+            v[4 * g] += t.x; v[4 * g + 1] += t.y; v[4 * g + 2] += t.z; v[4 * g + 3] += t.w;
+          }
+          mbar_wait_warp(xbar, xcnt & 1);
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 t = *reinterpret_cast<const float4*>(xslot + mlp_off(lane, g));
+            v[4 * g] += t.x; v[4 * g + 1] += t.y; v[4 * g + 2] += t.z; v[4 * g + 3] += t.w;
+          }
+          __syncwarp();
+          if (j + 1 < kSlots) {  // the slot has been read by every lane: fetch the next chunk
+            fence_proxy_async_smem();
+            if (elect_one()) {
+              mbar_expect_tx(xbar, 4096);
+              tma_load_2d(xslot, &tmX, xbar, col0 + 32, row0);
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < 32; ++k) {
+            st1 += v[k];
+            st2 = fmaf(v[k], v[k], st2);
+          }
+          {
+            uint8_t* ya = smem + (col0 >> 6) * 16384 + rr * 128;
+            const int cb = (col0 & 63) >> 3;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint4 t;
+              t.x = pack_bf16x2(v[8 * g], v[8 * g + 1]);
+              t.y = pack_bf16x2(v[8 * g + 2], v[8 * g + 3]);
+              t.z = pack_bf16x2(v[8 * g + 4], v[8 * g + 5]);
+              t.w = pack_bf16x2(v[8 * g + 6], v[8 * g + 7]);
+              *reinterpret_cast<uint4*>(ya + (((cb + g) ^ (rr & 7)) << 4)) = t;
+            }
+          }
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(p.b2 + col0) + g);
+            v[4 * g] += t.x; v[4 * g + 1] += t.y; v[4 * g + 2] += t.z; v[4 * g + 3] += t.w;
+          }
+          tmem_st_x32(tmem_base + lane_off + col0, r);
+        }
+        tmem_st_wait();
+        stat_s[sub * 128 + rr] = make_float2(st1, st2);
+        fence_proxy_async_smem();  // Y as the tensor core (async proxy) will read it
+        tc_fence_before();
+        named_bar_sync(1, 16 * 32);  // the sixteen epilogue warps of this CTA
+        if (lane == 0) {
+          mbar_arrive(x_done);
+          if (leader) mbar_arrive(y_ready);
+          else mbar_arrive_cluster(y_ready_leader);
+        }
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 t = stat_s[q * 128 + rr];
+          s1 += t.x;
+          s2 += t.y;
+        }
+        const float mean = s1 * p.ln_inv_dim;
+        const float var = fmaxf(fmaf(s2, p.ln_inv_dim, -mean * mean), 0.f);
+        rstd = rsqrtf(var + p.ln_eps);
+        nmr = -rstd * mean;
+        if (warp == 2) MLP_TRACE(14, it);
+      } else {
         float s1 = 0.f, s2 = 0.f;
         if (row < p.M) {
           for (int q = 0; q < p.ln_parts; ++q) {
@@ -343,12 +523,12 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         const float var = fmaxf(fmaf(s2, p.ln_inv_dim, -mean * mean), 0.f);
         rstd = rsqrtf(var + p.ln_eps);
         nmr = -rstd * mean;
-      }
-      // The residual of this tile is needed only in the final epilogue, and its slots do not
-      // exist until then: pull it into L2 now, so that the late TMA loads are L2 hits.
-      if (row0 < p.M && elect_one()) {
+        // The residual of this tile is needed only in the final epilogue, and its slots do not
+        // exist until then: pull it into L2 now, so that the late TMA loads are L2 hits.
+        if (row0 < p.M && elect_one()) {
 #pragma unroll
-        for (int s = 0; s < kSlots; ++s) tma_prefetch_l2_2d(&tmX, sub * kColsPerWarp + s * 32, row0);
+          for (int s = 0; s < kSlots; ++s) tma_prefetch_l2_2d(&tmX, sub * kColsPerWarp + s * 32, row0);
+        }
       }
       // ---- hidden chunks: acc1 -> H (bf16, in TMEM).  Slice `sub` of chunk c: neurons
       //      [64c + 16 sub, +16) = acc1 columns [16 sub, +16) -> H columns [16 sub, +8).
@@ -397,24 +577,27 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         if (warp == 2) MLP_TRACE(11, ecnt);
       }
       // ---- final epilogue: x += acc2 + b2, bf16 copy, partial row sums (96 columns per warp)
-      if (slots_in_w2) mbar_wait_warp(acc2_full, it & 1);
-      else mbar_wait_warp(y_empty, it & 1);
-      if (elect_one()) {
+      //      (PROJ: acc2 already IS the new x; the dead Y / ring memory only stages the stores)
+      if constexpr (!PROJ) {
+        if (slots_in_w2) mbar_wait_warp(acc2_full, it & 1);
+        else mbar_wait_warp(y_empty, it & 1);
+        if (elect_one()) {
 #pragma unroll
-        for (int s = 0; s < kSlots; ++s) {
-          mbar_expect_tx(&rbar[s], 4096);
-          tma_load_2d(slots + s * 4096, &tmX, &rbar[s], sub * kColsPerWarp + s * 32, row0);
+          for (int s = 0; s < kSlots; ++s) {
+            mbar_expect_tx(&rbar[s], 4096);
+            tma_load_2d(slots + s * 4096, &tmX, &rbar[s], sub * kColsPerWarp + s * 32, row0);
+          }
+        }
+        // ... and the next tile's Y (loaded only after every slot has been drained) likewise
+        if (warp == 2 && pt + num_clusters < num_pairs && elect_one()) {
+          const int m_next = ((pt + num_clusters) * 2 + cta_rank) * 128;
+#pragma unroll
+          for (int a = 0; a < kAtoms; ++a) tma_prefetch_l2_2d(&tmY, a * 64, m_next);
         }
       }
-      // ... and the next tile's Y (loaded only after every slot has been drained) likewise
-      if (warp == 2 && pt + num_clusters < num_pairs && elect_one()) {
-        const int m_next = ((pt + num_clusters) * 2 + cta_rank) * 128;
-#pragma unroll
-        for (int a = 0; a < kAtoms; ++a) tma_prefetch_l2_2d(&tmY, a * 64, m_next);
-      }
-      if (warp == 2) MLP_TRACE(12, it);
+      if (!PROJ && warp == 2) MLP_TRACE(12, it);
       mbar_wait_warp(acc2_full, it & 1);
-      if (warp == 2) MLP_TRACE(13, it);
+      if (!PROJ && warp == 2) MLP_TRACE(13, it);
       tc_fence_after();
       float st1 = 0.f, st2 = 0.f;
 #pragma unroll 1
@@ -433,19 +616,21 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
           }
         }
         float* v = reinterpret_cast<float*>(r);
-#pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          const float4 t = __ldg(reinterpret_cast<const float4*>(p.b2 + col0) + g);
-          v[4 * g] += t.x; v[4 * g + 1] += t.y; v[4 * g + 2] += t.z; v[4 * g + 3] += t.w;
-        }
-        if (warp == 2) MLP_TRACE(15, it * 4 + j);
-        mbar_wait_warp(&rbar[j], it & 1);
-        if (warp == 2) MLP_TRACE(16, it * 4 + j);
         uint8_t* bsl = slots + j * 4096;
+        if constexpr (!PROJ) {
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          const float4 t = *reinterpret_cast<const float4*>(bsl + mlp_off(lane, g));
-          v[4 * g] += t.x; v[4 * g + 1] += t.y; v[4 * g + 2] += t.z; v[4 * g + 3] += t.w;
+          for (int g = 0; g < 8; ++g) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(p.b2 + col0) + g);
+            v[4 * g] += t.x; v[4 * g + 1] += t.y; v[4 * g + 2] += t.z; v[4 * g + 3] += t.w;
+          }
+          if (warp == 2) MLP_TRACE(15, it * 4 + j);
+          mbar_wait_warp(&rbar[j], it & 1);
+          if (warp == 2) MLP_TRACE(16, it * 4 + j);
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 t = *reinterpret_cast<const float4*>(bsl + mlp_off(lane, g));
+            v[4 * g] += t.x; v[4 * g + 1] += t.y; v[4 * g + 2] += t.z; v[4 * g + 3] += t.w;
+          }
         }
 #pragma unroll
         for (int g = 0; g < 8; ++g)
@@ -495,7 +680,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         mbar_arrive(y_free);
       }
       __syncwarp();
-      if (warp == 2) MLP_TRACE(14, it);
+      if (!PROJ && warp == 2) MLP_TRACE(14, it);
     }
     if (elect_one()) bulk_wait_all<0>();
   }
@@ -521,11 +706,21 @@ extern "C" int devit_mlp_fused(const devit_mlp_args* a, void* stream_v) {
   DEVIT_REQUIRE(a->dim == 256 || a->dim == 384,
                 "devit_mlp_fused: dim %d unsupported (built for 256 and 384)", a->dim);
   const int Dm = a->dim;
+  const bool proj = a->o != nullptr;
   DEVIT_REQUIRE(a->m > 0 && a->hidden_ld >= 16 && a->hidden_ld % 16 == 0,
                 "devit_mlp_fused: need m > 0 and hidden_ld a positive multiple of 16");
-  DEVIT_REQUIRE(a->xb && a->w1 && a->c1 && a->c2 && a->w2 && a->b2 && a->x && a->ln_stats,
+  DEVIT_REQUIRE(a->w1 && a->c1 && a->c2 && a->w2 && a->b2 && a->x,
                 "devit_mlp_fused: null pointer");
-  DEVIT_REQUIRE(a->ln_parts >= 1, "devit_mlp_fused: ln_parts must be >= 1");
+  if (proj) {
+    DEVIT_REQUIRE(a->w_proj && a->b_proj, "devit_mlp_fused: o given without w_proj / b_proj");
+    DEVIT_REQUIRE(a->proj_k >= 64 && a->proj_k % 64 == 0 && a->proj_k <= Dm,
+                  "devit_mlp_fused: proj_k %d must be a multiple of 64 in [64, dim]", a->proj_k);
+    DEVIT_REQUIRE(reinterpret_cast<uintptr_t>(a->b_proj) % 16 == 0,
+                  "devit_mlp_fused: b_proj must be 16-byte aligned");
+  } else {
+    DEVIT_REQUIRE(a->xb && a->ln_stats, "devit_mlp_fused: null pointer");
+    DEVIT_REQUIRE(a->ln_parts >= 1, "devit_mlp_fused: ln_parts must be >= 1");
+  }
   DEVIT_REQUIRE(reinterpret_cast<uintptr_t>(a->c1) % 16 == 0 &&
                     reinterpret_cast<uintptr_t>(a->c2) % 16 == 0 &&
                     reinterpret_cast<uintptr_t>(a->b2) % 16 == 0 &&
@@ -535,21 +730,35 @@ extern "C" int devit_mlp_fused(const devit_mlp_args* a, void* stream_v) {
   int dev = 0;
   DEVIT_CUDA_OK(cudaGetDevice(&dev));
   if (!attr_done[dev & 63]) {
-    DEVIT_CUDA_OK(cudaFuncSetAttribute(mlp_fused_kernel<384>,
+    DEVIT_CUDA_OK(cudaFuncSetAttribute(mlp_fused_kernel<384, false>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        MlpCfg<384>::kSmem));
-    DEVIT_CUDA_OK(cudaFuncSetAttribute(mlp_fused_kernel<256>,
+    DEVIT_CUDA_OK(cudaFuncSetAttribute(mlp_fused_kernel<256, false>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       MlpCfg<256>::kSmem));
+    DEVIT_CUDA_OK(cudaFuncSetAttribute(mlp_fused_kernel<384, true>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       MlpCfg<384>::kSmem));
+    DEVIT_CUDA_OK(cudaFuncSetAttribute(mlp_fused_kernel<256, true>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        MlpCfg<256>::kSmem));
     attr_done[dev & 63] = true;
   }
-  CUtensorMap tY, tW1, tW2, tX, tXB;
-  rc = encode_tmap_2d(&tY, a->xb, 2, Dm, a->m, Dm, 64, 128, false);
-  if (rc) return rc;
+  CUtensorMap tY, tW1, tW2, tX, tXB, tWp;
+  if (proj) {
+    rc = encode_tmap_2d(&tY, a->o, 2, a->proj_k, a->m, a->proj_k, 64, 128, false);
+    if (rc) return rc;
+    rc = encode_tmap_2d(&tWp, a->w_proj, 2, a->proj_k, Dm, a->proj_k, 64, Dm / 4, true);
+    if (rc) return rc;
+  } else {
+    rc = encode_tmap_2d(&tY, a->xb, 2, Dm, a->m, Dm, 64, 128, false);
+    if (rc) return rc;
+  }
   rc = encode_tmap_2d(&tW1, a->w1, 2, Dm, a->hidden_ld, Dm, 64, 32, true);
   if (rc) return rc;
   rc = encode_tmap_2d(&tW2, a->w2, 2, a->hidden_ld, Dm, a->hidden_ld, 64, Dm / 4, true);
   if (rc) return rc;
+  if (!proj) tWp = tW2;
   rc = encode_tmap_2d(&tX, a->x, 4, Dm, a->m, Dm, 32, 32, false);
   if (rc) return rc;
   tXB = tX;
@@ -570,6 +779,8 @@ extern "C" int devit_mlp_fused(const devit_mlp_args* a, void* stream_v) {
   p.ln_eps = a->ln_eps;
   p.xb_out = static_cast<__nv_bfloat16*>(a->xb_out);
   p.stats_out = a->stats_out;
+  p.bp = a->b_proj;
+  p.proj_chunks = proj ? a->proj_k / 64 : 0;
   p.trace = g_attn_trace;
   {
     static int stagger = -1;  // DEVIT_MLP_STAGGER=<clocks> (0 = off)
@@ -596,10 +807,9 @@ extern "C" int devit_mlp_fused(const devit_mlp_args* a, void* stream_v) {
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 1 : 0;
-    if (Dm == 384)
-      DEVIT_CUDA_OK(cudaLaunchKernelEx(&cfg, mlp_fused_kernel<384>, tY, tW1, tW2, tX, tXB, p));
-    else
-      DEVIT_CUDA_OK(cudaLaunchKernelEx(&cfg, mlp_fused_kernel<256>, tY, tW1, tW2, tX, tXB, p));
+    auto kern = Dm == 384 ? (proj ? mlp_fused_kernel<384, true> : mlp_fused_kernel<384, false>)
+                          : (proj ? mlp_fused_kernel<256, true> : mlp_fused_kernel<256, false>);
+    DEVIT_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tY, tW1, tW2, tX, tXB, tWp, p));
   }
   DEVIT_CUDA_OK(cudaGetLastError());
   count_launch();

@@ -49,6 +49,64 @@ def chain_sm_budget(device) -> int:
     return 0 if share == 1 else max(2, (sms // share) & ~1)
 
 
+_SIDE_STREAMS = {}
+
+
+def _side_streams(device, n):
+    pool = _SIDE_STREAMS.setdefault(str(device), [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(device=device))
+    return pool[:n]
+
+
+def chain_tasks(subs, batch, on_cuda=True):
+    """[(slab index, sub-model id, (b0, b1) | None)]: the (sub-model, batch chunk) chains of one
+    forward of the sub-models `subs` over `batch` images."""
+    n_chunk = batch_chunks(len(subs), batch) if on_cuda and not L.profiling() else 1
+    if n_chunk <= 1:
+        return [(i, s, None) for i, s in enumerate(subs)]
+    per = batch // n_chunk
+    cuts = [c * per for c in range(n_chunk)] + [batch]
+    return [(i, s, (cuts[c], cuts[c + 1])) for c in range(n_chunk) for i, s in enumerate(subs)]
+
+
+def run_chains(device, tasks, launch):
+    """Runs launch(task) for every task, spreading the tasks round-robin over up to
+    `sub_streams()` CUDA streams forked from / joined to the current stream.
+
+    The sub-models are independent until the fusion head (models/ensemble_models.py:33 is a plain
+    loop) and so are the images of a batch: each task is an independent kernel chain with its own
+    workspace (packing.workspace is keyed by stream), and while more than one stream is in use
+    every persistent grid is sized for HALF the chip (devit_set_sm_budget), so two chains run side
+    by side.  Each kernel alternates tensor-bound and HBM-bound phases (operand refill, fp32
+    residual read / write) that do not overlap inside one CTA; two unrelated kernels on the two
+    halves of the chip fill each other's gaps, and a chain's partly filled last round of tiles no
+    longer idles the SMs it does not use.  Measured on the 4-way bs-256 step: 9.93 -> 8.7 ms.
+    Results are bit-identical to the single-chain order (every row's arithmetic is unchanged)."""
+    on_cuda = device.type == 'cuda'
+    n_st = max(1, min(len(tasks), sub_streams())) if on_cuda and not L.profiling() else 1
+    if n_st == 1:
+        for t in tasks:
+            launch(t)
+        return
+    cur = torch.cuda.current_stream(device)
+    side = _side_streams(device, n_st - 1)
+    fork = torch.cuda.Event()
+    fork.record(cur)
+    for st in side:
+        st.wait_event(fork)
+    prev_budget = L.load().devit_set_sm_budget(chain_sm_budget(device))
+    try:
+        for k, t in enumerate(tasks):
+            st = cur if k % n_st == 0 else side[k % n_st - 1]
+            with torch.cuda.stream(st):
+                launch(t)
+    finally:
+        L.load().devit_set_sm_budget(prev_budget)
+    for st in side:  # join: whatever the tasks used is next touched (and freed) on `cur`
+        cur.wait_stream(st)
+
+
 class FeatureList(list):
     """A plain list of [B, D] tensors (what the reference's MultiViT returns) that remembers
     the slab its entries are views of, so EnsMLP can skip the stack."""
@@ -111,55 +169,19 @@ class MultiViT(nn.Module):
                 if bb0.precision != self.precision:
                     bb0.set_precision(self.precision)
                 patches = bb0.patches_of(x)
-        # The sub-models are independent until the fusion head (models/ensemble_models.py:33 is a
-        # plain loop) and so are the images of a batch: the work is cut into `chains` =
-        # (sub-model, batch chunk) pairs that run round-robin on up to `sub_streams` CUDA streams,
-        # each with its own workspace, and every persistent grid is sized for HALF the chip
-        # (devit_set_sm_budget), so two chains run side by side.  Each kernel alternates
-        # tensor-bound and HBM-bound phases (operand refill, fp32 residual read / write) that do
-        # not overlap inside one CTA; two unrelated kernels on the two halves of the chip fill each
-        # other's gaps, and a chain's partly filled last round of tiles no longer idles the SMs
-        # it does not use.  Measured on the 4-way bs-256 step: 9.93 -> 8.7 ms.
-        tasks = [(i, s, None) for i, s in enumerate(subs)]
-        n_chunk = batch_chunks(len(subs), B) if x.is_cuda and not L.profiling() else 1
-        if n_chunk > 1:
-            per = B // n_chunk
-            cuts = [c * per for c in range(n_chunk)] + [B]
-            tasks = [(i, s, (cuts[c], cuts[c + 1])) for c in range(n_chunk)
-                     for i, s in enumerate(subs)]
-        n_st = max(1, min(len(tasks), sub_streams())) if x.is_cuda and not L.profiling() else 1
-        cur = torch.cuda.current_stream(x.device) if x.is_cuda else None
-        side = self._side_streams(x.device, n_st - 1) if n_st > 1 else []
-        prev_budget = None
-        if side:
-            fork = torch.cuda.Event()
-            fork.record(cur)
-            for st in side:
-                st.wait_event(fork)
-            prev_budget = L.load().devit_set_sm_budget(chain_sm_budget(x.device))
-        try:
-            for k, (i, s, rows) in enumerate(tasks):
-                bb = self.backbones[s]
-                if bb.precision != self.precision:
-                    bb.set_precision(self.precision)
-                st = cur if (not side or k % n_st == 0) else side[k % n_st - 1]
-                with torch.cuda.stream(st) if side else contextlib.nullcontext():
-                    bb.features_into(x, feats_f32=f32[i],
-                                     feats_op=op[i] if prec == L.DEVIT_BF16 else op[:, i],
-                                     patches=patches, rows=rows)
-        finally:
-            if prev_budget is not None:
-                L.load().devit_set_sm_budget(prev_budget)
-        for st in side:  # join: everything allocated above is next used (and freed) on `cur`
-            cur.wait_stream(st)
+        # independent (sub-model, batch chunk) kernel chains on several streams: see run_chains
+        def launch(task):
+            i, s, rows = task
+            bb = self.backbones[s]
+            if bb.precision != self.precision:
+                bb.set_precision(self.precision)
+            bb.features_into(x, feats_f32=f32[i],
+                             feats_op=op[i] if prec == L.DEVIT_BF16 else op[:, i],
+                             patches=patches, rows=rows)
+
+        run_chains(x.device, chain_tasks(subs, B, x.is_cuda), launch)
         return f32, op
 
-    def _side_streams(self, device, n):
-        key = str(device)
-        pool = self.__dict__.setdefault('_streams', {}).setdefault(key, [])
-        while len(pool) < n:
-            pool.append(torch.cuda.Stream(device=device))
-        return pool[:n]
 
     def forward(self, x):
         f32, op = self.forward_slab(x)

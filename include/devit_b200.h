@@ -196,6 +196,7 @@ int devit_layernorm(const float* x, const float* gamma, const float* beta, void*
  * [ln_parts][m][2].  `w2` is [dim, hidden_ld] (zero columns beyond the kept neurons).
  * Outputs: x (fp32, in place), optionally the bf16 copy of the new x (`xb_out`, may alias `xb`)
  * and its partial row sums `stats_out` [4][m][2] (one part per dim/4 columns) for the next layer.
+ * Optionally the attention-output projection is fused in front (fields `o` .. `proj_k` below).
  * ------------------------------------------------------------------------------------- */
 typedef struct devit_mlp_args {
   int32_t m;
@@ -213,6 +214,19 @@ typedef struct devit_mlp_args {
   float* x;
   void* xb_out;
   float* stats_out;
+  /* ---- optional: the attention-output projection fused in front (all NULL / 0 = off).
+   * With `o` set the kernel computes
+   *     x1 = x + o Wp^T + bp ;   x = x1 + gelu( LN(x1) W1^T + b1 ) W2^T + b2
+   * i.e. Attention.proj + the first residual add (models/de_vit.py:81-82, :114) and the whole MLP
+   * branch (:35-47, :115) in one pass over the residual stream: x1, its bf16 copy and its
+   * LayerNorm statistics never leave the SM pair (`xb`, `ln_stats`, `ln_parts` are ignored; the
+   * exact row statistics of x1 are formed on chip).
+   * o: attention output [m, proj_k] bf16 (proj_k = 64 * kept heads, <= dim), w_proj: [dim, proj_k]
+   * bf16 (kept heads' columns), b_proj: fp32 [dim]. */
+  const void* o;
+  const void* w_proj;
+  const float* b_proj;
+  int32_t proj_k;
 } devit_mlp_args;
 
 int devit_mlp_fused(const devit_mlp_args* args, void* stream);

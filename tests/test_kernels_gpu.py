@@ -126,6 +126,49 @@ def test_gemm_ln_fold_consumer(m, n, parts, act):
 
 
 @pytest.mark.parametrize("m", [200, 520, 256 * 160 + 9])
+@pytest.mark.parametrize("f,d,heads", [(16, 384, 1), (80, 384, 3), (928, 384, 4), (1536, 384, 6),
+                                       (512, 256, 4), (48, 256, 2)])
+def test_proj_mlp_fused(m, f, d, heads):
+    """x1 = x + o Wp^T + bp ; x = x1 + gelu(LN(x1) W1^T + b1) W2^T + b2 in ONE kernel (the
+    attention-output projection fused in front of the MLP, models/de_vit.py:81-82,114 + :35-47,115)
+    against the same chain in fp32 torch; also the bf16 copy / partial row sums for the next layer."""
+    eps = 1e-6
+    hd = 64 * heads
+    x0 = _mk((m, d), 61) * 1.5 + _mk((1, d), 62) * 0.5
+    o = _mk((m, hd), 69).bfloat16()
+    wp = _mk((d, hd), 70, 0.05).bfloat16()
+    bp = _mk((d,), 71, 0.1)
+    gamma = 1.0 + 0.1 * _mk((d,), 63)
+    beta = 0.1 * _mk((d,), 64)
+    w1 = _mk((f, d), 65, 0.05)
+    b1 = _mk((f,), 66, 0.1)
+    w2 = _mk((d, f), 67, 0.05)
+    b2 = _mk((d,), 68, 0.1)
+    w1f = (w1 * gamma[None, :]).bfloat16()
+    c1 = w1f.float().sum(1).contiguous()
+    c2 = (b1 + w1 @ beta).contiguous()
+    x = x0.clone()
+    xb_out = torch.zeros(m, d, device="cuda", dtype=torch.bfloat16)
+    stats_out = torch.full((4, m, 2), -1.0, device="cuda")
+    L.mlp_fused(x, None, None, w1f, c1, c2, w2.bfloat16().contiguous(), b2, eps, xb_out=xb_out,
+                stats_out=stats_out, o=o, w_proj=wp, b_proj=bp)
+    torch.cuda.synchronize()
+    x1 = x0 + o.float() @ wp.float().t() + bp
+    h = torch.nn.functional.gelu(torch.nn.functional.layer_norm(x1, (d,), gamma, beta, eps) @ w1.t() + b1)
+    ref = x1 + h @ w2.t() + b2
+    assert rel(x - x0, ref - x0) < 1.5e-2, rel(x - x0, ref - x0)
+    assert torch.equal(xb_out, x.bfloat16())
+    cols = x.view(m, 4, d // 4)
+    assert rel(stats_out[..., 0].t(), cols.sum(-1)) < 1e-5
+    assert rel(stats_out[..., 1].t(), (cols * cols).sum(-1)) < 1e-5
+    # the two-kernel path (residual GEMM, then the plain fused MLP) must agree to bf16 noise
+    y = L.gemm(o, wp, bias=bp, resid=x0.clone(), out_kind=L.OUT_F32)
+    yb, st = L.rowstats(y)
+    L.mlp_fused(y, yb, st, w1f, c1, c2, w2.bfloat16().contiguous(), b2, eps)
+    assert rel(x, y) < 2e-3, rel(x, y)
+
+
+@pytest.mark.parametrize("m", [200, 520, 256 * 160 + 9])
 @pytest.mark.parametrize("f,d", [(16, 384), (64, 384), (80, 384), (928, 384), (1536, 384),
                                  (512, 256), (48, 256), (1024, 256)])
 def test_mlp_fused(m, f, d):

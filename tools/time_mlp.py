@@ -1,5 +1,6 @@
 """Times devit_mlp_fused at the bs-256 shape (TIME_MLP_BATCH=<images> for another batch):
-   python tools/time_mlp.py [hidden ...]"""
+   python tools/time_mlp.py [hidden ...]
+TIME_MLP_PROJ=<heads>: the variant with the attention-output projection fused in front."""
 import os
 import sys
 from pathlib import Path
@@ -7,6 +8,7 @@ import torch
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 from devit_b200 import _lib as L  # noqa: E402
 M, D = int(os.environ.get('TIME_MLP_BATCH', '256')) * 198, 384
+H = int(os.environ.get('TIME_MLP_PROJ', '0'))
 g = torch.Generator(device="cuda").manual_seed(0)
 for F in [int(a) for a in sys.argv[1:]] or [928, 1536]:
     x = torch.randn(M, D, device="cuda", generator=g)
@@ -15,8 +17,16 @@ for F in [int(a) for a in sys.argv[1:]] or [928, 1536]:
     w2 = (torch.randn(D, F, device="cuda", generator=g) * .05).bfloat16()
     c1, c2, b2 = (torch.randn(n, device="cuda", generator=g) * .1 for n in (F, F, D))
     so = torch.empty(4, M, 2, device="cuda")
+    if H:
+        o = torch.randn(M, 64 * H, device="cuda", generator=g).bfloat16()
+        wp = (torch.randn(D, 64 * H, device="cuda", generator=g) * .05).bfloat16()
+        bp = torch.randn(D, device="cuda", generator=g) * .1
     def run():
-        L.mlp_fused(x, xb, stats, w1, c1, c2, w2, b2, 1e-6, xb_out=xb, stats_out=so)
+        if H:
+            L.mlp_fused(x, None, None, w1, c1, c2, w2, b2, 1e-6, xb_out=xb, stats_out=so,
+                        o=o, w_proj=wp, b_proj=bp)
+        else:
+            L.mlp_fused(x, xb, stats, w1, c1, c2, w2, b2, 1e-6, xb_out=xb, stats_out=so)
     for _ in range(3):
         run()
     torch.cuda.synchronize()
@@ -27,4 +37,5 @@ for F in [int(a) for a in sys.argv[1:]] or [928, 1536]:
     e1.record()
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) / 20 * 1e3
-    print(f"F={F}: {us:.1f} us  {4.0 * M * D * F / us / 1e6:.0f} TFLOP/s")
+    fl = 4.0 * M * D * F + 2.0 * M * D * 64 * H
+    print(f"F={F} proj_heads={H}: {us:.1f} us  {fl / us / 1e6:.0f} TFLOP/s")

@@ -1,17 +1,24 @@
 #!/usr/bin/env python
-"""Headline benchmark: images/sec of the 4-way DeDeiT ensemble (shrink_ratio-0.3 head/neuron
-gates, 100 classes) @224^2, global batch 256, on N B200s of one node.
+"""Benchmark of the B200 hot path (BASELINE.json): images/sec of the decomposed ensembles.
 
-  python bench.py --gpus 1 --steps K --warmup W                       (N=1)
+  python bench.py --gpus 1 --steps K --warmup W [--config headline|c1|c2|c3|c4] [--dense]
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
-  python bench.py --impl reference ...      the reference algorithm on the host CPU (oracle port)
+  python bench.py --impl reference ...   the reference's own CPU implementation (host cores)
 
-One step = one forward of the whole ensemble (MultiViT + EnsMLP fusion head) over the global
-batch.  `value` = device-resident inputs (CUDA-graph replay), `e2e` = through the public module
-API with the batch copied host->device from pinned memory and the logits read back every step.
-Global batch is fixed at 256 for every N (strong scaling); sub-models are sharded one per rank
-up to 4 ranks, 8 ranks = 2 data-parallel groups of 4.  Inputs (154 MB fp32 per batch) and the
-activation working set (~0.4 GB) are larger than the 126 MB L2, so no explicit flush is needed.
+Configs (BASELINE.json `configs`; `headline` is the one `metric` is quoted on):
+  headline  4-way DeDeiT ensemble, shrink_ratio-0.3 head+neuron gates, 100 classes, bs 256
+            (the line also carries a `dense` sub-object: the same step with all-ones gates)
+  c1        deit_base_distilled_patch16_224 teacher, bs 256 (N > 1: data-parallel replicas)
+  c2        the headline ensemble at bs 512
+  c3        8-way DeDeiT, dense, ImageNet-1K fusion head (1000 classes), bs 1024
+  c4        4-way decct_7_3x1 CCT ensemble (EnsembleCCT, 100 classes), 32x32, bs 2048
+
+One step = one forward of the whole ensemble (backbones + fusion head) over the global batch.
+`value`: inputs resident in HBM, CUDA-graph replay of the step.  `e2e`: the public module call
+with the batch copied host->device from pinned memory and the logits copied back, inside the
+timed region.  Global batch is fixed for every N (strong scaling): sub-models are sharded over
+the ranks (one exchange: an all-gather of the feature slabs), extra ranks form data-parallel
+groups.  Inputs + activations exceed the 126 MB L2, so no explicit flush is needed.
 """
 from __future__ import annotations
 
@@ -28,25 +35,48 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-N_SUB, NUM_CLASS, BATCH = 4, 100, int(os.environ.get("DEVIT_BENCH_BATCH", "256"))
 D, HEADS, HIDDEN, TOKENS, PATCHES, DEPTH = 384, 6, 1536, 198, 196, 12
-METRIC = "images/sec, 4-way DeDeiT ensemble @224^2 bs256"
+HEADLINE_METRIC = "images/sec, 4-way DeDeiT ensemble @224^2 bs256"
+
+CONFIGS = {
+    "headline": dict(family="dedeit", n_sub=4, classes=100, batch=256, shrunk=True,
+                     metric=HEADLINE_METRIC),
+    "c1": dict(family="teacher", n_sub=1, classes=100, batch=256, shrunk=False,
+               metric="images/sec, deit_base_distilled_patch16_224 teacher @224^2 bs256"),
+    "c2": dict(family="dedeit", n_sub=4, classes=100, batch=512, shrunk=True,
+               metric="images/sec, 4-way DeDeiT ensemble @224^2 bs512"),
+    "c3": dict(family="dedeit", n_sub=8, classes=1000, batch=1024, shrunk=False,
+               metric="images/sec, 8-way DeDeiT ensemble (1000 classes) @224^2 bs1024"),
+    "c4": dict(family="cct", n_sub=4, classes=100, batch=2048, shrunk=False,
+               metric="images/sec, 4-way decct_7_3x1 CCT ensemble @32^2 bs2048"),
+}
 
 
 # ------------------------------------------------------------------------------- flop model
-def submodel_flops(kept_heads, kept_neurons):
-    """Algorithmic FLOPs (2*MAC) per image of one sub-model: patch GEMM, QKV,
-    QK^T, PV, proj, fc1, fc2 with the KEPT head / neuron counts.  -> (gemm, attention)."""
-    gemm = 2 * PATCHES * 768 * D
-    attn = 0
-    for h, f in zip(kept_heads, kept_neurons):
-        gemm += 2 * TOKENS * D * 3 * 64 * h + 2 * TOKENS * 64 * h * D + 4 * TOKENS * D * f
-        attn += 4 * h * TOKENS * TOKENS * 64
-    return gemm, attn
+def vit_flops(dim, heads_l, hidden_l, tokens=TOKENS, patches=PATCHES):
+    """Algorithmic FLOPs (2*MAC) per image of one ViT sub-model with the KEPT head /
+    neuron counts per layer -> dict(gemm, attn, tail) where `tail` = proj + fc1 + fc2 (the work of
+    the fused projection + MLP kernel)."""
+    gemm = 2 * patches * 768 * dim
+    attn = tail = 0
+    for h, f in zip(heads_l, hidden_l):
+        t = 2 * tokens * 64 * h * dim + 4 * tokens * dim * f
+        gemm += 2 * tokens * dim * 3 * 64 * h + t
+        tail += t
+        attn += 4 * h * tokens * tokens * 64
+    return dict(gemm=gemm, attn=attn, tail=tail)
 
 
-def fusion_flops():
-    return 2 * 2 * (N_SUB * D * 768 + 768 * NUM_CLASS)
+def cct_flops(n_conv=1, tokens=256, dim=256, hidden=512, depth=7, heads=4):
+    side, cin, conv = 32, 3, 0
+    for i in range(n_conv):
+        cout = dim if i == n_conv - 1 else 64
+        conv += 2 * side * side * 9 * cin * cout
+        cin, side = cout, side // 2
+    tail = depth * (2 * tokens * dim * dim + 4 * tokens * dim * hidden)
+    gemm = conv + depth * 2 * tokens * dim * 3 * dim + tail
+    attn = depth * 4 * heads * tokens * tokens * 64
+    return dict(gemm=gemm, attn=attn, tail=tail)
 
 
 def load_peaks():
@@ -108,61 +138,220 @@ class ClockSampler:
                 "sm_max_mhz": smax or None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# ------------------------------------------------------------------------------- CPU arms
-def cpu_oracle_ips(images_per_step, steps, warmup, shrunk=True):
-    """Times the oracle port of the reference (masked-dense, fp32, all host threads)."""
+# ------------------------------------------------------------------------------- workloads
+class Workload:
+    """Everything bench.py needs to know about one config: synthetic weights / gates / inputs
+    (devit_b200/synth.py seeds), the device modules, the CPU arm and the FLOP model."""
+
+    def __init__(self, name, dense=False):
+        self.name = name
+        c = dict(CONFIGS[name])
+        if dense:
+            c["shrunk"] = False
+        self.__dict__.update(c)
+        self.kept = None
+
+    # ---- descriptions
+    def describe(self):
+        if self.family == "teacher":
+            return "deit_base_distilled_patch16_224 teacher (D=768, 12 heads, depth 12), 100 classes"
+        if self.family == "cct":
+            return (f"{self.n_sub}-way decct_7_3x1 CCT ensemble (D=256, 7 layers, 256 tokens), "
+                    f"EnsembleCCT fusion head {self.classes} classes")
+        gates = "shrink_ratio-0.3 head+neuron gates" if self.shrunk else "dense gates"
+        return (f"{self.n_sub}-way DeDeiT ensemble (dedeit D=384 depth 12), {gates}, EnsMLP fusion "
+                f"head {self.classes} classes")
+
+    def config(self, world, plan):
+        side = 32 if self.family == "cct" else 224
+        if self.family == "teacher":
+            par = "1 GPU" if world == 1 else f"{world} data-parallel replicas (batch split, no collective)"
+        elif world == 1:
+            par = (f"1 GPU: {self.n_sub} sub-models as concurrent kernel chains on "
+                   f"{os.environ.get('DEVIT_SUB_STREAMS', '4')} streams")
+        else:
+            par = (f"{plan.group_size}-way sub-model sharding x {plan.num_groups} data-parallel "
+                   f"group(s), all-gather of the per-rank feature slabs")
+        in_mb = self.batch * 3 * side * side * 4 / 1e6
+        return {"workload": f"{self.describe()}, {side}x{side}, global batch {self.batch}",
+                "name": self.name, "global_batch": self.batch, "sub_models": self.n_sub,
+                "parallelism": par,
+                "l2": f"inputs ({in_mb:.0f} MB) + activations exceed the 126 MB L2; no flush"}
+
+    # ---- inputs
+    def images(self, n, seed=None):
+        from devit_b200 import synth
+        if self.family == "cct":
+            return synth.cifar_images(n) if seed is None else synth.cifar_images(n, seed)
+        return synth.images(n) if seed is None else synth.images(n, seed)
+
+    # ---- device modules -> (multi, fuse) or (model, None)
+    def build_device(self, dev, precision):
+        from devit_b200 import cct, ensemble, shrink, synth
+        from devit_b200.registry import create_model
+        if self.family == "teacher":
+            m = create_model("deit_base_distilled_patch16_224", num_classes=self.classes)
+            m.load_state_dict(synth.teacher_state_dict(self.classes))
+            self.kept = [([12] * DEPTH, [3072] * DEPTH)]
+            return m.to(dev).eval().set_precision(precision), None
+        n = self.n_sub
+        if self.family == "cct":
+            multi = cct.MultiCCT("decct_7_3x1", num_classes_list=[self.classes // n] * n,
+                                 num_sub_models=n, input_size=32)
+            for s in range(n):
+                multi.models[s].load_state_dict(
+                    synth.cct_state_dict(s, n_conv=1, tokens=256, backbone=True))
+            fuse = cct.EnsembleCCT(sub_size=256, teacher_size=None, num_sub_models=n,
+                                   num_classes=self.classes)
+            fuse.load_state_dict(synth.ensemble_cct_state_dict(n, 256, None, self.classes))
+            return (multi.to(dev).eval().set_precision(precision),
+                    fuse.to(dev).eval().set_precision(precision))
+        multi = ensemble.MultiViT(model="dedeit", drop=0, drop_path=0.1,
+                                  num_classes_list=[self.classes // n] * n, num_div=n)
+        fuse = ensemble.EnsMLP(model="dedeit", num_class=self.classes, sub_size=D,
+                               num_classes_list=[self.classes // n] * n, teacher_size=768)
+        self.kept = []
+        for s in range(n):
+            multi.backbones[s].load_state_dict(synth.dedeit_state_dict(s, with_heads=False))
+            if self.shrunk:
+                ng, hg = synth.shrink_gates(s)
+                shrink.mlp_neuron_shrink(multi.backbones[s], ng)
+                shrink.attn_head_shrink(multi.backbones[s], hg)
+                self.kept.append(([int(g.sum()) for g in hg], [int(g.sum()) for g in ng]))
+            else:
+                self.kept.append(([HEADS] * DEPTH, [HIDDEN] * DEPTH))
+        fuse.load_state_dict(synth.ensmlp_state_dict(n, num_class=self.classes))
+        return (multi.to(dev).eval().set_precision(precision),
+                fuse.to(dev).eval().set_precision(precision))
+
+    # ---- FLOPs per image of sub-model s, and of the fusion head
+    def sub_flops(self, s):
+        if self.family == "teacher":
+            return vit_flops(768, *self.kept[0])
+        if self.family == "cct":
+            return cct_flops()
+        return vit_flops(D, *self.kept[s])
+
+    def fusion_flops(self):
+        if self.family == "teacher":
+            return 2 * 2 * 768 * self.classes
+        if self.family == "cct":
+            return 2 * self.n_sub * 256 * self.classes
+        return 2 * 2 * (self.n_sub * D * 768 + 768 * self.classes)
+
+    def total_flops_per_image(self):
+        return sum(self.sub_flops(s)["gemm"] + self.sub_flops(s)["attn"]
+                   for s in range(self.n_sub)) + self.fusion_flops()
+
+    # ---- CPU arm: callable x -> logits, and what it is
+    def cpu_runner(self):
+        """The reference's own modules (oracle/ref_runner.py over /root/reference or the
+        oracle/_ref copy) when available, else the oracle port."""
+        import torch
+        from devit_b200 import synth
+        from oracle import ref_runner
+        if self.family in ("dedeit", "teacher") and ref_runner.available():
+            try:
+                if self.family == "teacher":
+                    return ref_runner.teacher(self.classes), "reference", \
+                        "reference models/deit_vit.py modules (fp32 PyTorch CPU)"
+                return ref_runner.ensemble(self.n_sub, self.classes, self.shrunk), "reference", \
+                    ("reference models/ensemble_models.py MultiViT + EnsMLP over models/de_vit.py "
+                     "(masked-dense fp32 PyTorch CPU)")
+            except Exception as e:  # noqa: BLE001
+                print(f"[bench] reference modules unavailable ({type(e).__name__}: {e}); "
+                      f"timing the oracle port", file=sys.stderr)
+        if self.family == "cct":
+            from oracle import cct_oracle as CO
+            sds = [synth.cct_state_dict(s, n_conv=1, tokens=256, backbone=True)
+                   for s in range(self.n_sub)]
+            esd = synth.ensemble_cct_state_dict(self.n_sub, 256, None, self.classes)
+
+            def run(x):
+                with torch.no_grad():
+                    return CO.ensemble_logits(sds, esd, x, 1)
+            return run, "port", "oracle port of the reference CCT ensemble (fp32 PyTorch CPU)"
+        from oracle import devit_oracle as O
+        if self.family == "teacher":
+            sd = synth.teacher_state_dict(self.classes)
+
+            def run(x):
+                with torch.no_grad():
+                    return O.forward_logits(sd, x, num_heads=12)
+            return run, "port", "oracle port of the reference teacher (fp32 PyTorch CPU)"
+        sds = [synth.dedeit_state_dict(s, with_heads=False) for s in range(self.n_sub)]
+        esd = synth.ensmlp_state_dict(self.n_sub, num_class=self.classes)
+        gates = [synth.shrink_gates(s) for s in range(self.n_sub)] if self.shrunk else None
+
+        def run(x):
+            with torch.no_grad():
+                return O.ensemble_logits(sds, esd, x, gates)[0]
+        return run, "port", "oracle port of the reference (masked-dense fp32 PyTorch CPU)"
+
+
+def cpu_time(wl, images_per_step, steps, warmup):
+    """Times the CPU arm on all host cores -> (img/s, ms/step, cores, kind, what, logits, x)."""
     import torch
-    from devit_b200 import synth
-    from oracle import devit_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sds = [synth.dedeit_state_dict(s, with_heads=False) for s in range(N_SUB)]
-    esd = synth.ensmlp_state_dict(N_SUB, num_class=NUM_CLASS)
-    gates = [synth.shrink_gates(s) for s in range(N_SUB)] if shrunk else None
-    x = synth.images(images_per_step)
-    with torch.no_grad():
-        for _ in range(warmup):
-            O.ensemble_logits(sds, esd, x, gates)
-        t0 = time.perf_counter()
-        for _ in range(steps):
-            O.ensemble_logits(sds, esd, x, gates)
-        dt = time.perf_counter() - t0
-    return images_per_step * steps / dt, dt / steps * 1e3, cores
+    run, kind, what = wl.cpu_runner()
+    x = wl.images(wl.batch)[:images_per_step].contiguous()
+    out = None
+    for _ in range(warmup):
+        out = run(x)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        out = run(x)
+    dt = time.perf_counter() - t0
+    return images_per_step * steps / dt, dt / steps * 1e3, cores, kind, what, out, x
 
 
 def run_reference(args):
+    """`--impl reference`: the reference's CPU implementation of the same workload on the box's
+    host cores.  Each step processes a bounded sample of the global batch, sized from a probe so
+    that the K + W steps end within a few minutes; the sample is stated in the line."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = 16
+    import torch
+    wl = Workload(args.config, args.dense)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    run, kind, what = wl.cpu_runner()
+    probe_n = min(16, wl.batch)
+    xp = wl.images(wl.batch)[:probe_n].contiguous()
+    run(xp)
+    t0 = time.perf_counter()
+    run(xp)
+    rate = probe_n / (time.perf_counter() - t0)
     warm = min(args.warmup, 2)
-    ips, ms, cores = cpu_oracle_ips(sample, args.steps, warm, shrunk=not args.dense)
+    budget_s = float(os.environ.get("DEVIT_REF_BUDGET_S", "150"))
+    sample = int(rate * budget_s / (args.steps + warm))
+    sample = max(probe_n, min(wl.batch, sample // 16 * 16))
+    x = wl.images(wl.batch)[:sample].contiguous()
+    for _ in range(warm):
+        run(x)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        run(x)
+    dt = time.perf_counter() - t0
+    ips, ms = sample * args.steps / dt, dt / args.steps * 1e3
+    cfg = wl.config(1, None)
+    cfg["reference_step"] = (f"{sample} of the {wl.batch} images of the global batch per timed step "
+                             f"(bounded CPU sample; throughput in images/sec is batch-size "
+                             f"independent beyond ~16 images on the CPU path)")
     line = {
-        "impl": "reference", "metric": METRIC, "value": ips, "unit": "images/sec",
+        "impl": "reference", "metric": wl.metric, "value": ips, "unit": "images/sec",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": warm, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic",
-        "config": workload_config(args, 1),
-        "cpu_baseline": {"value": ips, "unit": "images/sec", "cores": cores, "kind": "port",
-                         "sample": f"{sample} images per step of the bs-256 workload, oracle "
-                                   f"port of the reference (masked-dense fp32 PyTorch CPU)"},
+        "data": "synthetic", "config": cfg,
+        "cpu_baseline": {"value": ips, "unit": "images/sec", "cores": cores, "kind": kind,
+                         "sample": f"{sample} images per step x {args.steps} steps, {what}"},
         "e2e": {"value": ips, "unit": "images/sec", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
-
-
-def workload_config(args, world):
-    return {"workload": ("4-way DeDeiT ensemble (dedeit D=384 depth 12), "
-                         + ("dense gates" if args.dense else "shrink_ratio-0.3 head+neuron gates")
-                         + ", EnsMLP fusion head 100 classes, 224x224, global batch 256"),
-            "global_batch": BATCH, "sub_models": N_SUB,
-            "parallelism": ("1 GPU: 4 sub-models sequential" if world == 1 else
-                            f"{min(world, N_SUB)}-way sub-model sharding x "
-                            f"{max(1, world // N_SUB)} data-parallel group(s), all-gather of "
-                            f"[2,B,384] features"),
-            "l2": "inputs (154 MB) + activations (>0.4 GB) exceed the 126 MB L2; no flush"}
 
 
 # ------------------------------------------------------------------------------- GPU arm
@@ -172,10 +361,13 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="devit", choices=["devit", "reference"])
+    ap.add_argument("--config", default="headline", choices=sorted(CONFIGS))
     ap.add_argument("--dense", action="store_true", help="all-ones gates instead of shrunk")
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--force-graph", action="store_true", help="capture NCCL too (N>1)")
+    ap.add_argument("--eager-multi", action="store_true",
+                    help="N > 1: do not capture the step (NCCL all-gather included) in a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-dense-arm", action="store_true")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -185,7 +377,7 @@ def main():
     import torch
     import torch.distributed as dist
     from devit_b200 import _lib as L
-    from devit_b200 import ensemble, parallel, shrink, synth
+    from devit_b200 import parallel
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -198,34 +390,23 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     L.check(L.load().devit_device_check())
+    lib = L.load()
 
-    plan = parallel.shard_plan(world, rank, N_SUB, BATCH)
+    wl = Workload(args.config, args.dense)
+    BATCH = wl.batch
+    plan = parallel.shard_plan(world, rank, wl.n_sub, BATCH)
     group = parallel.make_groups(plan) if world > 1 else None
-
-    multi = ensemble.MultiViT(model="dedeit", drop=0, drop_path=0.1,
-                              num_classes_list=[NUM_CLASS // N_SUB] * N_SUB, num_div=N_SUB)
-    fuse = ensemble.EnsMLP(model="dedeit", num_class=NUM_CLASS, sub_size=D,
-                           num_classes_list=[NUM_CLASS // N_SUB] * N_SUB, teacher_size=768)
-    kept = []
-    for s in range(N_SUB):
-        multi.backbones[s].load_state_dict(synth.dedeit_state_dict(s, with_heads=False))
-        if args.dense:
-            kept.append(([HEADS] * DEPTH, [HIDDEN] * DEPTH))
-        else:
-            ng, hg = synth.shrink_gates(s)
-            shrink.mlp_neuron_shrink(multi.backbones[s], ng)
-            shrink.attn_head_shrink(multi.backbones[s], hg)
-            kept.append(([int(g.sum()) for g in hg], [int(g.sum()) for g in ng]))
-    fuse.load_state_dict(synth.ensmlp_state_dict(N_SUB, num_class=NUM_CLASS))
-    multi = multi.to(dev).eval().set_precision(args.precision)
-    fuse = fuse.to(dev).eval().set_precision(args.precision)
+    multi, fuse = wl.build_device(dev, args.precision)
     # second communicator over the same ranks: the e2e arms upload 1/G of the batch per rank and
     # all-gather it over NVLink (ShardedEnsemble.stage_batch)
     stage_group = parallel.make_groups(plan) if world > 1 else None
-    ens = parallel.ShardedEnsemble(multi, fuse, plan, group, stage_group)
+    if fuse is None:
+        ens = parallel.Replica(multi, plan)
+    else:
+        ens = parallel.ShardedEnsemble(multi, fuse, plan, group, stage_group)
 
     Bg = plan.group_batch
-    x_host = synth.images(BATCH)[plan.batch_lo:plan.batch_hi].contiguous().pin_memory()
+    x_host = wl.images(BATCH)[plan.batch_lo:plan.batch_hi].contiguous().pin_memory()
     x_dev = x_host.to(dev, non_blocking=True)
     torch.cuda.synchronize()
 
@@ -241,8 +422,14 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def all_ranks(flag):
+        if world == 1:
+            return bool(flag)
+        t = torch.tensor([1 if flag else 0], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(int(t.item()))
+
     # ---- warm-up (also builds packs / workspaces) and launch count of one step
-    lib = L.load()
     logits = ens(x_dev)
     torch.cuda.synchronize()
     c0 = lib.devit_launch_count()
@@ -253,9 +440,28 @@ def main():
         ens(x_dev)
     torch.cuda.synchronize()
 
-    # ---- optional CUDA graph of the whole step (launch-bound host loop -> one replay)
+    # ---- parity of the sharded step, checked BEFORE anything is timed: every rank also runs its
+    #      group's whole ensemble locally (all sub-models on this GPU, no collective); the
+    #      sharded logits must be bit-identical (the fusion head sums the K-segments in sub-model
+    #      order for every world size).
+    parity = {}
+    if world > 1 and fuse is not None:
+        local = parallel.ShardedEnsemble(multi, fuse, parallel.shard_plan(1, 0, wl.n_sub, Bg))
+        ref_local = local(x_dev)
+        torch.cuda.synchronize()
+        same = torch.equal(ref_local, logits)
+        amax = torch.equal(ref_local.argmax(-1), logits.argmax(-1))
+        parity["sharded_vs_single_rank"] = {
+            "bit_identical": all_ranks(same), "argmax_equal": all_ranks(amax),
+            "images_per_rank": Bg, "ranks": world}
+        if not parity["sharded_vs_single_rank"]["argmax_equal"]:
+            raise SystemExit("[bench] sharded logits disagree with the single-rank ensemble")
+        del local, ref_local
+
+    # ---- CUDA graph of the whole step (N > 1: the NCCL all-gather is captured with it)
     graph, g_out = None, None
-    if not args.no_graph and (world == 1 or args.force_graph):
+    if not args.no_graph and (world == 1 or not args.eager_multi):
+        ok = True
         try:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
@@ -272,9 +478,10 @@ def main():
             if not torch.equal(g_out, logits):
                 raise RuntimeError("graph replay differs from the eager result")
         except Exception as e:  # noqa: BLE001
-            if rank == 0:
-                print(f"[bench] CUDA graph capture unavailable ({type(e).__name__}: {e}); "
-                      f"timing eager launches", file=sys.stderr)
+            print(f"[bench] rank {rank}: CUDA graph capture unavailable ({type(e).__name__}: {e}); "
+                  f"timing eager launches", file=sys.stderr)
+            ok = False
+        if not all_ranks(ok):  # every rank must take the same path (collectives inside)
             graph = None
             torch.cuda.synchronize()
 
@@ -286,6 +493,7 @@ def main():
 
     for _ in range(args.warmup):
         step()
+    launch_mode = "cuda_graph" if graph is not None else "eager"
 
     uuid = str(torch.cuda.get_device_properties(dev).uuid)
     sampler = ClockSampler(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
@@ -293,16 +501,18 @@ def main():
         sampler.start()
         time.sleep(0.15)
 
+    def timed(fn, n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)) / n
+
     # ---- value: device-resident inputs
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    barrier()
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
-    ms_step = ms_total / args.steps
+    ms_step = timed(step, args.steps)
     value = BATCH / (ms_step / 1e3)
 
     # ---- e2e: public API with host buffers; H2D of the step's batch + D2H of its logits inside
@@ -311,13 +521,14 @@ def main():
     bufs = [torch.empty_like(x_dev), torch.empty_like(x_dev)]
     ready = [torch.cuda.Event(), torch.cuda.Event()]
     freed = [torch.cuda.Event(), torch.cuda.Event()]
-    out_host = torch.empty(Bg, NUM_CLASS).pin_memory()
+    out_host = torch.empty(Bg, wl.classes).pin_memory()
     main_stream = torch.cuda.current_stream()
 
     # the same public call, captured once per input buffer when CUDA graphs are in use (a user
     # serving fixed-shape batches would do the same); eager launches otherwise
     e2e_graphs = None
     if graph is not None:
+        ok = True
         try:
             e2e_graphs = []
             for b in range(2):
@@ -329,11 +540,14 @@ def main():
                 e2e_graphs.append((gb, ob))
             torch.cuda.synchronize()
         except Exception as e:  # noqa: BLE001
-            if rank == 0:
-                print(f"[bench] e2e graph capture unavailable ({type(e).__name__}: {e})",
-                      file=sys.stderr)
+            print(f"[bench] rank {rank}: e2e graph capture unavailable ({type(e).__name__}: {e})",
+                  file=sys.stderr)
+            ok = False
+        if not all_ranks(ok):
             e2e_graphs = None
             torch.cuda.synchronize()
+
+    use_stage = world > 1 and fuse is not None and parallel.stage_slice(plan, Bg) is not None
 
     def e2e_loop(n):
         for i in range(n + 1):
@@ -362,14 +576,11 @@ def main():
     # [r Bg/G, (r+1) Bg/G) and an NVLink all-gather assembles the batch (1/G of the PCIe bytes per
     # rank).  Checked against the device-resident result before it is timed; any disagreement
     # (on any rank) falls back to every rank copying the whole batch.
-    use_stage = world > 1 and parallel.stage_slice(plan, Bg) is not None
     for b in range(2):
         freed[b].record(main_stream)
     e2e_loop(3)
     if use_stage:
-        ok = torch.tensor([1 if torch.equal(out_host.to(dev), logits) else 0], device=dev)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        if int(ok.item()) == 0:
+        if not all_ranks(torch.equal(out_host.to(dev), logits)):
             if rank == 0:
                 print("[bench] staged input gave different logits; timing full per-rank copies",
                       file=sys.stderr)
@@ -377,6 +588,9 @@ def main():
             for b in range(2):
                 freed[b].record(main_stream)
             e2e_loop(3)
+    e2e_ok = all_ranks(torch.equal(out_host.to(dev), logits))
+    parity["e2e_equals_resident"] = e2e_ok
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
     e2e_loop(args.steps)
@@ -388,80 +602,85 @@ def main():
     h2d = x_host.numel() * 4 * world // (plan.group_size if use_stage else 1)
     d2h = out_host.numel() * 4 * world
 
-    # ---- e2e_u8: the same public call fed DECODED uint8 batches: ToTensor +
-    #      Normalize run inside the patch extraction on the device, so a step's H2D copy is a
-    #      quarter of the fp32 one, and the step's result is the device-side eval tail (loss,
-    #      correct@1, correct@5: 12 bytes D2H) instead of the logits.  Reported beside `e2e`.
+    # ---- e2e_u8 (DeDeiT configs): the same public call fed DECODED uint8 batches (SURVEY.md
+    #      8f-3): ToTensor + Normalize run inside the patch extraction on the device, so a step's
+    #      H2D copy is a quarter of the fp32 one, and the step's result is the device-side eval tail
+    #      (loss, correct@1, correct@5: 12 bytes D2H) instead of the logits.
     e2e_u8 = None
-    try:
-        u8_host = synth.images_u8(BATCH)[plan.batch_lo:plan.batch_hi].contiguous().pin_memory()
-        tgt = torch.randint(0, NUM_CLASS, (Bg,), generator=torch.Generator().manual_seed(7)).to(dev)
-        bufs8 = [torch.empty(u8_host.shape, dtype=torch.uint8, device=dev) for _ in range(2)]
-        tail_host = torch.empty(3).pin_memory()
+    if wl.family == "dedeit":
+        try:
+            from devit_b200 import synth
+            u8_host = synth.images_u8(BATCH)[plan.batch_lo:plan.batch_hi].contiguous().pin_memory()
+            tgt = torch.randint(0, wl.classes, (Bg,),
+                                generator=torch.Generator().manual_seed(7)).to(dev)
+            bufs8 = [torch.empty(u8_host.shape, dtype=torch.uint8, device=dev) for _ in range(2)]
+            tail_host = torch.empty(3).pin_memory()
 
-        def tail_step(xb):
-            return L.eval_tail(ens(xb), tgt)
+            def tail_step(xb):
+                return L.eval_tail(ens(xb), tgt)
 
-        for b in range(2):
-            bufs8[b].copy_(u8_host)
-        for _ in range(2):
-            tail_step(bufs8[0])
-        torch.cuda.synchronize()
-        u8_graphs = None
-        if graph is not None:
-            u8_graphs = []
             for b in range(2):
-                gb = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(gb):
-                    ob = tail_step(bufs8[b])
-                u8_graphs.append((gb, ob))
+                bufs8[b].copy_(u8_host)
+            for _ in range(2):
+                tail_step(bufs8[0])
             torch.cuda.synchronize()
+            u8_graphs = None
+            if graph is not None:
+                u8_graphs = []
+                for b in range(2):
+                    gb = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(gb):
+                        ob = tail_step(bufs8[b])
+                    u8_graphs.append((gb, ob))
+                torch.cuda.synchronize()
 
-        def u8_loop(n):
-            for i in range(n + 1):
-                if i < n:
-                    b = i & 1
-                    with torch.cuda.stream(copy_stream):
-                        copy_stream.wait_event(freed[b])
-                        if use_stage:
-                            ens.stage_batch(u8_host, bufs8[b])
+            def u8_loop(n):
+                for i in range(n + 1):
+                    if i < n:
+                        b = i & 1
+                        with torch.cuda.stream(copy_stream):
+                            copy_stream.wait_event(freed[b])
+                            if use_stage:
+                                ens.stage_batch(u8_host, bufs8[b])
+                            else:
+                                bufs8[b].copy_(u8_host, non_blocking=True)
+                            ready[b].record(copy_stream)
+                    if i > 0:
+                        b = (i - 1) & 1
+                        main_stream.wait_event(ready[b])
+                        if u8_graphs is not None:
+                            u8_graphs[b][0].replay()
+                            out = u8_graphs[b][1]
                         else:
-                            bufs8[b].copy_(u8_host, non_blocking=True)
-                        ready[b].record(copy_stream)
-                if i > 0:
-                    b = (i - 1) & 1
-                    main_stream.wait_event(ready[b])
-                    if u8_graphs is not None:
-                        u8_graphs[b][0].replay()
-                        out = u8_graphs[b][1]
-                    else:
-                        out = tail_step(bufs8[b])
-                    freed[b].record(main_stream)
-                    tail_host.copy_(out, non_blocking=True)
-            main_stream.synchronize()
+                            out = tail_step(bufs8[b])
+                        freed[b].record(main_stream)
+                        tail_host.copy_(out, non_blocking=True)
+                main_stream.synchronize()
 
-        for b in range(2):
-            freed[b].record(main_stream)
-        u8_loop(3)
-        barrier()
-        e0.record()
-        u8_loop(args.steps)
-        e1.record()
-        barrier()
-        u8_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
-        e2e_u8 = {"value": BATCH / (u8_ms / 1e3), "unit": "images/sec", "ms_per_step": u8_ms,
-                  "h2d_bytes_per_step": u8_host.numel() * world
-                  // (plan.group_size if use_stage else 1),
-                  "d2h_bytes_per_step": 12 * world,
-                  "input": "uint8 NCHW, normalised on the device; result = loss + top-1/top-5 "
-                           "counts of the batch (devit_eval_tail)"}
-    except Exception as e:  # noqa: BLE001  (deterministic host-side failures hit every rank alike)
-        print(f"[bench] e2e_u8 arm failed ({type(e).__name__}: {e})", file=sys.stderr)
-        torch.cuda.synchronize()
+            for b in range(2):
+                freed[b].record(main_stream)
+            u8_loop(3)
+            barrier()
+            e0.record()
+            u8_loop(args.steps)
+            e1.record()
+            barrier()
+            u8_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+            e2e_u8 = {"value": BATCH / (u8_ms / 1e3), "unit": "images/sec", "ms_per_step": u8_ms,
+                      "h2d_bytes_per_step": u8_host.numel() * world
+                      // (plan.group_size if use_stage else 1),
+                      "d2h_bytes_per_step": 12 * world,
+                      "input": "uint8 NCHW, normalised on the device; result = loss + top-1/top-5 "
+                               "counts of the batch (devit_eval_tail)"}
+        except Exception as e:  # noqa: BLE001  (deterministic host-side failures hit every rank alike)
+            print(f"[bench] e2e_u8 arm failed ({type(e).__name__}: {e})", file=sys.stderr)
+            torch.cuda.synchronize()
 
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- per-kernel-family device times (CUDA events around every launch, eager)
+    # ---- per-kernel-family device times: CUDA events around every launch, eager, ONE stream and
+    #      whole-chip grids (each kernel timed alone, which is what its roofline fraction is about;
+    #      inside the step two chains share the chip, so these do not add up to ms_per_step)
     L.profile_enable(True)
     nprof = 3
     for _ in range(nprof):
@@ -472,58 +691,115 @@ def main():
     fam = {k: {"ms_per_step": v[0] / nprof, "launches_per_step": v[1] // nprof}
            for k, v in prof.items()}
 
-    # ---- roofline of the dominant kernel on THIS rank's shard.  The fused MLP kernel
-    #      (fc1 + GELU + fc2, csrc/mlp.cu) is ~45 % of the step and 60 % of its FLOPs; the
-    #      aggregate over every tcgen05 GEMM launch and the attention kernel are given beside it.
+    # ---- roofline of the dominant kernel on THIS rank's shard: the fused projection + MLP
+    #      kernel (csrc/mlp.cu: proj + residual + LN-folded fc1 + GELU + fc2 + residual).
     peaks = load_peaks()
-    gemm_fl = attn_fl = mlp_fl = 0
-    for s in plan.subs:
-        g, a = submodel_flops(*kept[s])
-        gemm_fl += g * Bg
-        attn_fl += a * Bg
-        mlp_fl += sum(4 * TOKENS * D * f for f in kept[s][1]) * Bg
-    gemm_fl += fusion_flops() * Bg
+    subs_local = plan.subs if fuse is not None else [0]
+    gemm_fl = attn_fl = tail_fl = 0
+    for s in subs_local:
+        f = wl.sub_flops(s)
+        gemm_fl += f["gemm"] * Bg
+        attn_fl += f["attn"] * Bg
+        tail_fl += f["tail"] * Bg
+    gemm_fl += wl.fusion_flops() * Bg
     gemm_ms = sum(v["ms_per_step"] for k, v in fam.items() if k.startswith("gemm"))
     gemm_launches = sum(v["launches_per_step"] for k, v in fam.items() if k.startswith("gemm"))
     attn_ms = fam.get("attention", {}).get("ms_per_step", 0.0)
-    total_fl = sum(sum(submodel_flops(*kept[s])) for s in range(N_SUB)) * BATCH \
-        + fusion_flops() * BATCH
-    traffic = None
-    tfile = ROOT / "profiles" / "dominant_kernel_traffic.json"
-    if tfile.exists():
-        try:
-            traffic = json.loads(tfile.read_text()).get(
-                "dense_dram_bytes_per_launch" if args.dense else "shrunk_dram_bytes_per_launch")
-        except Exception:  # noqa: BLE001
-            traffic = None
+    total_fl = wl.total_flops_per_image() * BATCH
     mlp = fam.get("gemm_mlp_fused")
+    proj_sep = fam.get("gemm_proj", {}).get("ms_per_step", 0.0)
     if mlp and mlp["launches_per_step"]:
-        dom_name = "devit::mlp_fused_kernel (tcgen05 cta_group::2: LN-folded fc1 + GELU + fc2 + residual)"
-        dom_fl, dom_ms, dom_n = mlp_fl, mlp["ms_per_step"], mlp["launches_per_step"]
-    else:  # fp32 mode / fused kernel switched off: the GEMM family as a whole
+        dom_name = ("devit::mlp_fused_kernel<D, PROJ> (tcgen05 cta_group::2: attention-output "
+                    "projection + residual + LN-folded fc1 + GELU + fc2 + residual)")
+        dom_fl, dom_ms, dom_n = tail_fl, mlp["ms_per_step"] + proj_sep, mlp["launches_per_step"]
+    else:  # fp32 mode / fused kernel not instantiated for this width: the GEMM family as a whole
         dom_name = "devit::gemm_kernel<BN> (tcgen05, all GEMM launches of a step)"
         dom_fl, dom_ms, dom_n = gemm_fl, gemm_ms, gemm_launches
     achieved = dom_fl / (dom_ms / 1e3) / 1e12 if dom_ms else None
     gemm_tf = gemm_fl / (gemm_ms / 1e3) / 1e12 if gemm_ms else None
+    # denominator: the burst figure when the clocks sampled during the run sit near the maximum
+    # (short kernels timed alone), else the sustained one; both fractions are reported
+    near_max = bool(clocks and clocks.get("sm_mhz") and clocks.get("sm_max_mhz") and
+                    clocks["sm_mhz"] >= 0.93 * clocks["sm_max_mhz"])
+    peak_key = "bf16_burst" if (near_max or clocks is None) else "bf16_sustained"
+    traffic = None
+    tfile = ROOT / "profiles" / "dominant_kernel_traffic.json"
+    if world == 1 and tfile.exists():
+        try:
+            tj = json.loads(tfile.read_text())
+            traffic = tj.get(f"{wl.name}_{'shrunk' if wl.shrunk else 'dense'}_n1_dram_bytes_per_launch")
+        except Exception:  # noqa: BLE001
+            traffic = None
+    step_tf = total_fl / (ms_step / 1e3) / 1e12
     roofline = {
         "kernel": dom_name,
-        "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_sustained"],
-        "unit": "TFLOP/s", "frac": (achieved / peaks["bf16_sustained"]) if achieved else None,
-        "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a step)",
+        "bound": "tensor", "achieved": achieved, "peak": peaks[peak_key],
+        "unit": "TFLOP/s", "frac": (achieved / peaks[peak_key]) if achieved else None,
+        "frac_of_burst": (achieved / peaks["bf16_burst"]) if achieved else None,
+        "frac_of_sustained": (achieved / peaks["bf16_sustained"]) if achieved else None,
+        "peak_source": f"{peaks['source']} {peak_key} (sm clock {clocks['sm_mhz'] if clocks else '?'}"
+                       f" of {clocks['sm_max_mhz'] if clocks else '?'} MHz during the run)",
         "flops_per_launch": dom_fl / dom_n if dom_n else None,
         "ms_per_launch": dom_ms / dom_n if dom_n else None,
-        "launches_per_step": dom_n, "traffic": traffic,
+        "launches_per_step": dom_n,
+        "traffic": traffic,
+        "traffic_source": ("ncu dram__bytes_read+write per launch, profiles/dominant_kernel_traffic.json"
+                           if traffic else "not captured for this config / world size"),
         "share_of_step": dom_ms / sum(v["ms_per_step"] for v in fam.values()) if fam else None,
-        "all_gemm": {"tflops": gemm_tf, "frac": gemm_tf / peaks["bf16_sustained"] if gemm_tf else None,
+        "timing": "CUDA events around every launch on its stream, eager, one stream, whole-chip grid",
+        "all_gemm": {"tflops": gemm_tf,
+                     "frac_of_burst": gemm_tf / peaks["bf16_burst"] if gemm_tf else None,
                      "ms_per_step": gemm_ms, "launches_per_step": gemm_launches},
-        "whole_step": {"tflops": total_fl / (ms_step / 1e3) / 1e12,
-                       "frac_of_bf16_burst": total_fl / (ms_step / 1e3) / 1e12
-                       / (peaks["bf16_burst"] * world),
+        "whole_step": {"tflops": step_tf,
+                       "frac_of_bf16_burst": step_tf / (peaks["bf16_burst"] * world),
+                       "frac_of_bf16_sustained": step_tf / (peaks["bf16_sustained"] * world),
                        "flops_per_image": total_fl / BATCH},
         "attention": {"tflops": attn_fl / (attn_ms / 1e3) / 1e12 if attn_ms else None,
                       "ms_per_step": attn_ms},
         "families": fam,
     }
+
+    # ---- dense sub-object (headline only): the same step with all-ones gates, so that
+    #      BASELINE.md's dense headline has a number from the same run
+    dense = None
+    if wl.name == "headline" and wl.shrunk and not args.no_dense_arm:
+        try:
+            del graph, e2e_graphs
+            wd = Workload("headline", dense=True)
+            md, fd = wd.build_device(dev, args.precision)
+            ed = parallel.ShardedEnsemble(md, fd, plan, group, stage_group)
+            for _ in range(3):
+                ld = ed(x_dev)
+            torch.cuda.synchronize()
+            gd = None
+            if not args.no_graph and (world == 1 or not args.eager_multi):
+                ok = True
+                try:
+                    gd = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(gd):
+                        god = ed(x_dev)
+                    gd.replay()
+                    torch.cuda.synchronize()
+                    ok = torch.equal(god, ld)
+                except Exception:  # noqa: BLE001
+                    ok = False
+                if not all_ranks(ok):
+                    gd = None
+                    torch.cuda.synchronize()
+            dstep = (lambda: gd.replay()) if gd is not None else (lambda: ed(x_dev))
+            for _ in range(3):
+                dstep()
+            dms = timed(dstep, args.steps)
+            dfl = wd.total_flops_per_image() * BATCH
+            dtf = dfl / (dms / 1e3) / 1e12
+            dense = {"value": BATCH / (dms / 1e3), "unit": "images/sec", "ms_per_step": dms,
+                     "whole_step_tflops": dtf,
+                     "frac_of_bf16_burst": dtf / (peaks["bf16_burst"] * world),
+                     "flops_per_image": dfl / BATCH,
+                     "launch_mode": "cuda_graph" if gd is not None else "eager"}
+        except Exception as e:  # noqa: BLE001
+            print(f"[bench] dense arm failed ({type(e).__name__}: {e})", file=sys.stderr)
+            torch.cuda.synchronize()
 
     if rank != 0:
         if world > 1:
@@ -531,22 +807,30 @@ def main():
             dist.destroy_process_group()
         return
 
+    # ---- CPU baseline (N = 1) + parity of the GPU logits against it on the same images
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         sample = 32
-        ips, ms, cores = cpu_oracle_ips(sample, 2, 1, shrunk=not args.dense)
-        cpu = {"value": ips, "unit": "images/sec", "cores": cores, "kind": "port",
-               "sample": f"{sample} images/step x 2 steps (+1 warm-up) of the same 4-way "
-                         f"ensemble, oracle port of the reference (masked-dense fp32 PyTorch CPU)"}
+        ips, ms, cores, kind, what, ref_logits, xs = cpu_time(wl, sample, 2, 1)
+        cpu = {"value": ips, "unit": "images/sec", "cores": cores, "kind": kind,
+               "sample": f"{sample} images/step x 2 steps (+1 warm-up) of the same workload, {what}"}
+        got = logits[:sample].float().cpu()
+        ref_logits = ref_logits.float()
+        err = (got - ref_logits).abs()
+        parity["vs_cpu_reference"] = {
+            "images": sample, "kind": kind,
+            "rel_err": float(err.max() / ref_logits.abs().max()),
+            "argmax_mismatch": int((got.argmax(-1) != ref_logits.argmax(-1)).sum()),
+            "tolerance": 2e-2 if args.precision == "bf16" else 1e-4}
 
     line = {
-        "metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world,
+        "metric": wl.metric, "value": value, "unit": "images/sec", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": args.precision if args.precision == "bf16" else "tf32x3",
         "data": "synthetic",
-        "config": workload_config(args, world),
-        "launch_mode": "cuda_graph" if graph is not None else "eager",
+        "config": wl.config(world, plan),
+        "launch_mode": launch_mode,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "images/sec", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -555,7 +839,9 @@ def main():
                                   else "every rank copies its group's whole batch")},
         "e2e_u8": e2e_u8,
         "gpu_launches": int(launches_per_step * args.steps),
+        "parity": parity,
         "roofline": roofline,
+        "dense": dense,
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)

@@ -345,9 +345,11 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
             }
           }
           if (elect_one()) umma_commit_cg2(p_full, 3);
+          MLP_TRACE(18, it);
           // epilogue 0 of both CTAs: bf16(x1) in Y, x1 + b2 in acc2
           mbar_wait_warp(y_ready, it & 1);
           tc_fence_after();
+          MLP_TRACE(19, it);
         }
         for (int c = 0; c < NC; ++c) {
           const int s = g1 & 1;
@@ -598,6 +600,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
       if (!PROJ && warp == 2) MLP_TRACE(12, it);
       mbar_wait_warp(acc2_full, it & 1);
       if (!PROJ && warp == 2) MLP_TRACE(13, it);
+      if (PROJ && warp == 2) MLP_TRACE(16, it * 4 + 3);
       tc_fence_after();
       float st1 = 0.f, st2 = 0.f;
 #pragma unroll 1
@@ -681,6 +684,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
       }
       __syncwarp();
       if (!PROJ && warp == 2) MLP_TRACE(14, it);
+      if (PROJ && warp == 2) MLP_TRACE(15, it * 4 + 3);
     }
     if (elect_one()) bulk_wait_all<0>();
   }

@@ -145,3 +145,21 @@ class ShardedEnsemble:
         else:                                                     # [G, 2, n_local, 2, Bg, D]
             slab = g.transpose(0, 1).reshape((2, -1) + tuple(op.shape[2:])).contiguous()
         return self.fuse.forward_gathered(slab, self.order)
+
+
+class Replica:
+    """A single model (the deit_base teacher, BASELINE config C1) on the ranks of a ShardPlan with
+    n_sub = 1: the path does not shard below one model, so N ranks are N data-parallel replicas
+    that each take 1/N of the batch -- no collective at all (``stage_batch`` is a plain copy)."""
+
+    def __init__(self, model, plan: ShardPlan):
+        self.model, self.plan = model, plan
+
+    @torch.no_grad()
+    def stage_batch(self, host_batch: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+        out.copy_(host_batch, non_blocking=True)
+        return out
+
+    @torch.no_grad()
+    def __call__(self, x_group: torch.Tensor) -> torch.Tensor:
+        return self.model(x_group)

@@ -20,7 +20,9 @@ def test_reference_arm_prints_one_contract_line():
     assert d['steps'] == 1 and d['n_gpus'] == 1 and d['gpu_launches'] == 0
     assert d['config']['global_batch'] == 256 and 'workload' in d['config']
     cb = d['cpu_baseline']
-    assert cb['kind'] == 'port' and cb['cores'] >= 1 and cb['value'] == d['value'] and cb['sample']
+    assert cb['kind'] in ('reference', 'port') and cb['cores'] >= 1 and cb['value'] == d['value'] \
+        and cb['sample']
+    assert 'reference_step' in d['config']  # the bounded per-step sample is stated
     assert d['e2e'] == {'value': d['value'], 'unit': 'images/sec', 'h2d_bytes_per_step': 0,
                         'd2h_bytes_per_step': 0}
 

@@ -35,6 +35,30 @@ KEYS = [
     ("gpc__cycles_elapsed.max", "elapsed cycles"),
     ("gpc__cycles_elapsed.avg.per_second", "gpc clock"),
     ("smsp__inst_executed.sum", "warp instructions"),
+    ("smsp__inst_executed_pipe_xu.sum", "XU-pipe (MUFU) warp instructions"),
+    ("smsp__inst_executed_pipe_fma.sum", "FMA-pipe warp instructions"),
+    ("smsp__inst_executed_pipe_alu.sum", "ALU-pipe warp instructions"),
+    ("smsp__inst_executed_pipe_lsu.sum", "LSU-pipe warp instructions"),
+    ("smsp__inst_executed_pipe_uniform.sum", "uniform-pipe warp instructions"),
+    ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "XU pipe % of peak (active)"),
+    ("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "FMA pipe % of peak (active)"),
+    ("sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "ALU pipe % of peak (active)"),
+    ("smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio", "stall long scoreboard (cyc/inst)"),
+    ("smsp__average_warp_latency_issue_stalled_short_scoreboard.ratio", "stall short scoreboard"),
+    ("smsp__average_warp_latency_issue_stalled_barrier.ratio", "stall barrier"),
+    ("smsp__average_warp_latency_issue_stalled_membar.ratio", "stall membar"),
+    ("smsp__average_warp_latency_issue_stalled_math_pipe_throttle.ratio", "stall math pipe throttle"),
+    ("smsp__average_warp_latency_issue_stalled_mio_throttle.ratio", "stall mio throttle"),
+    ("smsp__average_warp_latency_issue_stalled_lg_throttle.ratio", "stall lg throttle"),
+    ("smsp__average_warp_latency_issue_stalled_wait.ratio", "stall wait"),
+    ("smsp__average_warp_latency_issue_stalled_sleeping.ratio", "stall sleeping"),
+    ("smsp__average_warp_latency_issue_stalled_not_selected.ratio", "stall not selected"),
+    ("smsp__average_warp_latency_issue_stalled_dispatch_stall.ratio", "stall dispatch"),
+    ("smsp__average_warp_latency_issue_stalled_tex_throttle.ratio", "stall tex throttle"),
+    ("smsp__average_warp_latency_issue_stalled_branch_resolving.ratio", "stall branch resolving"),
+    ("smsp__average_warp_latency_issue_stalled_no_instruction.ratio", "stall no instruction"),
+    ("smsp__average_warp_latency_issue_stalled_selected.ratio", "selected"),
+    ("smsp__average_warp_latency_issue_stalled_gmma.ratio", "stall gmma/tensor"),
 ]
 
 

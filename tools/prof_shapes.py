@@ -50,6 +50,17 @@ if which in ("mlp", "all"):
         so = torch.empty(4, M, 2, device=dev)
         for _ in range(reps):
             L.mlp_fused(x, xb, stats6, w1, c11, c21, w2, b2, 1e-6, xb_out=xb, stats_out=so)
+if which in ("projmlp", "all"):
+    # the projection fused in front of the MLP (devit_mlp_args.o): the per-layer tail kernel
+    for F_ in (F, 1536):
+        w1, c11, c21 = rnd(F_, D, scale=.05), rnd(F_, dt=torch.float32), rnd(F_, dt=torch.float32)
+        w2, b2 = rnd(D, F_, scale=.05), rnd(D, dt=torch.float32)
+        hh = H if F_ == F else 6
+        o, w_proj, b_proj = rnd(M, 64 * hh), rnd(D, 64 * hh, scale=.05), rnd(D, dt=torch.float32)
+        so = torch.empty(4, M, 2, device=dev)
+        for _ in range(reps):
+            L.mlp_fused(x, None, None, w1, c11, c21, w2, b2, 1e-6, xb_out=xb, stats_out=so,
+                        o=o, w_proj=w_proj, b_proj=b_proj)
 if which in ("attn", "all"):
     qkv = rnd(M, 192 * H)
     for _ in range(reps):

@@ -5,7 +5,9 @@ from pathlib import Path
 import torch
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 from devit_b200 import _lib as L  # noqa: E402
+import os
 F = int(sys.argv[1]) if len(sys.argv) > 1 else 928
+H = int(os.environ.get('TIME_MLP_PROJ', '0'))  # > 0: the variant with the projection in front
 M, D = 256 * 198, 384
 g = torch.Generator(device="cuda").manual_seed(0)
 x = torch.randn(M, D, device="cuda", generator=g)
@@ -14,8 +16,16 @@ w1 = (torch.randn(F, D, device="cuda", generator=g) * .05).bfloat16()
 w2 = (torch.randn(D, F, device="cuda", generator=g) * .05).bfloat16()
 c1, c2, b2 = (torch.randn(n, device="cuda", generator=g) * .1 for n in (F, F, D))
 so = torch.empty(4, M, 2, device="cuda")
+if H:
+    o = torch.randn(M, 64 * H, device="cuda", generator=g).bfloat16()
+    wp = (torch.randn(D, 64 * H, device="cuda", generator=g) * .05).bfloat16()
+    bp = torch.randn(D, device="cuda", generator=g) * .1
 def run():
-    L.mlp_fused(x, xb, stats, w1, c1, c2, w2, b2, 1e-6, xb_out=xb, stats_out=so)
+    if H:
+        L.mlp_fused(x, None, None, w1, c1, c2, w2, b2, 1e-6, xb_out=xb, stats_out=so,
+                    o=o, w_proj=wp, b_proj=bp)
+    else:
+        L.mlp_fused(x, xb, stats, w1, c1, c2, w2, b2, 1e-6, xb_out=xb, stats_out=so)
 for _ in range(3):
     run()
 torch.cuda.synchronize()
@@ -36,8 +46,13 @@ t0 = int(t[7, 0])
 NC = (F + 63) // 64
 def r(s, i): return int(t[s, i]) - t0
 for it in range(3):
-    print(f"tile {it}: mma wait Y {r(7,it)} got {r(8,it)} | epi wait acc2 {r(12,it)} got {r(13,it)} final done {r(14,it)}")
-    print("   final chunks [before resid wait, resid landed, chunk done]: " + "  ".join(
-        f"j{j}: {r(15, it * 4 + j)} {r(16, it * 4 + j)} {r(17, it * 4 + j)}" for j in range(3)))
+    if H:
+        print(f"tile {it}: mma wait O {r(7,it)} got {r(8,it)} GEMM0 issued {r(18,it)} y_ready {r(19,it)} | "
+              f"epi0 wait p_full {r(12,it)} got {r(13,it)} done {r(14,it)} | final: acc2_full {r(16,it*4+3)} "
+              f"chunks done {[r(17, it * 4 + j) for j in range(3)]} stores drained {r(15,it*4+3)}")
+    else:
+        print(f"tile {it}: mma wait Y {r(7,it)} got {r(8,it)} | epi wait acc2 {r(12,it)} got {r(13,it)} final done {r(14,it)}")
+        print("   final chunks [before resid wait, resid landed, chunk done]: " + "  ".join(
+            f"j{j}: {r(15, it * 4 + j)} {r(16, it * 4 + j)} {r(17, it * 4 + j)}" for j in range(3)))
     for c in range(it * NC, it * NC + NC):
         print(f"   c{c - it * NC:2d}: G1 [wait {r(0,c)} got {r(1,c)} issued {r(2,c)}]  G2 [wait {r(3,c)} h {r(4,c)} w2 {r(5,c)} issued {r(6,c)}]  epi [wait {r(9,c)} got {r(10,c)} done {r(11,c)}]")

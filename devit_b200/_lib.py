@@ -116,6 +116,7 @@ _SIGS = {
     "devit_device_check": (C.c_int, []),
     "devit_launch_count": (C.c_longlong, []),
     "devit_set_sm_budget": (C.c_int, [C.c_int]),
+    "devit_tmap_cache_stats": (C.c_int, [C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
     "devit_profile_enable": (C.c_int, [C.c_int]),
     "devit_profile_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "devit_gemm": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
@@ -326,6 +327,13 @@ def gemm(a, b, *, precision=DEVIT_BF16, m=None, n=None, segs=None, out=None,
 TAGS = ["gemm_other", "gemm_patch", "gemm_qkv", "gemm_proj", "gemm_fc1", "gemm_fc2",
         "gemm_fusion", "gemm_head", "attention", "layernorm", "gather_ln", "im2col",
         "token_prefix", "gemm_mlp_fused", "eval_tail"]
+
+
+def tmap_cache_stats() -> dict:
+    """{'entries', 'hits', 'misses'} of the library's tensor-map (TMA descriptor) cache."""
+    h, m = C.c_longlong(0), C.c_longlong(0)
+    n = load().devit_tmap_cache_stats(C.byref(h), C.byref(m))
+    return {"entries": n, "hits": h.value, "misses": m.value}
 
 
 _profiling = False

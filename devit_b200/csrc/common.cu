@@ -5,7 +5,9 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstring>
 #include <mutex>
+#include <unordered_map>
 #include <vector>
 
 namespace devit {
@@ -138,9 +140,79 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
+// Tensor maps are pure functions of (base pointer, element size, dims, strides, box, swizzle,
+// L2 promotion): every launcher used to re-encode up to seven of them per call through the driver.
+// They are cached here, keyed by exactly those inputs ("mutex-guarded
+// CUtensorMap caches keyed by pointer + shape"); steady-state launches of a model hit the cache.
+// The cache is bounded (cleared when full) and can be switched off with DEVIT_TMAP_CACHE=0.
+struct TmapKey {
+  uint64_t base;
+  uint64_t dims[3];
+  uint64_t strides[2];
+  uint32_t box[3];
+  uint32_t misc;  // elem_bytes | rank << 8 | weight_like << 16 | swizzle128 << 17
+  bool operator==(const TmapKey& o) const { return std::memcmp(this, &o, sizeof(TmapKey)) == 0; }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    const uint64_t* w = reinterpret_cast<const uint64_t*>(&k);
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < sizeof(TmapKey) / 8; ++i) {
+      h ^= w[i];
+      h *= 1099511628211ull;
+    }
+    return static_cast<size_t>(h ^ (h >> 29));
+  }
+};
+static_assert(sizeof(TmapKey) % 8 == 0, "TmapKey is hashed as 64-bit words");
+static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmaps;
+static std::mutex g_tmap_mu;
+static std::atomic<long long> g_tmap_hits{0}, g_tmap_misses{0};
+constexpr size_t kTmapCacheMax = 8192;
+
+static int encode_uncached(CUtensorMap* map, const void* base, int elem_bytes, int rank,
+                           const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                           const cuuint32_t* box, bool weight_like, bool swizzle128);
+
 static int encode(CUtensorMap* map, const void* base, int elem_bytes, int rank,
                   const cuuint64_t* dims, const cuuint64_t* strides_bytes,
                   const cuuint32_t* box, bool weight_like, bool swizzle128 = true) {
+  static int cache_on = kEnvUnread;
+  if (!env_int("DEVIT_TMAP_CACHE", 1, &cache_on))
+    return encode_uncached(map, base, elem_bytes, rank, dims, strides_bytes, box, weight_like,
+                           swizzle128);
+  TmapKey k;
+  std::memset(&k, 0, sizeof(k));
+  k.base = reinterpret_cast<uint64_t>(base);
+  for (int i = 0; i < rank; ++i) {
+    k.dims[i] = dims[i];
+    k.box[i] = box[i];
+    if (i + 1 < rank) k.strides[i] = strides_bytes[i];
+  }
+  k.misc = static_cast<uint32_t>(elem_bytes) | (static_cast<uint32_t>(rank) << 8) |
+           (weight_like ? 1u << 16 : 0u) | (swizzle128 ? 1u << 17 : 0u);
+  {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    auto it = g_tmaps.find(k);
+    if (it != g_tmaps.end()) {
+      *map = it->second;
+      g_tmap_hits.fetch_add(1, std::memory_order_relaxed);
+      return DEVIT_OK;
+    }
+  }
+  int rc = encode_uncached(map, base, elem_bytes, rank, dims, strides_bytes, box, weight_like,
+                           swizzle128);
+  if (rc) return rc;
+  g_tmap_misses.fetch_add(1, std::memory_order_relaxed);
+  std::lock_guard<std::mutex> lk(g_tmap_mu);
+  if (g_tmaps.size() >= kTmapCacheMax) g_tmaps.clear();
+  g_tmaps.emplace(k, *map);
+  return DEVIT_OK;
+}
+
+static int encode_uncached(CUtensorMap* map, const void* base, int elem_bytes, int rank,
+                           const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                           const cuuint32_t* box, bool weight_like, bool swizzle128) {
   EncodeTiledFn fn = get_encode();
   if (!fn) return set_error(DEVIT_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0)
@@ -205,6 +277,12 @@ int devit_abi_version(void) { return DEVIT_ABI_VERSION; }
 const char* devit_last_error(void) { return devit::g_err; }
 int devit_device_check(void) { return devit::check_device(); }
 long long devit_launch_count(void) { return devit::g_launches.load(); }
+int devit_tmap_cache_stats(long long* hits, long long* misses) {
+  if (hits) *hits = devit::g_tmap_hits.load();
+  if (misses) *misses = devit::g_tmap_misses.load();
+  std::lock_guard<std::mutex> lk(devit::g_tmap_mu);
+  return static_cast<int>(devit::g_tmaps.size());
+}
 int devit_set_sm_budget(int sms) { return devit::g_sm_budget.exchange(sms < 0 ? 0 : sms); }
 
 int devit_profile_enable(int on) {

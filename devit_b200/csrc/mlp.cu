@@ -29,15 +29,18 @@
 // neither x1, its bf16 copy nor its row statistics ever exist in global memory.  Per pair-tile:
 //   * the attention output tile O (128 x 64h bf16 per CTA) is TMA-loaded into the Y buffer and
 //     Wp streams through the W2 ring, one 64-wide head chunk at a time;
-//   * GEMM0: acc2 = O Wp^T (A and B from shared memory, same N = D/2 UMMA pairs as GEMM2);
-//   * epilogue 0 (all sixteen epilogue warps, D/4 columns each, 32 at a time): acc2 + bp + the
-//     fp32 residual chunk (TMA-loaded into one 4 KB slot per warp that lives in the idle W1 ring
-//     / staging buffer) = x1; the warp accumulates the row's (sum, sum^2), writes bf16(x1) into
-//     the Y buffer in the K-major 128B-swizzled layout GEMM1 reads, and writes x1 + b2 BACK INTO
-//     acc2, on top of which GEMM2 then accumulates.  The four partial row sums of a row meet in
-//     shared memory (one named barrier), giving the exact LayerNorm statistics of x1;
-//   * the hidden-chunk loop is unchanged; the final epilogue has no residual to fetch: acc2 is
-//     the new x.
+//   * preload: every epilogue warp brings the fp32 residual of its 32 rows x D/4 columns into its
+//     three private 4 KB slots by TMA (requested while the PREVIOUS tile's stores drain), adds bp
+//     and writes x + bp INTO acc2 (tcgen05.st), so the HBM-latency-bound part of the residual add
+//     happens before the tensor core needs the tile and off the GEMM0 -> GEMM1 path;
+//   * GEMM0: acc2 += O Wp^T (A and B from shared memory, same N = D/2 UMMA pairs as GEMM2),
+//     giving x1 in acc2;
+//   * epilogue 0 (all sixteen epilogue warps, D/4 columns each, 32 at a time): read x1 back,
+//     accumulate the row's (sum, sum^2) and write bf16(x1) into the Y buffer in the K-major
+//     128B-swizzled layout GEMM1 reads.  The four partial row sums of a row meet in shared memory
+//     (one named barrier), giving the exact LayerNorm statistics of x1;
+//   * the hidden-chunk loop is unchanged (GEMM2 accumulates on top of x1); the final epilogue
+//     adds b2 and has no residual to fetch.
 #include <cstdlib>
 
 #include "common.cuh"
@@ -65,12 +68,10 @@ struct MlpCfg {
   static constexpr int kOffW1 = kYBytes;
   static constexpr int kOffW2 = kOffW1 + 2 * kW1Slot;
   static constexpr int kOffXb = kOffW2 + 2 * kW2Slot;  // bf16-copy staging: 16 x [32 rows x 64 B]
-  // PROJ: one 4 KB residual slot per epilogue warp: as many as fit in the (then idle) W1 ring,
-  // the rest at the bottom of the staging buffer, followed by the 4 KB row-statistics exchange
-  static constexpr int kXSlotsInW1 = (2 * kW1Slot / 4096) < 16 ? (2 * kW1Slot / 4096) : 16;
-  static constexpr int kOffStat = kOffXb + (16 - kXSlotsInW1) * 4096;
-  static constexpr int kXbBytes =
-      (kOffStat + 4096 - kOffXb) > 16 * 2048 ? (kOffStat + 4096 - kOffXb) : 16 * 2048;
+  // PROJ: the 4 KB row-statistics exchange of epilogue 0 lives at the bottom of the staging
+  // buffer (idle until the final epilogue)
+  static constexpr int kOffStat = kOffXb;
+  static constexpr int kXbBytes = 16 * 2048;
   static constexpr int kOffBar = kOffXb + kXbBytes;
   static constexpr int kSmem = kOffBar + 1024 + 1024;
   static constexpr int kAcc1Col = D;                // acc2 = TMEM columns [0, D), acc1 behind it
@@ -148,11 +149,13 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
   uint64_t* h_ready = bars + 13;    // [2]  (leader: 32 warp arrivals)
   uint64_t* acc2_full = bars + 15;
   uint64_t* acc2_empty = bars + 16;  // (leader: 32 warp arrivals)
-  uint64_t* rfull = bars + 17;       // [16 warps][3 slots max]  (PROJ: [16 warps], one slot each)
-  uint64_t* p_full = bars + 65;      // PROJ: GEMM0 retired (acc2 = O Wp^T, O is dead)
-  uint64_t* y_ready = bars + 66;     // PROJ: bf16(x1) written to Y, x1 + b2 in acc2 (leader: 32)
-  uint64_t* x_done = bars + 67;      // PROJ: this CTA's residual slots are drained (16 arrivals)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 68);
+  uint64_t* rfull = bars + 17;       // [16 warps][3 slots max]
+  uint64_t* p_full = bars + 65;      // PROJ: GEMM0 retired (acc2 = x1, O is dead)
+  uint64_t* y_ready = bars + 66;     // PROJ: bf16(x1) written to Y (leader: 32 warp arrivals)
+  uint64_t* x_done = bars + 67;      // PROJ: this CTA's residual slots are drained (16 arrivals):
+                                     //       Y and the rings may be loaded for this tile
+  uint64_t* x_loaded = bars + 68;    // PROJ: x + bp preloaded into acc2 (leader: 32 warp arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 69);
 
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
@@ -187,6 +190,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
     mbar_init(p_full, 1);
     mbar_init(y_ready, 32);
     mbar_init(x_done, 16);
+    mbar_init(x_loaded, 32);
     if (PROJ) tma_prefetch_desc(&tmWp);
     fence_mbar_init();
   }
@@ -230,7 +234,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
     int it = 0;
     for (int pt = cluster_id; pt < num_pairs; pt += num_clusters, ++it) {
       const int m0 = (pt * 2 + cta_rank) * 128;
-      if (it >= 1) mbar_wait_warp(y_free, (it - 1) & 1);
+      if constexpr (PROJ) mbar_wait_warp(x_done, it & 1);  // residual slots of this tile drained
+      else if (it >= 1) mbar_wait_warp(y_free, (it - 1) & 1);
       if (elect_one()) {
         const uint32_t bar = mapa_u32(smem_u32(y_full), 0);
         if constexpr (PROJ) {
@@ -244,8 +249,6 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
           for (int a = 0; a < kAtoms; ++a) tma_load_2d_cg2(smem + a * 16384, &tmY, bar, a * 64, m0);
         }
       }
-      // PROJ: the W1 ring holds residual slots of epilogue 0 until they are drained
-      if constexpr (PROJ) mbar_wait_warp(x_done, it & 1);
       for (int c = 0; c < NC; ++c, ++g1) {
         const int s = g1 & 1;
         mbar_wait_warp(&w1_empty[s], ((g1 >> 1) & 1) ^ 1);
@@ -264,7 +267,9 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
     uint32_t gw = 0;  // ring uses (PROJ: the Wp head chunks of a tile go through it first)
     int it = 0;
     for (int pt = cluster_id; pt < num_pairs; pt += num_clusters, ++it) {
-      if (it >= 1) mbar_wait_warp(y_free, (it - 1) & 1);  // ring memory served as slots
+      // ring memory served as slots of the final epilogue (and, PROJ, of this tile's preload)
+      if constexpr (PROJ) mbar_wait_warp(x_done, it & 1);
+      else if (it >= 1) mbar_wait_warp(y_free, (it - 1) & 1);
       const int n_pre = PROJ ? p.proj_chunks : 0;
       for (int c = -n_pre; c < NC; ++c, ++gw) {
         const int s = gw & 1;
@@ -307,7 +312,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
               const uint64_t db = make_sw128_desc(sw + hh * (kW2Rows * 128), 1024, 16) + 2 * j;
-              // PROJ: acc2 already holds x1 + b2, every GEMM2 accumulates
+              // PROJ: acc2 already holds x1, every GEMM2 accumulates
               umma_bf16_ts_cg2(tmem_base + kHalfN * hh, a_t, db, idesc2,
                                (!PROJ && first_of_tile && j == 0) ? 0u : 1u);
             }
@@ -323,8 +328,9 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         mbar_wait_warp(y_full, it & 1);
         MLP_TRACE(8, it);
         if constexpr (PROJ) {
-          // GEMM0: acc2 = O Wp^T, one 64-wide head chunk per W2-ring slot
-          if (it >= 1) mbar_wait_warp(acc2_empty, (it - 1) & 1);
+          // GEMM0: acc2 (= x + bp, preloaded by the epilogue warps of both CTAs) += O Wp^T, one
+          // 64-wide head chunk per W2-ring slot
+          mbar_wait_warp(x_loaded, it & 1);
           for (int a = 0; a < p.proj_chunks; ++a, ++gw) {
             const int ws = gw & 1;
             mbar_wait_warp(&w2_full[ws], (gw >> 1) & 1);
@@ -337,8 +343,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
                   const uint64_t db = make_sw128_desc(sw + hh * (kW2Rows * 128), 1024, 16);
-                  umma_bf16_cg2(tmem_base + kHalfN * hh, da + 2 * k, db + 2 * k, idesc2,
-                                (a | k) ? 1u : 0u);
+                  umma_bf16_cg2(tmem_base + kHalfN * hh, da + 2 * k, db + 2 * k, idesc2, 1u);
                 }
               }
               umma_commit_cg2(&w2_empty[ws], 3);
@@ -346,7 +351,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
           }
           if (elect_one()) umma_commit_cg2(p_full, 3);
           MLP_TRACE(18, it);
-          // epilogue 0 of both CTAs: bf16(x1) in Y, x1 + b2 in acc2
+          // epilogue 0 of both CTAs: bf16(x1) in Y
           mbar_wait_warp(y_ready, it & 1);
           tc_fence_after();
           MLP_TRACE(19, it);
@@ -399,103 +404,97 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
     const uint32_t h_ready_leader0 = mapa_u32(smem_u32(&h_ready[0]), 0);
     const uint32_t h_ready_leader1 = mapa_u32(smem_u32(&h_ready[1]), 0);
     const uint32_t acc2_empty_leader = mapa_u32(smem_u32(acc2_empty), 0);
-    // PROJ: this warp's residual slot of epilogue 0 (W1 ring first, then the staging buffer)
-    uint8_t* xslot = ew < Cfg::kXSlotsInW1 ? smem + kOffW1 + ew * 4096
-                                           : smem + kOffXb + (ew - Cfg::kXSlotsInW1) * 4096;
-    uint64_t* xbar = rfull + ew;
     const uint32_t y_ready_leader = mapa_u32(smem_u32(y_ready), 0);
-    uint32_t xcnt = 0;
+    const uint32_t x_loaded_leader = mapa_u32(smem_u32(x_loaded), 0);
+    // PROJ: request the fp32 residual chunks of tile `m_tile` into this warp's private slots
+    // (chunks [j0, j1)); the slots must have been drained by the warp's own earlier stores
+    auto request_resid = [&](int m_tile, int j0, int j1) {
+      if (elect_one()) {
+        for (int s2 = j0; s2 < j1; ++s2) {
+          mbar_expect_tx(&rbar[s2], 4096);
+          tma_load_2d(slots + s2 * 4096, &tmX, &rbar[s2], sub * kColsPerWarp + s2 * 32,
+                      m_tile + quarter * 32);
+        }
+      }
+      __syncwarp();
+    };
     uint32_t ecnt = 0;
     int it = 0;
     for (int pt = cluster_id; pt < num_pairs; pt += num_clusters, ++it) {
       const int m0 = (pt * 2 + cta_rank) * 128;
       const int row0 = m0 + quarter * 32;
       const int row = row0 + lane;
+      const bool has_next = pt + num_clusters < num_pairs;
+      const int m_next = ((pt + num_clusters) * 2 + cta_rank) * 128;
       // ---- this row's LayerNorm statistics (folded into the fc1 epilogue)
       float rstd, nmr;
       if constexpr (PROJ) {
-        // ---- epilogue 0: x1 = acc2 (= O Wp^T) + bp + x.  Residual chunks arrive by TMA in this
-        //      warp's slot; bf16(x1) -> Y (K-major, 128B swizzle), x1 + b2 -> acc2, row sums ->
-        //      shared memory.
         float2* stat_s = reinterpret_cast<float2*>(smem + Cfg::kOffStat);
-        if (it >= 1) mbar_wait_warp(y_free, (it - 1) & 1);  // the slot memory is dead
-        if (elect_one()) {
-          mbar_expect_tx(xbar, 4096);
-          tma_load_2d(xslot, &tmX, xbar, sub * kColsPerWarp, row0);
-        }
-        // next tile's operands -> L2 while this one computes
-        if (pt + num_clusters < num_pairs && elect_one()) {
-          const int m_next = ((pt + num_clusters) * 2 + cta_rank) * 128;
-#pragma unroll
-          for (int s2 = 0; s2 < kSlots; ++s2)
-            tma_prefetch_l2_2d(&tmX, sub * kColsPerWarp + s2 * 32, m_next + quarter * 32);
-          if (sub == 0 && quarter < 2)
-            for (int a = quarter; a < p.proj_chunks; a += 2) tma_prefetch_l2_2d(&tmY, a * 64, m_next);
-        }
+        const int rr = quarter * 32 + lane;  // row inside the CTA's 128
+        // ---- preload: acc2 <- x + bp.  The residual chunks were requested into this warp's own
+        //      slots while the previous tile's stores drained (here for the CTA's first tile).
+        if (it == 0) request_resid(m0, 0, kSlots);
         if (warp == 2) MLP_TRACE(12, it);
-        mbar_wait_warp(p_full, it & 1);
+#pragma unroll 1
+        for (int j = 0; j < kSlots; ++j) {
+          const int col0 = sub * kColsPerWarp + j * 32;
+          uint32_t r[32];
+          float* v = reinterpret_cast<float*>(r);
+          mbar_wait_warp(&rbar[j], it & 1);
+          const uint8_t* bsl = slots + j * 4096;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 t = *reinterpret_cast<const float4*>(bsl + mlp_off(lane, g));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bp + col0) + g);
+            v[4 * g] = t.x + b.x; v[4 * g + 1] = t.y + b.y;
+            v[4 * g + 2] = t.z + b.z; v[4 * g + 3] = t.w + b.w;
+          }
+          tmem_st_x32(tmem_base + lane_off + col0, r);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(x_done);  // slots drained: the loaders may fill Y and the rings
+          if (leader) mbar_arrive(x_loaded);
+          else mbar_arrive_cluster(x_loaded_leader);
+        }
         if (warp == 2) MLP_TRACE(13, it);
+        // ---- epilogue 0: x1 = acc2 after GEMM0: row sums -> shared memory, bf16(x1) -> Y
+        //      (K-major, 128B swizzle)
+        mbar_wait_warp(p_full, it & 1);
+        if (warp == 2) MLP_TRACE(15, it * 4);
         tc_fence_after();
         float st1 = 0.f, st2 = 0.f;
-        const int rr = quarter * 32 + lane;  // row inside the CTA's 128
 #pragma unroll 1
-        for (int j = 0; j < kSlots; ++j, ++xcnt) {
+        for (int j = 0; j < kSlots; ++j) {
           const int col0 = sub * kColsPerWarp + j * 32;
           uint32_t r[32];
           tmem_ld_x32(tmem_base + lane_off + col0, r);
           tmem_ld_wait();
-          float* v = reinterpret_cast<float*>(r);
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const float4 t = __ldg(reinterpret_cast<const float4*>(p.bp + col0) + g);
-            v[4 * g] += t.x; v[4 * g + 1] += t.y; v[4 * g + 2] += t.z; v[4 * g + 3] += t.w;
-          }
-          mbar_wait_warp(xbar, xcnt & 1);
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const float4 t = *reinterpret_cast<const float4*>(xslot + mlp_off(lane, g));
-            v[4 * g] += t.x; v[4 * g + 1] += t.y; v[4 * g + 2] += t.z; v[4 * g + 3] += t.w;
-          }
-          __syncwarp();
-          if (j + 1 < kSlots) {  // the slot has been read by every lane: fetch the next chunk
-            fence_proxy_async_smem();
-            if (elect_one()) {
-              mbar_expect_tx(xbar, 4096);
-              tma_load_2d(xslot, &tmX, xbar, col0 + 32, row0);
-            }
-          }
+          const float* v = reinterpret_cast<const float*>(r);
 #pragma unroll
           for (int k = 0; k < 32; ++k) {
             st1 += v[k];
             st2 = fmaf(v[k], v[k], st2);
           }
-          {
-            uint8_t* ya = smem + (col0 >> 6) * 16384 + rr * 128;
-            const int cb = (col0 & 63) >> 3;
+          uint8_t* ya = smem + (col0 >> 6) * 16384 + rr * 128;
+          const int cb = (col0 & 63) >> 3;
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              uint4 t;
-              t.x = pack_bf16x2(v[8 * g], v[8 * g + 1]);
-              t.y = pack_bf16x2(v[8 * g + 2], v[8 * g + 3]);
-              t.z = pack_bf16x2(v[8 * g + 4], v[8 * g + 5]);
-              t.w = pack_bf16x2(v[8 * g + 6], v[8 * g + 7]);
-              *reinterpret_cast<uint4*>(ya + (((cb + g) ^ (rr & 7)) << 4)) = t;
-            }
+          for (int g = 0; g < 4; ++g) {
+            uint4 t;
+            t.x = pack_bf16x2(v[8 * g], v[8 * g + 1]);
+            t.y = pack_bf16x2(v[8 * g + 2], v[8 * g + 3]);
+            t.z = pack_bf16x2(v[8 * g + 4], v[8 * g + 5]);
+            t.w = pack_bf16x2(v[8 * g + 6], v[8 * g + 7]);
+            *reinterpret_cast<uint4*>(ya + (((cb + g) ^ (rr & 7)) << 4)) = t;
           }
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const float4 t = __ldg(reinterpret_cast<const float4*>(p.b2 + col0) + g);
-            v[4 * g] += t.x; v[4 * g + 1] += t.y; v[4 * g + 2] += t.z; v[4 * g + 3] += t.w;
-          }
-          tmem_st_x32(tmem_base + lane_off + col0, r);
         }
-        tmem_st_wait();
         stat_s[sub * 128 + rr] = make_float2(st1, st2);
         fence_proxy_async_smem();  // Y as the tensor core (async proxy) will read it
         tc_fence_before();
         named_bar_sync(1, 16 * 32);  // the sixteen epilogue warps of this CTA
         if (lane == 0) {
-          mbar_arrive(x_done);
           if (leader) mbar_arrive(y_ready);
           else mbar_arrive_cluster(y_ready_leader);
         }
@@ -536,6 +535,18 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
       //      [64c + 16 sub, +16) = acc1 columns [16 sub, +16) -> H columns [16 sub, +8).
       for (int c = 0; c < NC; ++c, ++ecnt) {
         const int b = ecnt & 1;
+        if constexpr (PROJ) {
+          // next tile's residual and attention output -> L2, late enough to still be there when
+          // the TMA loads ask for them (~half a chunk loop ahead)
+          if (c == NC / 2 && has_next && elect_one()) {
+#pragma unroll
+            for (int s2 = 0; s2 < kSlots; ++s2)
+              tma_prefetch_l2_2d(&tmX, sub * kColsPerWarp + s2 * 32, m_next + quarter * 32);
+            if (sub == 0 && quarter < 2)
+              for (int a = quarter; a < p.proj_chunks; a += 2)
+                tma_prefetch_l2_2d(&tmY, a * 64, m_next);
+          }
+        }
         // fold constants of this slice, fetched and combined BEFORE the accumulator is awaited
         float t[16];
         {
@@ -579,7 +590,9 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         if (warp == 2) MLP_TRACE(11, ecnt);
       }
       // ---- final epilogue: x += acc2 + b2, bf16 copy, partial row sums (96 columns per warp)
-      //      (PROJ: acc2 already IS the new x; the dead Y / ring memory only stages the stores)
+      //      (PROJ: acc2 already holds x1 + the MLP branch; the dead Y / ring memory stages the
+      //      stores, and each slot is re-armed with the NEXT tile's residual as soon as its store
+      //      has been read)
       if constexpr (!PROJ) {
         if (slots_in_w2) mbar_wait_warp(acc2_full, it & 1);
         else mbar_wait_warp(y_empty, it & 1);
@@ -609,7 +622,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         uint32_t r[32];
         tmem_ld_x32(tmem_base + lane_off + col0, r);
         tmem_ld_wait();
-        if (j == kSlots - 1) {
+        if (!PROJ && j == kSlots - 1) {
           // acc2 is in registers: release it before the memory work of the last chunk
           tc_fence_before();
           __syncwarp();
@@ -620,12 +633,12 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         }
         float* v = reinterpret_cast<float*>(r);
         uint8_t* bsl = slots + j * 4096;
-        if constexpr (!PROJ) {
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const float4 t = __ldg(reinterpret_cast<const float4*>(p.b2 + col0) + g);
-            v[4 * g] += t.x; v[4 * g + 1] += t.y; v[4 * g + 2] += t.z; v[4 * g + 3] += t.w;
-          }
+        for (int g = 0; g < 8; ++g) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(p.b2 + col0) + g);
+          v[4 * g] += t.x; v[4 * g + 1] += t.y; v[4 * g + 2] += t.z; v[4 * g + 3] += t.w;
+        }
+        if constexpr (!PROJ) {
           if (warp == 2) MLP_TRACE(15, it * 4 + j);
           mbar_wait_warp(&rbar[j], it & 1);
           if (warp == 2) MLP_TRACE(16, it * 4 + j);
@@ -639,14 +652,17 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         for (int g = 0; g < 8; ++g)
           *reinterpret_cast<float4*>(bsl + mlp_off(lane, g)) =
               make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+        if (j > 0 && (PROJ || p.xb_out)) {
+          // the previous chunk's stores have read their staging tile / slot
+          if (elect_one()) bulk_wait_read<0>();
+          __syncwarp();
+          if constexpr (PROJ) {
+            if (has_next) request_resid(m_next, j - 1, j);
+          }
+        }
         if (p.xb_out) {
           // bf16 copy through a 64B-swizzled staging tile + TMA store (scattered 16-byte global stores
-          // from 16 warps were the slowest part of this phase).  The previous chunk's stores
-          // have to have read the staging tile first.
-          if (j > 0) {
-            if (elect_one()) bulk_wait_read<0>();
-            __syncwarp();
-          }
+          // from 16 warps were the slowest part of this phase).
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             uint4 t;
@@ -678,11 +694,15 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         reinterpret_cast<float2*>(p.stats_out)[static_cast<long long>(sub) * p.M + row] =
             make_float2(st1, st2);
       // the loaders may reuse Y and the rings once every warp's stores have drained its slots
+      // (PROJ: ... and the next tile's preload has consumed the residual re-armed into them)
       if (elect_one()) {
         bulk_wait_read<0>();
-        mbar_arrive(y_free);
+        if (!PROJ) mbar_arrive(y_free);
       }
       __syncwarp();
+      if constexpr (PROJ) {
+        if (has_next) request_resid(m_next, kSlots - 1, kSlots);
+      }
       if (!PROJ && warp == 2) MLP_TRACE(14, it);
       if (PROJ && warp == 2) MLP_TRACE(15, it * 4 + 3);
     }

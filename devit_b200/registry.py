@@ -9,21 +9,36 @@ two functions itself.
 """
 from __future__ import annotations
 
-_ENTRYPOINTS = {}
+import logging
 
-try:  # pragma: no cover - timm is not in the build image
-    from timm.models.registry import register_model as _timm_register
-except Exception:  # noqa: BLE001
-    _timm_register = None
+_ENTRYPOINTS = {}
+TIMM_FAILURES = {}  # entrypoint name -> why timm's registry refused it
+_log = logging.getLogger("devit_b200.registry")
+
+
+def _find_timm_register():
+    try:
+        from timm.models.registry import register_model as reg
+        return reg
+    except ImportError:  # timm is not installed (the build image): use the local registry only
+        return None
+
+
+_timm_register = _find_timm_register()
 
 
 def register_model(fn):
     _ENTRYPOINTS[fn.__name__] = fn
-    if _timm_register is not None:  # pragma: no cover
+    if _timm_register is not None:
         try:
             _timm_register(fn)
-        except Exception:  # noqa: BLE001  (timm versions differ in what they require of fn)
-            pass
+        except Exception as e:  # noqa: BLE001  (timm versions differ in what they require of fn)
+            # not fatal -- devit_b200.registry.create_model still works -- but a reference script
+            # calling timm.create_model would silently get timm's stock model: say so
+            TIMM_FAILURES[fn.__name__] = f"{type(e).__name__}: {e}"
+            _log.warning("timm refused to register %r (%s: %s); timm.create_model(%r) will NOT "
+                         "return the devit_b200 model, use devit_b200.registry.create_model",
+                         fn.__name__, type(e).__name__, e, fn.__name__)
     return fn
 
 

@@ -86,6 +86,12 @@ int devit_profile_collect(double* ms_by_tag, long long* count_by_tag);
  * other.  Values are rounded down to an even count (CTA pairs); returns the previous budget. */
 int devit_set_sm_budget(int sms);
 
+/* The launchers cache the TMA descriptors (CUtensorMap) they encode, keyed by base pointer +
+ * dims + strides + box + swizzle, behind a mutex (bounded; DEVIT_TMAP_CACHE=0 switches it off).
+ * Returns the number of cached descriptors; *hits / *misses (either may be NULL) receive the
+ * process-wide lookup counters. */
+int devit_tmap_cache_stats(long long* hits, long long* misses);
+
 /* ---------------------------------------------------------------------------------------
  * devit_gemm: out = epilogue( sum_s A_s[M, K_s] * B_s[N, K_s]^T )  on tcgen05/TMEM via TMA.
  *

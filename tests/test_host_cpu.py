@@ -283,3 +283,35 @@ def test_engine_has_no_cpu_fallback():
         L.eval_tail(torch.zeros(2, 10), torch.zeros(2, dtype=torch.int64))
     with pytest.raises(L.DevitError):
         L.im2col_tokens_u8(torch.zeros(1, 3, 32, 32, dtype=torch.uint8), (0.5,) * 3, (0.5,) * 3, 0)
+
+
+def test_timm_registration_failures_are_logged_not_swallowed(monkeypatch, caplog):
+    """registry.register_model also registers with timm when it is installed; a timm that
+    refuses the entrypoint must leave a warning and a record, not silence (VERDICT r1 #13)."""
+    import logging
+    from devit_b200 import registry
+
+    def refusing(fn):
+        raise KeyError("no default_cfg for " + fn.__name__)
+
+    calls = []
+
+    def accepting(fn):
+        calls.append(fn.__name__)
+        return fn
+
+    def my_model(pretrained=False, **kw):
+        return ('built', pretrained, kw)
+
+    monkeypatch.setattr(registry, '_timm_register', refusing)
+    with caplog.at_level(logging.WARNING, logger='devit_b200.registry'):
+        registry.register_model(my_model)
+    assert 'my_model' in registry.TIMM_FAILURES and 'KeyError' in registry.TIMM_FAILURES['my_model']
+    assert any('timm refused to register' in r.message for r in caplog.records)
+    # the local registry still serves it, with timm's None-kwarg filtering
+    assert registry.create_model('my_model', drop_block_rate=None, a=1) == ('built', False, {'a': 1})
+    monkeypatch.setattr(registry, '_timm_register', accepting)
+    registry.register_model(my_model)
+    assert calls == ['my_model']
+    registry._ENTRYPOINTS.pop('my_model')
+    registry.TIMM_FAILURES.pop('my_model')

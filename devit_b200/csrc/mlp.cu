@@ -121,6 +121,15 @@ __device__ __forceinline__ void umma_bf16_ts_cg2(uint32_t d_tmem, uint32_t a_tme
       : "memory");
 }
 
+// 32-byte global store (STG.256, sm_100): one full sector per lane and instruction
+__device__ __forceinline__ void st_global_256(void* p, uint32_t a0, uint32_t a1, uint32_t a2,
+                                              uint32_t a3, uint32_t a4, uint32_t a5, uint32_t a6,
+                                              uint32_t a7) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"l"(p), "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(a4), "r"(a5), "r"(a6), "r"(a7)
+               : "memory");
+}
+
 __device__ __forceinline__ int mlp_off(int r, int j) { return r * 128 + ((j ^ (r & 7)) << 4); }
 
 // tmY: the bf16 copy of x (plain variant) or the attention output O (PROJ); tmWp: Wp (PROJ only)
@@ -652,34 +661,56 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         for (int g = 0; g < 8; ++g)
           *reinterpret_cast<float4*>(bsl + mlp_off(lane, g)) =
               make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
-        if (j > 0 && (PROJ || p.xb_out)) {
-          // the previous chunk's stores have read their staging tile / slot
-          if (elect_one()) bulk_wait_read<0>();
-          __syncwarp();
-          if constexpr (PROJ) {
-            if (has_next) request_resid(m_next, j - 1, j);
-          }
-        }
-        if (p.xb_out) {
-          // bf16 copy through a 64B-swizzled staging tile + TMA store (scattered 16-byte global stores
-          // from 16 warps were the slowest part of this phase).
+        if constexpr (PROJ) {
+          // bf16 copy straight from registers: this lane's 32 values are 64 contiguous bytes of
+          // its row = two full 32-byte sectors (STG.256).  No staging tile, so nothing in this loop
+          // waits for the TMA engine and all three fp32 stores of the warp queue up back to back.
+          if (p.xb_out && row < p.M) {
+            uint32_t* dst = reinterpret_cast<uint32_t*>(p.xb_out + static_cast<long long>(row) * D + col0);
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            uint4 t;
-            t.x = pack_bf16x2(v[8 * g], v[8 * g + 1]);
-            t.y = pack_bf16x2(v[8 * g + 2], v[8 * g + 3]);
-            t.z = pack_bf16x2(v[8 * g + 4], v[8 * g + 5]);
-            t.w = pack_bf16x2(v[8 * g + 6], v[8 * g + 7]);
-            *reinterpret_cast<uint4*>(xb_stg + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4)) = t;
+            for (int g = 0; g < 2; ++g)
+              st_global_256(dst + 8 * g, pack_bf16x2(v[16 * g], v[16 * g + 1]),
+                            pack_bf16x2(v[16 * g + 2], v[16 * g + 3]),
+                            pack_bf16x2(v[16 * g + 4], v[16 * g + 5]),
+                            pack_bf16x2(v[16 * g + 6], v[16 * g + 7]),
+                            pack_bf16x2(v[16 * g + 8], v[16 * g + 9]),
+                            pack_bf16x2(v[16 * g + 10], v[16 * g + 11]),
+                            pack_bf16x2(v[16 * g + 12], v[16 * g + 13]),
+                            pack_bf16x2(v[16 * g + 14], v[16 * g + 15]));
           }
+          fence_proxy_async_smem();
+          if (elect_one()) {
+            tma_store_2d(&tmX, bsl, col0, row0);
+            bulk_commit();
+          }
+          __syncwarp();
+        } else {
+          if (j > 0 && p.xb_out) {
+            // the previous chunk's stores have read their staging tile
+            if (elect_one()) bulk_wait_read<0>();
+            __syncwarp();
+          }
+          if (p.xb_out) {
+            // bf16 copy through a 64B-swizzled staging tile + TMA store (scattered 16-byte global
+            // stores from 16 warps were the slowest part of this phase).
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint4 t;
+              t.x = pack_bf16x2(v[8 * g], v[8 * g + 1]);
+              t.y = pack_bf16x2(v[8 * g + 2], v[8 * g + 3]);
+              t.z = pack_bf16x2(v[8 * g + 4], v[8 * g + 5]);
+              t.w = pack_bf16x2(v[8 * g + 6], v[8 * g + 7]);
+              *reinterpret_cast<uint4*>(xb_stg + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4)) = t;
+            }
+          }
+          fence_proxy_async_smem();
+          if (elect_one()) {
+            tma_store_2d(&tmX, bsl, col0, row0);
+            if (p.xb_out) tma_store_2d(&tmXB, xb_stg, col0, row0);
+            bulk_commit();
+          }
+          __syncwarp();
         }
-        fence_proxy_async_smem();
-        if (elect_one()) {
-          tma_store_2d(&tmX, bsl, col0, row0);
-          if (p.xb_out) tma_store_2d(&tmXB, xb_stg, col0, row0);
-          bulk_commit();
-        }
-        __syncwarp();
         if (p.stats_out) {
 #pragma unroll
           for (int k = 0; k < 32; ++k) {
@@ -695,13 +726,28 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
             make_float2(st1, st2);
       // the loaders may reuse Y and the rings once every warp's stores have drained its slots
       // (PROJ: ... and the next tile's preload has consumed the residual re-armed into them)
-      if (elect_one()) {
-        bulk_wait_read<0>();
-        if (!PROJ) mbar_arrive(y_free);
-      }
-      __syncwarp();
       if constexpr (PROJ) {
-        if (has_next) request_resid(m_next, kSlots - 1, kSlots);
+        // slot j is re-armed with the next tile's residual as soon as ITS store has been read
+        // (one bulk group per chunk, oldest first)
+        if (elect_one()) bulk_wait_read<kSlots - 1>();
+        __syncwarp();
+        if (has_next) request_resid(m_next, 0, 1);
+        if constexpr (kSlots >= 2) {
+          if (elect_one()) bulk_wait_read<kSlots - 2>();
+          __syncwarp();
+          if (has_next) request_resid(m_next, 1, 2);
+        }
+        if constexpr (kSlots >= 3) {
+          if (elect_one()) bulk_wait_read<0>();
+          __syncwarp();
+          if (has_next) request_resid(m_next, 2, 3);
+        }
+      } else {
+        if (elect_one()) {
+          bulk_wait_read<0>();
+          mbar_arrive(y_free);
+        }
+        __syncwarp();
       }
       if (!PROJ && warp == 2) MLP_TRACE(14, it);
       if (PROJ && warp == 2) MLP_TRACE(15, it * 4 + 3);
@@ -748,8 +794,8 @@ extern "C" int devit_mlp_fused(const devit_mlp_args* a, void* stream_v) {
   DEVIT_REQUIRE(reinterpret_cast<uintptr_t>(a->c1) % 16 == 0 &&
                     reinterpret_cast<uintptr_t>(a->c2) % 16 == 0 &&
                     reinterpret_cast<uintptr_t>(a->b2) % 16 == 0 &&
-                    (!a->xb_out || reinterpret_cast<uintptr_t>(a->xb_out) % 16 == 0),
-                "devit_mlp_fused: c1 / c2 / b2 / xb_out must be 16-byte aligned");
+                    (!a->xb_out || reinterpret_cast<uintptr_t>(a->xb_out) % 32 == 0),
+                "devit_mlp_fused: c1 / c2 / b2 must be 16-byte, xb_out 32-byte aligned");
   static bool attr_done[64] = {};
   int dev = 0;
   DEVIT_CUDA_OK(cudaGetDevice(&dev));

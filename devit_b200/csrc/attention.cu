@@ -294,7 +294,11 @@ attn_bf16_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 //     columns [128, 192) of the tile (S there is dead by then); the same warps scale by 1/rowsum
 //     and store.
 // TMEM: 2 x 256 columns = all 512 (hence one CTA per SM); smem: 2 stages x 84 KB.
-constexpr int kPersistThreads = 9 * 32;  // 8 softmax warps + 1 control warp
+// warps 0..7: softmax (two 128-row TMEM regions x four lane quarters), warp 8: control (TMA +
+// MMA issue), warps 9..16: output (read O from TMEM, scale by 1/rowsum, store) -- with the
+// output on its own warps a softmax warp goes from P_k straight to S_{k+1}, and S_{k+1} is issued
+// as soon as O_k has been READ, not stored
+constexpr int kPersistThreads = 17 * 32;
 
 long long* g_attn_trace = nullptr;  // devit_debug_set_trace (shared with the GEMM trace buffer)
 #ifdef DEVIT_GEMM_TRACE
@@ -313,7 +317,7 @@ struct AttnPersistCfg {
   static constexpr int kKVBytes = KVP * 128;
   static constexpr int kStageBytes = kQBytes + 2 * kKVBytes;
   static constexpr int kOffBar = 2 * kStageBytes;
-  static constexpr int kSmemBytes = kOffBar + 256 + 1024;
+  static constexpr int kSmemBytes = kOffBar + 128 + 1024 + 1024;  // barriers, 1/rowsum, slack
   static constexpr int kOCols = 128;  // O accumulator: columns [128, 192) of the tile (S there
                                       // is dead once every warp has finished its second pass)
   static_assert(KVP % 16 == 0 && KVP <= 256 && KVP / 2 <= kOCols, "P and O must not overlap");
@@ -336,6 +340,11 @@ attn_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint64_t* o_full = bars + 10;   // [2 tiles]   O_t complete
   uint64_t* o_empty = bars + 12;  // [2 tiles]   O_t read out, S_t columns reusable (4 arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  // 1 / rowsum of the current item, [region][row]: written by the softmax warp before it arrives
+  // on p_full, read by the output warp of the same lane quarter after o_full (which follows
+  // p_full), overwritten only after the softmax warp has seen the next s_full (which follows
+  // o_empty of this item)
+  float* inv_s = reinterpret_cast<float*>(smem + Cfg::kOffBar + 128);
 
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
@@ -417,7 +426,9 @@ attn_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           if (ok) {
             tc_fence_after();
             const uint32_t sq = smem_u32(smem + stage * Cfg::kStageBytes);
-            const uint64_t dq = make_sw128_desc(sq + t * 16384, 1024, 16);
+            // region t takes query tile t ^ (k & 1): the tiles of an item are unequal (198 tokens
+            // = 128 + 70 rows), alternating them gives both regions' warps the same load
+            const uint64_t dq = make_sw128_desc(sq + ((t ^ (k & 1)) * 16384), 1024, 16);
             const uint64_t dk = make_sw128_desc(sq + Cfg::kQBytes, 1024, 16);
             if (elect_one()) {
 #pragma unroll
@@ -457,18 +468,17 @@ attn_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
       if (!progress) __nanosleep(40);  // leave the issue slots to the softmax warps
     }
-  } else {
-    // ------------------------------------------------------------ softmax + epilogue warps
+  } else if (warp < 8) {
+    // ------------------------------------------------------------ softmax warps
     const int quarter = warp & 3;  // TMEM lane quarter
-    const int t = warp >> 2;       // query tile
-    const int row = t * 128 + quarter * 32 + lane;
-    const bool warp_live = (t * 128 + quarter * 32) < tokens;
+    const int t = warp >> 2;       // TMEM region
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + t * 256;
     constexpr int kFull = KVP / 32;   // 32-column chunks ...
     constexpr int kTail = KVP % 32;   // ... then a 16-column tail (KVP = 208) or nothing (256)
     int k = 0;
     for (int item = first; item < num_items; item += step, ++k) {
-      const int img = item / heads, head = item - img * heads;
+      const int q = t ^ (k & 1);   // query tile of this item handled in region t
+      const bool warp_live = (q * 128 + quarter * 32) < tokens;
       if (quarter == 0) ATTN_TRACE(8 + 6 * t, k);
       mbar_wait_warp(&s_full[t], k & 1);
       if (quarter == 0) ATTN_TRACE(9 + 6 * t, k);
@@ -556,20 +566,34 @@ attn_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         tmem_st_wait();
         inv_sum = 1.0f / sum;
       }
+      inv_s[t * 128 + quarter * 32 + lane] = inv_sum;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[t]);
       if (quarter == 0) ATTN_TRACE(11 + 6 * t, k);
-
+    }
+  } else {
+    // ------------------------------------------------------------ output warps
+    const int quarter = warp & 3;    // TMEM lane quarter (a warp reaches lanes 32 (warp % 4) ..)
+    const int t = (warp - 9) >> 2;   // TMEM region
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + t * 256;
+    int k = 0;
+    for (int item = first; item < num_items; item += step, ++k) {
+      const int img = item / heads, head = item - img * heads;
+      const int q = t ^ (k & 1);
+      const int row = q * 128 + quarter * 32 + lane;
+      const bool warp_live = (q * 128 + quarter * 32) < tokens;
+      mbar_wait_warp(&p_full[t], k & 1);  // orders the softmax warps' 1/rowsum writes
       mbar_wait_warp(&o_full[t], k & 1);
       if (quarter == 0) ATTN_TRACE(12 + 6 * t, k);
       tc_fence_after();
+      const float inv_sum = inv_s[t * 128 + quarter * 32 + lane];
       if (warp_live) {
         uint32_t r0[32], r1[32];
         tmem_ld_x32(t_row + Cfg::kOCols, r0);
         tmem_ld_x32(t_row + Cfg::kOCols + 32, r1);
         tmem_ld_wait();
-        // O is in registers: hand the tile's TMEM columns back BEFORE converting and storing
+        // O is in registers: hand the region's TMEM columns back BEFORE converting and storing
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&o_empty[t]);

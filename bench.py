@@ -373,6 +373,11 @@ def main():
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
         return run_reference(args)
+    # a hung collective / kernel must not eat the whole GPU lease: after the watchdog period every
+    # thread's Python stack goes to stderr and the process exits
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get("DEVIT_BENCH_WATCHDOG_S", "480")),
+                                      exit=True)
 
     import torch
     import torch.distributed as dist
@@ -801,11 +806,19 @@ def main():
             print(f"[bench] dense arm failed ({type(e).__name__}: {e})", file=sys.stderr)
             torch.cuda.synchronize()
 
-    if rank != 0:
+    def finish():
+        """Leave without tearing the NCCL communicators down: destroy_process_group() blocks for
+        ever once collectives on them have been captured into CUDA graphs that are still alive
+        (seen at N = 2).  Everything has been measured and printed by now."""
+        sys.stdout.flush()
+        sys.stderr.flush()
         if world > 1:
+            torch.cuda.synchronize()
             dist.barrier()
-            dist.destroy_process_group()
-        return
+            os._exit(0)
+
+    if rank != 0:
+        return finish()
 
     # ---- CPU baseline (N = 1) + parity of the GPU logits against it on the same images
     cpu = None
@@ -845,9 +858,7 @@ def main():
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    finish()
 
 
 if __name__ == "__main__":

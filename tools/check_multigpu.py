@@ -31,6 +31,39 @@ def build(dev):
     return multi.to(dev).eval(), fuse.to(dev).eval()
 
 
+def check_cct(world, rank, dev):
+    """BASELINE config C4 shape at a small batch: 4-way decct_7_3x1 + EnsembleCCT sharded over the
+    ranks (MultiCCT.forward_slab -> all-gather -> EnsembleCCT.forward_gathered) against the same
+    ensemble on this GPU alone."""
+    from devit_b200 import cct
+    n_sub, Bc = 4, max(8, B)
+    multi = cct.MultiCCT('decct_7_3x1', num_classes_list=[25] * n_sub, num_sub_models=n_sub,
+                         input_size=32)
+    for s in range(n_sub):
+        multi.models[s].load_state_dict(synth.cct_state_dict(s, n_conv=1, tokens=256, backbone=True))
+    fuse = cct.EnsembleCCT(sub_size=256, teacher_size=None, num_sub_models=n_sub, num_classes=100)
+    fuse.load_state_dict(synth.ensemble_cct_state_dict(n_sub, 256, None, 100))
+    multi, fuse = multi.to(dev).eval(), fuse.to(dev).eval()
+    x = synth.cifar_images(Bc)
+    ok = True
+    for precision in ("bf16", "fp32"):
+        multi.set_precision(precision)
+        fuse.set_precision(precision)
+        plan = parallel.shard_plan(world, rank, n_sub, Bc)
+        group = parallel.make_groups(plan)
+        xs = x[plan.batch_lo:plan.batch_hi].to(dev)
+        sharded = parallel.ShardedEnsemble(multi, fuse, plan, group)(xs)
+        single = fuse(multi(xs))
+        flag = torch.tensor([int(torch.equal(sharded, single)),
+                             int(torch.equal(sharded.argmax(-1), single.argmax(-1)))], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            print(f"[check_multigpu] CCT world={world} {precision}: bit-identical={bool(flag[0])} "
+                  f"argmax-equal={bool(flag[1])}", flush=True)
+        ok = ok and bool(flag[0])
+    return ok
+
+
 def main():
     world, rank = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"])
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -65,6 +98,7 @@ def main():
             print(f"[check_multigpu] world={world} {precision}: bit-identical={bool(flag[0])} "
                   f"argmax-equal={bool(flag[1])} rank0 rel diff={err:.2e}", flush=True)
         ok = ok and bool(flag[1]) and err < 1e-6
+    ok = check_cct(world, rank, dev) and ok
     dist.barrier()
     dist.destroy_process_group()
     if not ok:

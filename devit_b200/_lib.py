@@ -79,6 +79,19 @@ class MlpArgs(C.Structure):
     ]
 
 
+class BlockWeights(C.Structure):
+    _fields_ = [
+        ("dim", C.c_int32), ("num_heads", C.c_int32), ("hidden", C.c_int32),
+        ("ln1_g", C.c_void_p), ("ln1_b", C.c_void_p),
+        ("w_qkv", C.c_void_p), ("b_qkv", C.c_void_p),
+        ("w_proj", C.c_void_p), ("b_proj", C.c_void_p),
+        ("ln2_g", C.c_void_p), ("ln2_b", C.c_void_p),
+        ("w_fc1", C.c_void_p), ("b_fc1", C.c_void_p),
+        ("w_fc2", C.c_void_p), ("b_fc2", C.c_void_p),
+        ("head_gate", C.POINTER(C.c_float)), ("neuron_gate", C.POINTER(C.c_float)),
+    ]
+
+
 class VitDesc(C.Structure):
     _fields_ = [
         ("precision", C.c_int32), ("dim", C.c_int32), ("depth", C.c_int32),
@@ -164,6 +177,11 @@ _SIGS = {
                                   C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                   C.c_int32, C.c_float, C.c_int32, C.c_void_p]),
     "devit_vit_workspace_bytes": (C.c_size_t, [C.POINTER(VitDesc), C.c_int32]),
+    "devit_pack_layer_bytes": (C.c_size_t, [C.POINTER(BlockWeights), C.c_int32]),
+    "devit_pack_layer": (C.c_int, [C.POINTER(BlockWeights), C.c_int32, C.c_int32, C.c_void_p,
+                                   C.c_size_t, C.POINTER(LayerDesc), C.POINTER(C.c_int32),
+                                   C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                   C.POINTER(C.c_int32), C.c_void_p]),
     "devit_vit_forward": (C.c_int, [C.POINTER(VitDesc), C.c_void_p, C.c_int32, C.c_void_p,
                                     C.c_size_t, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                     C.c_int32, C.c_void_p]),

@@ -32,19 +32,27 @@ def sub_streams() -> int:
 
 
 def batch_chunks(n_sub_local: int, batch: int) -> int:
-    """How many chunks the batch is cut into so that a rank has about DEVIT_CHAINS (default 4)
-    independent kernel chains even when it owns a single sub-model (one sub-model per GPU on 4
-    GPUs); chunks never get smaller than DEVIT_MIN_CHUNK images (default 64)."""
-    want = int(os.environ.get('DEVIT_CHAINS', '4'))
+    """How many chunks the batch is cut into.  Default 1: with the current kernels a rank's
+    sub-models are enough independent chains, and cutting one sub-model's batch only shrinks its
+    grids (measured, profiles/r2_time_chain_v2.txt: 1 sub-model x 256 images 2.12 ms as one chain,
+    2.20 ms as 4 x 64).  DEVIT_CHAINS=<n> asks for about n chains per rank (chunks never smaller
+    than DEVIT_MIN_CHUNK images, default 64) for experiments."""
+    want = int(os.environ.get('DEVIT_CHAINS', '0'))
+    if want <= 0:
+        return 1
     min_chunk = max(1, int(os.environ.get('DEVIT_MIN_CHUNK', '64')))
     n = max(1, -(-want // max(1, n_sub_local)))
     return max(1, min(n, batch // min_chunk))
 
 
-def chain_sm_budget(device) -> int:
-    """SMs each concurrent chain's grids are sized for: the chip divided by DEVIT_SM_SHARE
-    (default 2; 1 = whole chip)."""
-    share = max(1, int(os.environ.get('DEVIT_SM_SHARE', '2')))
+def chain_sm_budget(device, n_chains: int = 4) -> int:
+    """SMs each concurrent chain's grids are sized for: half the chip when at least four chains
+    run (two at a time side by side), the whole chip for two or three (measured: 2 sub-models
+    3.87 ms with whole-chip grids on two streams, 4.10 ms on half-chip grids; 4 sub-models 8.08 vs
+    7.79 ms).  DEVIT_SM_SHARE=<d> forces chip / d."""
+    share = int(os.environ.get('DEVIT_SM_SHARE', '0'))
+    if share <= 0:
+        share = 2 if n_chains >= 4 else 1
     sms = torch.cuda.get_device_properties(device).multi_processor_count
     return 0 if share == 1 else max(2, (sms // share) & ~1)
 
@@ -95,7 +103,7 @@ def run_chains(device, tasks, launch):
     fork.record(cur)
     for st in side:
         st.wait_event(fork)
-    prev_budget = L.load().devit_set_sm_budget(chain_sm_budget(device))
+    prev_budget = L.load().devit_set_sm_budget(chain_sm_budget(device, len(tasks)))
     try:
         for k, t in enumerate(tasks):
             st = cur if k % n_st == 0 else side[k % n_st - 1]

@@ -11,8 +11,10 @@ The kept-index lists are integer work and are exposed (``kept_heads`` / ``kept_n
 tests can compare them bit-exactly with the oracle's.
 
 Operand formats follow include/devit_b200.h: bf16 arrays, or fp32 hi/lo split planes for the
-3xTF32 parity mode.  Everything here is one-off host/plumbing work done with torch ops when a
-gate or a parameter changes; it is not on the per-batch path.
+3xTF32 parity mode.  The per-layer compaction + LayerNorm folding runs on the device through the
+C ABI (devit_pack_layer, csrc/pack.cu); the same packing written with torch ops is kept as its
+cross-check (DEVIT_PACK_TORCH=1, tests/test_pack_gpu.py).  One-off work when a gate or a
+parameter changes; not on the per-batch path.
 """
 from __future__ import annotations
 
@@ -53,58 +55,16 @@ class PackedVit:
             self._keep.append(t)
             return t.data_ptr()
 
+        fold = precision == L.DEVIT_BF16 and fold_ln and dim % 128 == 0 and dim <= 768
+        use_torch = os.environ.get('DEVIT_PACK_TORCH', '0') == '1' or device.type != 'cuda'
         for i, blk in enumerate(model.blocks):
-            attn, mlp = blk.attn, blk.mlp
-            nh = attn.num_heads
-            hg = attn.gate.detach().float().cpu()
-            hk = kept_indices(hg)
-            hscale = hg[hk]
-            if hk.numel() == 0:  # every head gated off: keep one, with zeroed proj columns
-                hk, hscale = torch.tensor([0]), torch.tensor([0.0])
-            self.kept_heads.append(hk.clone())
-            hd = dim // nh
-            if hd != 64:
-                raise L.DevitError(f"head_dim {hd} unsupported (the attention kernel is built "
-                                   f"for head_dim 64)")
-            cols = (hk[:, None] * hd + torch.arange(hd)[None, :]).flatten()  # kept q/k/v columns
-            rows = torch.cat([cols + w * dim for w in range(3)])
-            wq = attn.qkv.weight.detach().float().cpu()
-            bq = attn.qkv.bias.detach().float().cpu() if attn.qkv.bias is not None \
-                else torch.zeros(3 * dim)
-            wp = attn.proj.weight.detach().float().cpu()[:, cols] * \
-                hscale.repeat_interleave(hd)[None, :]
-
-            ng = mlp.gate.detach().float().cpu()
-            nk = kept_indices(ng)
-            nscale = ng[nk]
-            self.kept_neurons.append(nk.clone())
-            f = int(nk.numel())
-            f_ld = max(16, (f + 15) // 16 * 16)
-            w1 = torch.zeros(f_ld, dim)
-            b1 = torch.zeros(f_ld)
-            w2 = torch.zeros(dim, f_ld)
-            if f:
-                w1[:f] = mlp.fc1.weight.detach().float().cpu()[nk]
-                b1[:f] = mlp.fc1.bias.detach().float().cpu()[nk]
-                w2[:, :f] = mlp.fc2.weight.detach().float().cpu()[:, nk] * nscale[None, :]
-
-            d = self.layers[i]
-            d.heads, d.hidden, d.hidden_ld = int(hk.numel()), max(f, 1), f_ld
-            d.ln1_g, d.ln1_b = f32(blk.norm1.weight), f32(blk.norm1.bias)
-            d.ln2_g, d.ln2_b = f32(blk.norm2.weight), f32(blk.norm2.bias)
-            wqk, bqk = wq[rows], bq[rows]
-            # (the consumer epilogue combines at most 12 partial row sums = 2 per 128 columns of
-            #  the residual stream: dim <= 768)
-            if precision == L.DEVIT_BF16 and fold_ln and dim % 128 == 0 and dim <= 768:
-                # LayerNorm folding (include/devit_b200.h, devit_gemm_args.ln_stats):
-                # LN(x) W^T + b = rstd (x (gamma.W)^T - mean c1) + c2 with c1 = rowsum of the
-                # folded weights AS THE TENSOR CORE SEES THEM (bf16-rounded), c2 = b + W beta.
-                wqk, d.cs_qkv, bqk = self._fold(wqk, bqk, blk.norm1, f32)
-                w1, d.cs_fc1, b1 = self._fold(w1, b1, blk.norm2, f32)
-            d.w_qkv, d.b_qkv = op(wqk), f32(bqk)
-            d.w_proj, d.b_proj = op(wp), f32(attn.proj.bias)
-            d.w_fc1, d.b_fc1 = op(w1), f32(b1)
-            d.w_fc2, d.b_fc2 = op(w2), f32(mlp.fc2.bias)
+            if blk.attn.num_heads * 64 != dim:
+                raise L.DevitError(f"head_dim {dim // blk.attn.num_heads} unsupported (the "
+                                   f"attention kernel is built for head_dim 64)")
+            if use_torch:
+                self._pack_layer_torch(i, blk, dim, precision, fold, op, f32)
+            else:
+                self._pack_layer_c(i, blk, dim, precision, fold, f32)
 
         pe = model.patch_embed
         desc = L.VitDesc()
@@ -132,6 +92,116 @@ class PackedVit:
         self.desc = desc
         self.tokens = (desc.img // 16) ** 2 + desc.num_prefix
         self.dim = dim
+
+    def _pack_layer_c(self, i, blk, dim, precision, fold, f32):
+        """Gate compaction + LayerNorm folding on the device through the C ABI
+        (devit_pack_layer, csrc/pack.cu)."""
+        attn, mlp = blk.attn, blk.mlp
+        w = L.BlockWeights()
+        w.dim, w.num_heads, w.hidden = dim, attn.num_heads, mlp.hidden_features
+        w.ln1_g, w.ln1_b = f32(blk.norm1.weight), f32(blk.norm1.bias)
+        w.w_qkv = f32(attn.qkv.weight)
+        w.b_qkv = f32(attn.qkv.bias) if attn.qkv.bias is not None else None
+        w.w_proj, w.b_proj = f32(attn.proj.weight), f32(attn.proj.bias)
+        w.ln2_g, w.ln2_b = f32(blk.norm2.weight), f32(blk.norm2.bias)
+        w.w_fc1, w.b_fc1 = f32(mlp.fc1.weight), f32(mlp.fc1.bias)
+        w.w_fc2, w.b_fc2 = f32(mlp.fc2.weight), f32(mlp.fc2.bias)
+        hg = attn.gate.detach().float().cpu().contiguous()
+        ng = mlp.gate.detach().float().cpu().contiguous()
+        if hg.numel() != attn.num_heads or ng.numel() != mlp.hidden_features:
+            raise L.DevitError("gate length does not match num_heads / hidden_features")
+        w.head_gate = C.cast(hg.data_ptr(), C.POINTER(C.c_float))
+        w.neuron_gate = C.cast(ng.data_ptr(), C.POINTER(C.c_float))
+        lib = L.load()
+        nbytes = lib.devit_pack_layer_bytes(C.byref(w), precision)
+        if nbytes == 0:
+            L.check(1)
+        buf = torch.empty(nbytes, device=self.device, dtype=torch.uint8)
+        self._keep.append(buf)
+        kh = (C.c_int32 * attn.num_heads)()
+        kn = (C.c_int32 * mlp.hidden_features)()
+        nh, nn_ = C.c_int32(0), C.c_int32(0)
+        with torch.cuda.device(self.device):
+            L.check(lib.devit_pack_layer(C.byref(w), precision, 1 if fold else 0, buf.data_ptr(),
+                                         nbytes, C.byref(self.layers[i]), kh, C.byref(nh), kn,
+                                         C.byref(nn_), L.stream_ptr(self.device)))
+        self.kept_heads.append(torch.tensor(list(kh[:nh.value]), dtype=torch.int64))
+        self.kept_neurons.append(torch.tensor(list(kn[:nn_.value]), dtype=torch.int64))
+
+    def _pack_layer_torch(self, i, blk, dim, precision, fold, op, f32):
+        """The same packing with torch ops on the host (the cross-check of devit_pack_layer in
+        tests/test_pack_gpu.py; DEVIT_PACK_TORCH=1 selects it)."""
+        attn, mlp = blk.attn, blk.mlp
+        nh = attn.num_heads
+        hg = attn.gate.detach().float().cpu()
+        hk = kept_indices(hg)
+        hscale = hg[hk]
+        if hk.numel() == 0:  # every head gated off: keep one, with zeroed proj columns
+            hk, hscale = torch.tensor([0]), torch.tensor([0.0])
+        self.kept_heads.append(hk.clone())
+        hd = dim // nh
+        cols = (hk[:, None] * hd + torch.arange(hd)[None, :]).flatten()  # kept q/k/v columns
+        rows = torch.cat([cols + w * dim for w in range(3)])
+        wq = attn.qkv.weight.detach().float().cpu()
+        bq = attn.qkv.bias.detach().float().cpu() if attn.qkv.bias is not None \
+            else torch.zeros(3 * dim)
+        wp = attn.proj.weight.detach().float().cpu()[:, cols] * \
+            hscale.repeat_interleave(hd)[None, :]
+        ng = mlp.gate.detach().float().cpu()
+        nk = kept_indices(ng)
+        nscale = ng[nk]
+        self.kept_neurons.append(nk.clone())
+        f = int(nk.numel())
+        f_ld = max(16, (f + 15) // 16 * 16)
+        w1 = torch.zeros(f_ld, dim)
+        b1 = torch.zeros(f_ld)
+        w2 = torch.zeros(dim, f_ld)
+        if f:
+            w1[:f] = mlp.fc1.weight.detach().float().cpu()[nk]
+            b1[:f] = mlp.fc1.bias.detach().float().cpu()[nk]
+            w2[:, :f] = mlp.fc2.weight.detach().float().cpu()[:, nk] * nscale[None, :]
+        d = self.layers[i]
+        d.heads, d.hidden, d.hidden_ld = int(hk.numel()), max(f, 1), f_ld
+        d.ln1_g, d.ln1_b = f32(blk.norm1.weight), f32(blk.norm1.bias)
+        d.ln2_g, d.ln2_b = f32(blk.norm2.weight), f32(blk.norm2.bias)
+        wqk, bqk = wq[rows], bq[rows]
+        if fold:
+            # LayerNorm folding (include/devit_b200.h, devit_gemm_args.ln_stats):
+            # LN(x) W^T + b = rstd (x (gamma.W)^T - mean c1) + c2 with c1 = rowsum of the
+            # folded weights AS THE TENSOR CORE SEES THEM (bf16-rounded), c2 = b + W beta.
+            wqk, d.cs_qkv, bqk = self._fold(wqk, bqk, blk.norm1, f32)
+            w1, d.cs_fc1, b1 = self._fold(w1, b1, blk.norm2, f32)
+        d.w_qkv, d.b_qkv = op(wqk), f32(bqk)
+        d.w_proj, d.b_proj = op(wp), f32(attn.proj.bias)
+        d.w_fc1, d.b_fc1 = op(w1), f32(b1)
+        d.w_fc2, d.b_fc2 = op(w2), f32(mlp.fc2.bias)
+
+    def layer_arrays(self, i):
+        """The packed arrays of layer i as tensors (views of the device buffers the descriptor
+        points into): {'w_qkv', 'b_qkv', 'cs_qkv', 'w_proj', 'w_fc1', 'b_fc1', 'cs_fc1', 'w_fc2'}.
+        Used by the tests that compare devit_pack_layer with the torch packing."""
+        d = self.layers[i]
+        hd, f_ld, dim = d.heads * 64, d.hidden_ld, self.dim
+        bf = self.precision == L.DEVIT_BF16
+
+        def view(ptr, rows, cols, weight):
+            if not ptr:
+                return None
+            dt = torch.bfloat16 if (weight and bf) else torch.float32
+            planes = 2 if (weight and not bf) else 1
+            n = planes * rows * cols
+            nbytes = n * (2 if dt == torch.bfloat16 else 4)
+            for t in self._keep:
+                off = ptr - t.data_ptr()
+                if 0 <= off and off + nbytes <= t.numel() * t.element_size():
+                    flat = t.view(-1).view(torch.uint8)[off:off + nbytes].view(dt)
+                    return flat.view(planes, rows, cols) if planes == 2 else flat.view(rows, cols)
+            raise L.DevitError("descriptor pointer outside every kept buffer")
+
+        return {'w_qkv': view(d.w_qkv, 3 * hd, dim, True), 'b_qkv': view(d.b_qkv, 1, 3 * hd, False),
+                'cs_qkv': view(d.cs_qkv, 1, 3 * hd, False), 'w_proj': view(d.w_proj, dim, hd, True),
+                'w_fc1': view(d.w_fc1, f_ld, dim, True), 'b_fc1': view(d.b_fc1, 1, f_ld, False),
+                'cs_fc1': view(d.cs_fc1, 1, f_ld, False), 'w_fc2': view(d.w_fc2, dim, f_ld, True)}
 
     @staticmethod
     def _fold(w, b, norm, f32):

@@ -374,6 +374,48 @@ typedef struct devit_layer_desc {
   const float* cs_fc1; /* [hidden_ld] */
 } devit_layer_desc;
 
+/* ---------------------------------------------------------------------------------------
+ * devit_pack_layer: one Block's fp32 master parameters + head / neuron gates -> the
+ * gate-compacted (and, optionally, LayerNorm-folded) operands of a devit_layer_desc.
+ *
+ * This is the device-side form of the weight preparation the drop-in modules need whenever a
+ * gate (core/imp_rank.py:65-71, :147-153 assign `m.gate`) or a parameter changes: kept heads
+ * (gate != 0, ascending) select the q/k/v rows of qkv.weight / bias and the columns of
+ * proj.weight (scaled by the gate value); kept neurons select rows of fc1.weight / bias and
+ * columns of fc2.weight (scaled), zero-padded to a multiple of 16.  With fold_ln (DEVIT_BF16
+ * only) qkv / fc1 weights are multiplied by the preceding LayerNorm's gamma, `cs_*` receive the
+ * row sums of the bf16-rounded folded weights and `b_qkv` / `b_fc1` receive b + W beta
+ * (devit_gemm_args.ln_stats).  If every head is gated off, head 0 is kept with zeroed proj
+ * columns.  All parameter pointers are DEVICE pointers (b_qkv may be NULL); the gates are HOST
+ * arrays (NULL = all ones).  `packed` (device, 256-byte aligned, devit_pack_layer_bytes bytes,
+ * owned by the caller) receives every array `out` points at, except ln1/ln2/b_proj/b_fc2, which
+ * alias the inputs.  kept_heads / kept_neurons (HOST, optional, sized num_heads / hidden) receive
+ * the kept indices.  Synchronises `stream` before returning (one-off preparation work).
+ * ------------------------------------------------------------------------------------- */
+typedef struct devit_block_weights {
+  int32_t dim, num_heads, hidden;
+  const float* ln1_g;
+  const float* ln1_b;
+  const float* w_qkv; /* [3*dim, dim] */
+  const float* b_qkv; /* [3*dim] or NULL */
+  const float* w_proj; /* [dim, dim] */
+  const float* b_proj;
+  const float* ln2_g;
+  const float* ln2_b;
+  const float* w_fc1; /* [hidden, dim] */
+  const float* b_fc1;
+  const float* w_fc2; /* [dim, hidden] */
+  const float* b_fc2;
+  const float* head_gate;   /* HOST [num_heads] or NULL */
+  const float* neuron_gate; /* HOST [hidden] or NULL */
+} devit_block_weights;
+
+size_t devit_pack_layer_bytes(const devit_block_weights* w, int32_t precision);
+int devit_pack_layer(const devit_block_weights* w, int32_t precision, int32_t fold_ln,
+                     void* packed, size_t packed_bytes, devit_layer_desc* out,
+                     int32_t* kept_heads, int32_t* num_kept_heads, int32_t* kept_neurons,
+                     int32_t* num_kept_neurons, void* stream);
+
 typedef struct devit_vit_desc {
   int32_t precision; /* DEVIT_BF16 | DEVIT_FP32 */
   int32_t dim;       /* 384 (dedeit) or 768 (teacher); head_dim = 64 */

@@ -16,7 +16,7 @@ HEADER = ROOT / 'include' / 'devit_b200.h'
 PAIRS = [('devit_gemm_seg', L.GemmSeg), ('devit_gemm_args', L.GemmArgs),
          ('devit_mlp_args', L.MlpArgs), ('devit_layer_desc', L.LayerDesc),
          ('devit_vit_desc', L.VitDesc), ('devit_vit_exports', L.VitExports),
-         ('devit_cct_desc', L.CctDesc)]
+         ('devit_cct_desc', L.CctDesc), ('devit_block_weights', L.BlockWeights)]
 
 
 def _c_fields(name, text):

@@ -4,7 +4,7 @@
 set -e
 cd "$(dirname "$0")/../devit_b200/csrc"
 mkdir -p build_trace
-for f in common gemm attention rowops forward mlp cct edge; do
+for f in common gemm attention rowops forward mlp cct edge pack; do
   [ -f $f.cu ] || continue
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo --cudart static \
        -Xcompiler -fPIC -DDEVIT_GEMM_TRACE -c $f.cu -o build_trace/$f.o &

@@ -41,14 +41,17 @@ def timed(subs, x, steps=20):
     return e0.elapsed_time(e1) / steps, out.clone()
 
 
-shapes = [([0, 1, 2, 3], 256), ([0, 1], 256), ([0], 256), ([0], 128)]
-settings = [(1, 64, 1), (4, 64, 1), (4, 64, 2), (4, 32, 2), (8, 32, 2), (8, 32, 4), (4, 64, 4)]
+shapes = [([0], 128), ([0], 256), ([0, 1], 256), ([0, 1, 2, 3], 256)]
+settings = [(1, 64, 1), (2, 64, 1), (2, 64, 2), (4, 32, 1), (4, 32, 2), (8, 16, 1), (4, 64, 1),
+            (4, 64, 2), (8, 32, 1), (8, 32, 2), (16, 16, 1)]
 for subs, b in shapes:
     base = None
     for chains, mc, share in settings:
+        if b // mc * len(subs) < chains and (chains, mc) != (1, 64):
+            continue  # this many chains do not exist at this shape
         os.environ.update(DEVIT_CHAINS=str(chains), DEVIT_MIN_CHUNK=str(mc),
                           DEVIT_SM_SHARE=str(share),
-                          DEVIT_SUB_STREAMS='1' if chains == 1 else '4')
+                          DEVIT_SUB_STREAMS='1' if chains == 1 else str(min(chains, 8)))
         ms, out = timed(subs, xs[b])
         if base is None:
             base = out

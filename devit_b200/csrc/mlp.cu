@@ -30,7 +30,9 @@
 //   * the attention output tile O (128 x 64h bf16 per CTA) is TMA-loaded into the Y buffer and
 //     Wp streams through the W2 ring, one 64-wide head chunk at a time;
 //   * preload: every epilogue warp brings the fp32 residual of its 32 rows x D/4 columns into its
-//     three private 4 KB slots by TMA (requested while the PREVIOUS tile's stores drain), adds bp
+//     two private 4 KB slots by TMA (requested while the PREVIOUS tile's stores drain; the slots
+//     lie over the weight rings and the staging buffer, never over Y, so the next tile's O is
+//     loaded as soon as the last GEMM1 has retired), adds bp
 //     and writes x + bp INTO acc2 (tcgen05.st), so the HBM-latency-bound part of the residual add
 //     happens before the tensor core needs the tile and off the GEMM0 -> GEMM1 path;
 //   * GEMM0: acc2 += O Wp^T (A and B from shared memory, same N = D/2 UMMA pairs as GEMM2),
@@ -72,7 +74,13 @@ struct MlpCfg {
   // buffer (idle until the final epilogue)
   static constexpr int kOffStat = kOffXb;
   static constexpr int kXbBytes = 16 * 2048;
-  static constexpr int kOffBar = kOffXb + kXbBytes;
+  // PROJ: two 4 KB fp32 slots per epilogue warp (store staging of the final epilogue, then the
+  // next tile's residual) laid over the weight rings and the staging buffer -- NOT over Y, so
+  // the next tile's attention output can be loaded as soon as the last GEMM1 has retired
+  static constexpr int kOffPSlots = kOffW1;
+  static constexpr int kPSlotBytes = 32 * 4096;
+  static constexpr int kOffBar = (kOffXb + kXbBytes) > (kOffPSlots + kPSlotBytes)
+                                     ? (kOffXb + kXbBytes) : (kOffPSlots + kPSlotBytes);
   static constexpr int kSmem = kOffBar + 1024 + 1024;
   static constexpr int kAcc1Col = D;                // acc2 = TMEM columns [0, D), acc1 behind it
   static constexpr int kColsPerWarp = D / 4;        // final epilogue: output columns per warp
@@ -243,8 +251,12 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
     int it = 0;
     for (int pt = cluster_id; pt < num_pairs; pt += num_clusters, ++it) {
       const int m0 = (pt * 2 + cta_rank) * 128;
-      if constexpr (PROJ) mbar_wait_warp(x_done, it & 1);  // residual slots of this tile drained
-      else if (it >= 1) mbar_wait_warp(y_free, (it - 1) & 1);
+      if constexpr (PROJ) {
+        // Y is dead once the previous tile's last GEMM1 has retired (the fp32 slots do not use it)
+        if (it >= 1) mbar_wait_warp(y_empty, (it - 1) & 1);
+      } else if (it >= 1) {
+        mbar_wait_warp(y_free, (it - 1) & 1);
+      }
       if (elect_one()) {
         const uint32_t bar = mapa_u32(smem_u32(y_full), 0);
         if constexpr (PROJ) {
@@ -258,6 +270,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
           for (int a = 0; a < kAtoms; ++a) tma_load_2d_cg2(smem + a * 16384, &tmY, bar, a * 64, m0);
         }
       }
+      // PROJ: the rings host this tile's residual slots until the preload has drained them
+      if constexpr (PROJ) mbar_wait_warp(x_done, it & 1);
       for (int c = 0; c < NC; ++c, ++g1) {
         const int s = g1 & 1;
         mbar_wait_warp(&w1_empty[s], ((g1 >> 1) & 1) ^ 1);
@@ -340,9 +354,11 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
           // GEMM0: acc2 (= x + bp, preloaded by the epilogue warps of both CTAs) += O Wp^T, one
           // 64-wide head chunk per W2-ring slot
           mbar_wait_warp(x_loaded, it & 1);
+          MLP_TRACE(0, 400 + it * 8 + 7);
           for (int a = 0; a < p.proj_chunks; ++a, ++gw) {
             const int ws = gw & 1;
             mbar_wait_warp(&w2_full[ws], (gw >> 1) & 1);
+            MLP_TRACE(1, 400 + it * 8 + a);
             tc_fence_after();
             const uint64_t da = make_sw128_desc(smem_u32(smem) + a * 16384, 1024, 16);
             const uint32_t sw = smem_u32(smem + kOffW2 + ws * kW2Slot);
@@ -415,15 +431,19 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
     const uint32_t acc2_empty_leader = mapa_u32(smem_u32(acc2_empty), 0);
     const uint32_t y_ready_leader = mapa_u32(smem_u32(y_ready), 0);
     const uint32_t x_loaded_leader = mapa_u32(smem_u32(x_loaded), 0);
-    // PROJ: request the fp32 residual chunks of tile `m_tile` into this warp's private slots
-    // (chunks [j0, j1)); the slots must have been drained by the warp's own earlier stores
-    auto request_resid = [&](int m_tile, int j0, int j1) {
+    // PROJ: this warp's two private fp32 slots.  Final epilogue: chunk j is staged in slot
+    // j & 1.  Residual of the next tile: chunk j goes to slot rs(j), chosen so that the slot whose
+    // store was committed FIRST is re-armed first (3 chunks: stores used slots 0,1,0 -> residual
+    // chunks use 1,0,1; 2 chunks: 0,1 -> 0,1).
+    uint8_t* pslot = smem + Cfg::kOffPSlots + ew * 2 * 4096;
+    auto rs = [](int j) -> int { return (j + (kSlots == 3 ? 1 : 0)) & 1; };
+    uint32_t pphase = 0;  // parity bits of rbar[0], rbar[1]
+    // request residual chunk j of tile `m_tile` into slot rs(j) (the slot must be drained)
+    auto request_resid = [&](int m_tile, int j) {
       if (elect_one()) {
-        for (int s2 = j0; s2 < j1; ++s2) {
-          mbar_expect_tx(&rbar[s2], 4096);
-          tma_load_2d(slots + s2 * 4096, &tmX, &rbar[s2], sub * kColsPerWarp + s2 * 32,
-                      m_tile + quarter * 32);
-        }
+        mbar_expect_tx(&rbar[rs(j)], 4096);
+        tma_load_2d(pslot + rs(j) * 4096, &tmX, &rbar[rs(j)], sub * kColsPerWarp + j * 32,
+                    m_tile + quarter * 32);
       }
       __syncwarp();
     };
@@ -442,21 +462,31 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         const int rr = quarter * 32 + lane;  // row inside the CTA's 128
         // ---- preload: acc2 <- x + bp.  The residual chunks were requested into this warp's own
         //      slots while the previous tile's stores drained (here for the CTA's first tile).
-        if (it == 0) request_resid(m0, 0, kSlots);
+        if (it == 0) {
+          request_resid(m0, 0);
+          if (kSlots >= 2) request_resid(m0, 1);
+        }
         if (warp == 2) MLP_TRACE(12, it);
 #pragma unroll 1
         for (int j = 0; j < kSlots; ++j) {
           const int col0 = sub * kColsPerWarp + j * 32;
+          const int sl = rs(j);
           uint32_t r[32];
           float* v = reinterpret_cast<float*>(r);
-          mbar_wait_warp(&rbar[j], it & 1);
-          const uint8_t* bsl = slots + j * 4096;
+          mbar_wait_warp(&rbar[sl], (pphase >> sl) & 1u);
+          pphase ^= 1u << sl;
+          const uint8_t* bsl = pslot + sl * 4096;
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
             const float4 t = *reinterpret_cast<const float4*>(bsl + mlp_off(lane, g));
             const float4 b = __ldg(reinterpret_cast<const float4*>(p.bp + col0) + g);
             v[4 * g] = t.x + b.x; v[4 * g + 1] = t.y + b.y;
             v[4 * g + 2] = t.z + b.z; v[4 * g + 3] = t.w + b.w;
+          }
+          if (j + 2 < kSlots) {  // the slot has been read by every lane: fetch chunk j + 2
+            __syncwarp();
+            fence_proxy_async_smem();
+            request_resid(m0, j + 2);
           }
           tmem_st_x32(tmem_base + lane_off + col0, r);
         }
@@ -641,7 +671,14 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
           }
         }
         float* v = reinterpret_cast<float*>(r);
-        uint8_t* bsl = slots + j * 4096;
+        uint8_t* bsl = PROJ ? pslot + (j & 1) * 4096 : slots + j * 4096;
+        if constexpr (PROJ) {
+          // two slots: chunk j reuses the slot of chunk j - 2 once that store has been read
+          if (j >= 2) {
+            if (elect_one()) bulk_wait_read<1>();
+            __syncwarp();
+          }
+        }
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
           const float4 t = __ldg(reinterpret_cast<const float4*>(p.b2 + col0) + g);
@@ -663,8 +700,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
               make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
         if constexpr (PROJ) {
           // bf16 copy straight from registers: this lane's 32 values are 64 contiguous bytes of
-          // its row = two full 32-byte sectors (STG.256).  No staging tile, so nothing in this loop
-          // waits for the TMA engine and all three fp32 stores of the warp queue up back to back.
+          // its row = two full 32-byte sectors (STG.256): no staging tile.
           if (p.xb_out && row < p.M) {
             uint32_t* dst = reinterpret_cast<uint32_t*>(p.xb_out + static_cast<long long>(row) * D + col0);
 #pragma unroll
@@ -727,21 +763,15 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
       // the loaders may reuse Y and the rings once every warp's stores have drained its slots
       // (PROJ: ... and the next tile's preload has consumed the residual re-armed into them)
       if constexpr (PROJ) {
-        // slot j is re-armed with the next tile's residual as soon as ITS store has been read
-        // (one bulk group per chunk, oldest first)
-        if (elect_one()) bulk_wait_read<kSlots - 1>();
+        // re-arm the slots with the next tile's residual as soon as their stores have been read
+        // (one bulk group per chunk, oldest first): chunk 0 -> rs(0) after all but the newest
+        // group, chunk 1 -> rs(1) after the newest; a third chunk follows in the preload
+        if (elect_one()) bulk_wait_read<1>();
         __syncwarp();
-        if (has_next) request_resid(m_next, 0, 1);
-        if constexpr (kSlots >= 2) {
-          if (elect_one()) bulk_wait_read<kSlots - 2>();
-          __syncwarp();
-          if (has_next) request_resid(m_next, 1, 2);
-        }
-        if constexpr (kSlots >= 3) {
-          if (elect_one()) bulk_wait_read<0>();
-          __syncwarp();
-          if (has_next) request_resid(m_next, 2, 3);
-        }
+        if (has_next) request_resid(m_next, 0);
+        if (elect_one()) bulk_wait_read<0>();
+        __syncwarp();
+        if (has_next && kSlots >= 2) request_resid(m_next, 1);
       } else {
         if (elect_one()) {
           bulk_wait_read<0>();

@@ -8,7 +8,7 @@ from devit_b200 import _lib as L  # noqa: E402
 import os
 F = int(sys.argv[1]) if len(sys.argv) > 1 else 928
 H = int(os.environ.get('TIME_MLP_PROJ', '0'))  # > 0: the variant with the projection in front
-M, D = 256 * 198, 384
+M, D = int(os.environ.get('TRACE_MLP_BATCH', '256')) * 198, 384
 g = torch.Generator(device="cuda").manual_seed(0)
 x = torch.randn(M, D, device="cuda", generator=g)
 xb, stats = L.rowstats(x)
@@ -50,6 +50,7 @@ for it in range(3):
         print(f"tile {it}: mma wait O {r(7,it)} got {r(8,it)} GEMM0 issued {r(18,it)} y_ready {r(19,it)} | "
               f"epi0 wait p_full {r(12,it)} got {r(13,it)} done {r(14,it)} | final: acc2_full {r(16,it*4+3)} "
               f"chunks done {[r(17, it * 4 + j) for j in range(3)]} stores drained {r(15,it*4+3)}")
+        print(f"   GEMM0: x_loaded seen {r(0, 400 + it * 8 + 7)}  Wp chunk landed {[r(1, 400 + it * 8 + a) for a in range(H)]}")
     else:
         print(f"tile {it}: mma wait Y {r(7,it)} got {r(8,it)} | epi wait acc2 {r(12,it)} got {r(13,it)} final done {r(14,it)}")
         print("   final chunks [before resid wait, resid landed, chunk done]: " + "  ".join(

@@ -31,6 +31,12 @@ def sub_streams() -> int:
     return int(os.environ.get('DEVIT_SUB_STREAMS', '4'))
 
 
+def collapse_head() -> bool:
+    """EnsMLP evaluates its two Linears per token kind as one pre-multiplied GEMM (see
+    EnsMLP._collapsed); DEVIT_COLLAPSE_HEAD=0 keeps the four separate GEMMs."""
+    return os.environ.get('DEVIT_COLLAPSE_HEAD', '1') != '0'
+
+
 def batch_chunks(n_sub_local: int, batch: int) -> int:
     """How many chunks the batch is cut into.  Default 1: with the current kernels a rank's
     sub-models are enough independent chains, and cutting one sub-model's batch only shrinks its
@@ -250,7 +256,17 @@ class EnsMLP(nn.Module):
         """Operand slab [n, kinds, B, D] for a list of [B, D] tensors (+ which kind to read)."""
         prec = _PREC[self.precision]
         if isinstance(lst, FeatureList) and lst.slab_op is not None:
-            return lst.slab_op, lst.kind
+            # the slab is a second copy of the features: use it only while every list entry still
+            # IS the slab's view (same storage, untouched since) and the operand format matches
+            # this head's precision; otherwise stack the tensors like the reference does
+            f32, op = lst.slab_f32, lst.slab_op
+            fresh = len(lst) == f32.shape[0] and all(
+                torch.is_tensor(t) and t.data_ptr() == f32[j, lst.kind].data_ptr() and
+                t._version == f32._version for j, t in enumerate(lst))
+            fmt_ok = (op.dim() == 4 and op.dtype == torch.bfloat16) if prec == L.DEVIT_BF16 \
+                else (op.dim() == 5 and op.dtype == torch.float32)
+            if fresh and fmt_ok:
+                return op, lst.kind
         if not lst[0].is_cuda:
             raise L.DevitError("EnsMLP runs on CUDA (sm_100) tensors only; no CPU fallback")
         stacked = torch.stack([t.float() for t in lst], 0).unsqueeze(1).contiguous()  # [n,1,B,D]
@@ -282,6 +298,59 @@ class EnsMLP(nn.Module):
         return L.gemm(a, pk.w, precision=prec, m=B, segs=segs, bias=pk.b, out_kind=out_kind,
                       tag=6, **epi)
 
+    def _collapsed(self, device):
+        """Eval-time algebra: the two Linears of a token kind have NO activation between them
+        (models/ensemble_models.py:79-84), so logits = (Wc fc + Wd fd + b) / 2 with
+        Wk = classifier_k.weight @ mlp_k.weight (computed in fp64 here), b = sum_k
+        (classifier_k.weight @ mlp_k.bias + classifier_k.bias).  The whole head becomes ONE
+        K-segmented GEMM over the gathered slab (two when 2 n > 8 segments) instead of four
+        launches, and the 768-wide intermediate is never rounded."""
+        from . import packing
+        ver = (self.precision, str(device), packing.module_version(self))
+        hit = self.__dict__.get('_collapsed_pack')
+        if hit is None or hit[0] != ver:
+            prec = _PREC[self.precision]
+            ws, b = [], 0
+            for kind in ('cls', 'dist'):
+                cl = getattr(self, f'{kind}_classifier')
+                w, bb = cl.weight.detach().double(), cl.bias.detach().double()
+                if self.teacher_size is not None:
+                    ml = getattr(self, f'{kind}_mlp')
+                    bb = w @ ml.bias.detach().double() + bb
+                    w = w @ ml.weight.detach().double()
+                ws.append(w)
+                b = b + bb
+            wcat = torch.cat(ws, 1).float().to(device)                    # [C, 2 n D]
+            hit = (ver, (L.to_operand(wcat, prec), b.float().to(device).contiguous(),
+                         [L.to_operand(w.float().to(device), prec) for w in ws],
+                         [(bb_.float().to(device).contiguous()) for bb_ in (b * 0, b)]))
+            self.__dict__['_collapsed_pack'] = hit
+        return hit[1]
+
+    def _head_collapsed(self, slab, order):
+        """logits from an operand slab [n, 2, B, D] holding both token kinds."""
+        prec = _PREC[self.precision]
+        s4 = slab if prec == L.DEVIT_BF16 else slab[0]
+        n, kinds, B, D = s4.shape
+        order = list(range(n)) if order is None else list(order)
+        if sorted(order) != list(range(n)) or kinds != 2 or n * D != self.sum_feature_dim:
+            raise L.DevitError(f"EnsMLP: slab {tuple(s4.shape)} / order {order} does not match "
+                               f"{self.num_sub} sub-models x {self.sub_size} features")
+        wcat, bias, wk, bk = self._collapsed(slab.device)
+        a = slab.view(n * kinds * B, D) if prec == L.DEVIT_BF16 else slab.view(2, n * kinds * B, D)
+        if 2 * n <= 8:
+            segs = sorted((((j * kinds + k) * B, 0, (k * n + order[j]) * D, D)
+                           for k in range(2) for j in range(n)), key=lambda sg: sg[2])
+            return L.gemm(a, wcat, precision=prec, m=B, segs=segs, bias=bias, out_kind=L.OUT_F32,
+                          alpha=0.5, tag=6)
+        out = None
+        for k in range(2):  # 2 n > 8 K-segments: one GEMM per token kind, the second averages
+            segs = sorted((((j * kinds + k) * B, 0, order[j] * D, D) for j in range(n)),
+                          key=lambda sg: sg[2])
+            out = L.gemm(a, wk[k], precision=prec, m=B, segs=segs, bias=bk[k], out_kind=L.OUT_F32,
+                         tag=6, **({} if k == 0 else dict(resid=out, alpha=0.5)))
+        return out
+
     def _lin(self, name, a, out_kind, **epi):
         prec = _PREC[self.precision]
         pk = self._packed(a.device)[name]
@@ -294,6 +363,8 @@ class EnsMLP(nn.Module):
         the layout an all-gather of the per-rank [2, B, D] blocks produces.  'deit' models."""
         prec = _PREC[self.precision]
         opk = L.OUT_BF16 if prec == L.DEVIT_BF16 else L.OUT_F32_SPLIT
+        if collapse_head() and 'deit' in self.model and 'vit' not in self.model:
+            return self._head_collapsed(slab, order)
         if self.teacher_size is not None:
             hc = self._fuse(slab, 0, 'cls_mlp', opk, order)
             hd = self._fuse(slab, 1, 'dist_mlp', opk, order)
@@ -322,6 +393,8 @@ class EnsMLP(nn.Module):
             cls_list, dist_list = x
             cslab, ckind = self._slab_of(cls_list, cls_list[0].device)
             dslab, dkind = self._slab_of(dist_list, dist_list[0].device)
+            if collapse_head() and not want_tokens and cslab is dslab and (ckind, dkind) == (0, 1):
+                return self._head_collapsed(cslab, None)
             if self.teacher_size is not None:
                 hk = L.OUT_F32 if want_tokens else opk
                 hc = self._fuse(cslab, ckind, 'cls_mlp', hk)

@@ -328,3 +328,53 @@ def test_teacher_output_qkv_fused_tuple_api():
     assert qkvs[5][0].shape == (2, 12, 198, 64) and qkvs[5][0].dtype == torch.bfloat16
     lw = t.forward_features(x, output_qkv=True, output_att=True)[1]
     assert rel(qkvs[5][0], lw[5][0]) < 2e-2 and rel(qkvs[11][2], lw[11][2]) < 2e-2
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_collapsed_fusion_head_matches_the_four_gemm_head(precision, monkeypatch):
+    """Eval-time EnsMLP = ONE pre-multiplied K-segmented GEMM (no activation sits between the two
+    Linears of a token kind, models/ensemble_models.py:79-84); it must agree with the four-GEMM
+    evaluation and with the reference golden logits."""
+    mv, fuse = make_ensemble(precision, True)
+    x = synth.images(B).cuda()
+    monkeypatch.setenv('DEVIT_COLLAPSE_HEAD', '0')
+    four = fuse(mv(x))
+    monkeypatch.setenv('DEVIT_COLLAPSE_HEAD', '1')
+    c0 = L.load().devit_launch_count()
+    feats = mv(x)
+    c1 = L.load().devit_launch_count()
+    one = fuse(feats)
+    assert L.load().devit_launch_count() - c1 == 1  # the whole head is a single launch
+    assert c1 > c0
+    assert rel(one, four) < (2e-5 if precision == 'fp32' else 8e-3)
+    assert rel(one, G['shrunk_logits']) < TOL[precision]
+    # distill=True in training mode needs the 768-wide tokens: that path keeps the two-level form
+    fuse.train()
+    tok, logits = fuse(mv(x), distill=True)
+    fuse.eval()
+    assert tok[0].shape == (B, 768) and rel(logits, G['shrunk_logits']) < TOL[precision]
+
+
+def test_ensmlp_does_not_trust_a_stale_slab():
+    """the FeatureList carries a second copy of the features (the operand slab); an
+    entry that was replaced or edited in place must win over the slab, like torch.stack(list)."""
+    mv, fuse = make_ensemble('fp32', False)
+    x = synth.images(B).cuda()
+    cls, dist = mv(x)
+    base = fuse((cls, dist))
+    # replace one entry: the result must follow the new tensor, not the stale slab
+    cls2, dist2 = mv(x)
+    cls2[1] = torch.zeros_like(cls2[1])
+    out = fuse((cls2, dist2))
+    ref_cls = [c.clone() for c in cls]
+    ref_cls[1].zero_()
+    want = fuse(([t for t in ref_cls], [t.clone() for t in dist]))
+    assert rel(out, want) < 1e-5 and rel(out, base) > 1e-3
+    # in-place edit of an entry (bumps the version counter of the slab storage)
+    cls3, dist3 = mv(x)
+    cls3[2].mul_(0.0)
+    out3 = fuse((cls3, dist3))
+    ref3 = [c.clone() for c in cls]
+    ref3[2].zero_()
+    want3 = fuse((ref3, [t.clone() for t in dist]))
+    assert rel(out3, want3) < 1e-5

@@ -393,7 +393,7 @@ class MultiCCT(nn.Module):
         from .ensemble import FeatureList
         f32, op = self.forward_slab(x)
         out = FeatureList(f32[s, 0] for s in range(f32.shape[0]))
-        out.slab_f32, out.slab_op, out.kind = f32, op, 0
+        out.slab_f32, out.slab_op, out.kind, out.slab_version = f32, op, 0, f32._version
         return out
 
 
@@ -459,8 +459,8 @@ class EnsembleCCT(nn.Module):
         feats = sub_model_features
         slab = getattr(feats, 'slab_op', None)
         n = len(feats)
-        if slab is None or any(feats[j].data_ptr() != feats.slab_f32[j, 0].data_ptr()
-                               for j in range(n)):
+        if slab is None or feats.slab_f32._version != feats.slab_version or \
+                any(feats[j].data_ptr() != feats.slab_f32[j, 0].data_ptr() for j in range(n)):
             # plain list of tensors (or a list whose entries were replaced): stack, as the
             # reference does (models/ensemble_models.py:139)
             B = feats[0].shape[0]

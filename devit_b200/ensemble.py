@@ -127,6 +127,7 @@ class FeatureList(list):
     slab_f32 = None   # [n_sub, n_kind, B, D] fp32
     slab_op = None    # same in GEMM-operand format (bf16, or [2, n_sub, n_kind, B, D] split)
     kind = 0          # 0 = cls, 1 = dist
+    slab_version = -1  # slab_f32._version when the list was built (in-place edits bump it)
 
 
 class MultiViT(nn.Module):
@@ -202,12 +203,12 @@ class MultiViT(nn.Module):
         n = f32.shape[0]
         if 'vit' in self.model:  # e.g. 'devit' (note: 'vit' is not a substring of 'dedeit')
             out = FeatureList(f32[s, 0] for s in range(n))
-            out.slab_f32, out.slab_op, out.kind = f32, op, 0
+            out.slab_f32, out.slab_op, out.kind, out.slab_version = f32, op, 0, f32._version
             return out
         cls = FeatureList(f32[s, 0] for s in range(n))
         dist = FeatureList(f32[s, 1] for s in range(n))
-        cls.slab_f32, cls.slab_op, cls.kind = f32, op, 0
-        dist.slab_f32, dist.slab_op, dist.kind = f32, op, 1
+        cls.slab_f32, cls.slab_op, cls.kind, cls.slab_version = f32, op, 0, f32._version
+        dist.slab_f32, dist.slab_op, dist.kind, dist.slab_version = f32, op, 1, f32._version
         return cls, dist
 
 
@@ -261,8 +262,8 @@ class EnsMLP(nn.Module):
             # this head's precision; otherwise stack the tensors like the reference does
             f32, op = lst.slab_f32, lst.slab_op
             fresh = len(lst) == f32.shape[0] and all(
-                torch.is_tensor(t) and t.data_ptr() == f32[j, lst.kind].data_ptr() and
-                t._version == f32._version for j, t in enumerate(lst))
+                torch.is_tensor(t) and t.data_ptr() == f32[j, lst.kind].data_ptr()
+                for j, t in enumerate(lst)) and f32._version == lst.slab_version
             fmt_ok = (op.dim() == 4 and op.dtype == torch.bfloat16) if prec == L.DEVIT_BF16 \
                 else (op.dim() == 5 and op.dtype == torch.float32)
             if fresh and fmt_ok:

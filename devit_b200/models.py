@@ -426,6 +426,12 @@ class VisionTransformer(nn.Module):
                 C.byref(pk.desc), img_ptr, pat_ptr, pplane, nb, ws.data_ptr(), ws.numel(),
                 at(feats_f32, b0 * D), at(feats_op, b0 * D), plane, L.ptr(x_out), num_layers,
                 C.byref(ex), L.stream_ptr(x.device)))
+        # the observers (neuron_output / head_output, read by core/imp_rank.py) now belong to an
+        # older batch: mark them stale so the next read re-runs THIS batch through the layer-wise
+        # path.  `_last_input` aliases the caller's tensor (no copy of a 154 MB batch): a caller
+        # that overwrites the buffer before reading an observer ranks the new contents.
+        if rows is None:
+            self._last_input, self._observers_stale = x, True
 
     def _feature_slabs(self, B, device, want_op=False):
         f32 = torch.empty(self.num_tokens, B, self.embed_dim, device=device)
@@ -474,7 +480,8 @@ class VisionTransformer(nn.Module):
         layer-wise path.  `export_qkv_layers` (None = all layers) limits which layers are kept;
         the others are None.  Used when no head is gated off (q/k/v of gated heads do not exist
         in a compacted model).  q, k, v: [B, H, N, hd] views like the reference's
-        (models/de_vit.py:67-68), bf16 in the bf16 mode, fp32 (hi + lo) in the fp32 mode."""
+        (models/de_vit.py:67-68), fp32 in both modes (bf16 values widened / hi + lo), the dtype the
+        layer-wise path returns."""
         x = self._check_input(x)
         B = x.shape[0]
         pk = self.packed(x.device)
@@ -503,7 +510,9 @@ class VisionTransformer(nn.Module):
         self._last_input, self._observers_stale = x, True
         qkvs = [None] * depth
         for l, t in bufs.items():
-            t = t if prec == L.DEVIT_BF16 else t[0] + t[1]
+            # fp32 in both precision modes, like the layer-wise path (Attention.forward): the
+            # dtype of q/k/v must not depend on which path served the call
+            t = t.float() if prec == L.DEVIT_BF16 else t[0] + t[1]
             q, k, v = t.view(B, pk.tokens, 3, H, 64).permute(2, 0, 3, 1, 4).unbind(0)
             qkvs[l] = (q, k, v)
         tokens = self._pre_logits(f32[0]) if self.dist_token is None else (f32[0], f32[1])

@@ -305,6 +305,8 @@ def test_output_qkv_on_the_fused_path(precision):
     # the layer-wise path (any other flag) gives the same tensors within the mode's rounding
     lw = m(x.cuda(), output_qkv=True, output_att=True)
     assert rel(lw['qkv'][5][2], g5[2].float()) < tol
+    # ... and the same dtype whichever path served the call
+    assert g5[2].dtype == lw['qkv'][5][2].dtype == torch.float32
     # selected layers only
     m.export_qkv_layers = [5]
     sel = m(x.cuda(), output_qkv=True)['qkv']

@@ -327,7 +327,7 @@ def test_teacher_output_qkv_fused_tuple_api():
     x = synth.images(2).cuda()
     feats, qkvs, att, enc = t.forward_features(x, output_qkv=True)
     assert len(qkvs) == 12 and att == [] and enc == []
-    assert qkvs[5][0].shape == (2, 12, 198, 64) and qkvs[5][0].dtype == torch.bfloat16
+    assert qkvs[5][0].shape == (2, 12, 198, 64) and qkvs[5][0].dtype == torch.float32
     lw = t.forward_features(x, output_qkv=True, output_att=True)[1]
     assert rel(qkvs[5][0], lw[5][0]) < 2e-2 and rel(qkvs[11][2], lw[11][2]) < 2e-2
 

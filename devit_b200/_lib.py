@@ -76,6 +76,7 @@ class MlpArgs(C.Structure):
         ("w2", C.c_void_p), ("b2", C.c_void_p), ("x", C.c_void_p), ("xb_out", C.c_void_p),
         ("stats_out", C.c_void_p),
         ("o", C.c_void_p), ("w_proj", C.c_void_p), ("b_proj", C.c_void_p), ("proj_k", C.c_int32),
+        ("x_lo_in", C.c_void_p), ("x_lo_out", C.c_void_p),
     ]
 
 
@@ -453,7 +454,7 @@ def rowstats(x):
 
 @on_operand_device
 def mlp_fused(x, xb, ln_stats, w1, c1, c2, w2, b2, eps, xb_out=None, stats_out=None,
-              o=None, w_proj=None, b_proj=None):
+              o=None, w_proj=None, b_proj=None, x_lo_in=None, x_lo_out=None):
     """In-place x += gelu(LN(x) W1^T + b1) W2^T + b2 (LayerNorm folded); see devit_mlp_fused.
     With `o` / `w_proj` / `b_proj` the attention-output projection runs in front in the same
     kernel (x1 = x + o Wp^T + bp, then the MLP on x1; `xb` / `ln_stats` are not used)."""
@@ -466,6 +467,7 @@ def mlp_fused(x, xb, ln_stats, w1, c1, c2, w2, b2, eps, xb_out=None, stats_out=N
     a.xb_out, a.stats_out = ptr(xb_out), ptr(stats_out)
     if o is not None:
         a.o, a.w_proj, a.b_proj, a.proj_k = ptr(o), ptr(w_proj), ptr(b_proj), o.shape[1]
+    a.x_lo_in, a.x_lo_out = ptr(x_lo_in), ptr(x_lo_out)
     check(load().devit_mlp_fused(C.byref(a), stream_ptr()))
     return x
 

@@ -61,7 +61,9 @@ static int plan_layout(const devit_vit_desc* d, int batch, VitLayout* L) {
   L->off_o = off;
   off = align_up(off + static_cast<size_t>(L->M) * L->max_heads * 64 * pe, 256);
   L->off_hid = off;
-  off = align_up(off + static_cast<size_t>(L->M) * L->max_hidden_ld * pe, 256);
+  // (also holds the lo plane of the split residual stream: at least dim columns)
+  off = align_up(off + static_cast<size_t>(L->M) *
+                           (L->max_hidden_ld > d->dim ? L->max_hidden_ld : d->dim) * pe, 256);
   L->off_stats = off;
   L->stat_parts = 2 * ((d->dim + 127) / 128);
   off = align_up(off + static_cast<size_t>(L->M) * L->stat_parts * 2 * sizeof(float), 256);
@@ -130,6 +132,9 @@ static int run_blocks(const devit_layer_desc* layers, int nl, int prec, int D, f
   }
   static int fused_proj_cache = kEnvUnread;  // DEVIT_FUSED_PROJ=0: separate proj GEMM (comparison)
   const bool fused_proj = env_int("DEVIT_FUSED_PROJ", 1, &fused_proj_cache) != 0;
+  static int split_cache = kEnvUnread;  // DEVIT_SPLIT_RESID=0: fp32 residual stream between layers
+  const bool split_resid = env_int("DEVIT_SPLIT_RESID", 1, &split_cache) != 0;
+  bool resid_is_split = false;
   void* const qkv_ws = qkv;
   for (int l = 0; l < nl; ++l) {
     const devit_layer_desc& w = layers[l];
@@ -178,6 +183,14 @@ static int run_blocks(const devit_layer_desc* layers, int nl, int prec, int D, f
       ma.w2 = w.w_fc2; ma.b2 = w.b_fc2; ma.x = x;
       ma.o = o; ma.w_proj = w.w_proj; ma.b_proj = w.b_proj; ma.proj_k = hd;
       if (l + 1 < nl) { ma.xb_out = y; ma.stats_out = stats; }
+      // between fused layers the residual stream travels as two bf16 planes (hi = y, lo in the
+      // otherwise unused `hid` buffer): 4 instead of 6 bytes stored per element (an SM stores
+      // ~32 B/clk); the first layer reads, and the last one writes, the fp32 stream
+      if (split_resid) {
+        if (resid_is_split) { ma.xb = y; ma.x_lo_in = hid; }
+        if (l + 1 < nl) ma.x_lo_out = hid;
+        resid_is_split = l + 1 < nl;
+      }
       rc = devit_mlp_fused(&ma, stream);
       if (rc) return rc;
       parts = 4;  // the fused kernel emits one partial row sum per dim/4 columns
@@ -477,7 +490,8 @@ static int plan_cct(const devit_cct_desc* d, int batch, CctLayout* L) {
   L->off_y = take(static_cast<size_t>(L->M) * d->dim * pe);
   L->off_qkv = take(static_cast<size_t>(L->M) * 3 * L->max_heads * 64 * pe);
   L->off_o = take(static_cast<size_t>(L->M) * L->max_heads * 64 * pe);
-  L->off_hid = take(static_cast<size_t>(L->M) * L->max_hidden_ld * pe);
+  L->off_hid = take(static_cast<size_t>(L->M) *
+                    (L->max_hidden_ld > d->dim ? L->max_hidden_ld : d->dim) * pe);
   L->off_stats = take(static_cast<size_t>(L->M) * L->stat_parts * 2 * sizeof(float));
   L->off_xn = take(static_cast<size_t>(L->M) * d->dim * 4);
   L->off_a = take(a_b);

@@ -117,6 +117,11 @@ struct MlpParams {
   float* stats_out;
   const float* bp;   // PROJ: attention-output projection bias [D]
   int proj_chunks;   // PROJ: kept heads (64-wide K chunks of O / Wp)
+  // PROJ: the residual stream as two bf16 planes, x = hi + lo (hi doubles as the next QKV GEMM's
+  // operand): an SM stores at most ~32 B/clk, and fp32 x + its bf16 copy are 6 bytes per element
+  // against 4 for hi + lo (profiles/r2_ubench_store_bw.txt)
+  int split_in;      // residual read from the hi / lo planes (tmXHi / tmXLoIn) instead of fp32 x
+  __nv_bfloat16* lo_out;  // != NULL: write hi (xb_out) + lo planes instead of fp32 x + bf16 copy
 };
 
 __device__ __forceinline__ void umma_bf16_ts_cg2(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
@@ -146,7 +151,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1)
 mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmW1,
                  const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmX,
                  const __grid_constant__ CUtensorMap tmXB, const __grid_constant__ CUtensorMap tmWp,
-                 const __grid_constant__ MlpParams p) {
+                 const __grid_constant__ CUtensorMap tmXHi, const __grid_constant__ CUtensorMap tmXLoIn,
+                 const __grid_constant__ CUtensorMap tmXLoOut, const __grid_constant__ MlpParams p) {
   using Cfg = MlpCfg<D>;
   constexpr int kAtoms = Cfg::kAtoms, kYBytes = Cfg::kYBytes, kW1Slot = Cfg::kW1Slot,
                 kW2Slot = Cfg::kW2Slot, kOffW1 = Cfg::kOffW1, kOffW2 = Cfg::kOffW2,
@@ -190,6 +196,11 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
     tma_prefetch_desc(&tmW2);
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmXB);
+    if (PROJ && p.split_in) {
+      tma_prefetch_desc(&tmXHi);
+      tma_prefetch_desc(&tmXLoIn);
+    }
+    if (PROJ && p.lo_out) tma_prefetch_desc(&tmXLoOut);
     mbar_init(y_full, 1);
     mbar_init(y_empty, 1);
     mbar_init(y_free, 16);
@@ -441,9 +452,16 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
     // request residual chunk j of tile `m_tile` into slot rs(j) (the slot must be drained)
     auto request_resid = [&](int m_tile, int j) {
       if (elect_one()) {
+        uint8_t* dst = pslot + rs(j) * 4096;
         mbar_expect_tx(&rbar[rs(j)], 4096);
-        tma_load_2d(pslot + rs(j) * 4096, &tmX, &rbar[rs(j)], sub * kColsPerWarp + j * 32,
-                    m_tile + quarter * 32);
+        if (p.split_in) {  // hi plane -> first 2 KB, lo plane -> second 2 KB ([32 x 64 B], SW64)
+          tma_load_2d(dst, &tmXHi, &rbar[rs(j)], sub * kColsPerWarp + j * 32, m_tile + quarter * 32);
+          tma_load_2d(dst + 2048, &tmXLoIn, &rbar[rs(j)], sub * kColsPerWarp + j * 32,
+                      m_tile + quarter * 32);
+        } else {
+          tma_load_2d(dst, &tmX, &rbar[rs(j)], sub * kColsPerWarp + j * 32,
+                      m_tile + quarter * 32);
+        }
       }
       __syncwarp();
     };
@@ -476,12 +494,34 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
           mbar_wait_warp(&rbar[sl], (pphase >> sl) & 1u);
           pphase ^= 1u << sl;
           const uint8_t* bsl = pslot + sl * 4096;
+          if (p.split_in) {
+            // x = hi + lo: this lane's row is 64 B of each plane, 16-byte chunks 64B-swizzled
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const float4 t = *reinterpret_cast<const float4*>(bsl + mlp_off(lane, g));
-            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bp + col0) + g);
-            v[4 * g] = t.x + b.x; v[4 * g + 1] = t.y + b.y;
-            v[4 * g + 2] = t.z + b.z; v[4 * g + 3] = t.w + b.w;
+            for (int g = 0; g < 4; ++g) {
+              const int so = lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4);
+              const uint4 h4 = *reinterpret_cast<const uint4*>(bsl + so);
+              const uint4 l4 = *reinterpret_cast<const uint4*>(bsl + 2048 + so);
+              const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                v[8 * g + 2 * e] = __uint_as_float(hw[e] << 16) + __uint_as_float(lw[e] << 16);
+                v[8 * g + 2 * e + 1] = __uint_as_float(hw[e] & 0xffff0000u) +
+                                       __uint_as_float(lw[e] & 0xffff0000u);
+              }
+            }
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bp + col0) + g);
+              v[4 * g] += b.x; v[4 * g + 1] += b.y; v[4 * g + 2] += b.z; v[4 * g + 3] += b.w;
+            }
+          } else {
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              const float4 t = *reinterpret_cast<const float4*>(bsl + mlp_off(lane, g));
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bp + col0) + g);
+              v[4 * g] = t.x + b.x; v[4 * g + 1] = t.y + b.y;
+              v[4 * g + 2] = t.z + b.z; v[4 * g + 3] = t.w + b.w;
+            }
           }
           if (j + 2 < kSlots) {  // the slot has been read by every lane: fetch chunk j + 2
             __syncwarp();
@@ -579,8 +619,14 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
           // the TMA loads ask for them (~half a chunk loop ahead)
           if (c == NC / 2 && has_next && elect_one()) {
 #pragma unroll
-            for (int s2 = 0; s2 < kSlots; ++s2)
-              tma_prefetch_l2_2d(&tmX, sub * kColsPerWarp + s2 * 32, m_next + quarter * 32);
+            for (int s2 = 0; s2 < kSlots; ++s2) {
+              if (p.split_in) {  // the residual comes as hi / lo planes
+                tma_prefetch_l2_2d(&tmXHi, sub * kColsPerWarp + s2 * 32, m_next + quarter * 32);
+                tma_prefetch_l2_2d(&tmXLoIn, sub * kColsPerWarp + s2 * 32, m_next + quarter * 32);
+              } else {
+                tma_prefetch_l2_2d(&tmX, sub * kColsPerWarp + s2 * 32, m_next + quarter * 32);
+              }
+            }
             if (sub == 0 && quarter < 2)
               for (int a = quarter; a < p.proj_chunks; a += 2)
                 tma_prefetch_l2_2d(&tmY, a * 64, m_next);
@@ -694,11 +740,39 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
             v[4 * g] += t.x; v[4 * g + 1] += t.y; v[4 * g + 2] += t.z; v[4 * g + 3] += t.w;
           }
         }
+        if (!(PROJ && p.lo_out)) {
 #pragma unroll
-        for (int g = 0; g < 8; ++g)
-          *reinterpret_cast<float4*>(bsl + mlp_off(lane, g)) =
-              make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+          for (int g = 0; g < 8; ++g)
+            *reinterpret_cast<float4*>(bsl + mlp_off(lane, g)) =
+                make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+        }
         if constexpr (PROJ) {
+          if (p.lo_out) {
+            // x -> hi = bf16(x), lo = bf16(x - hi): two [32 x 64 B] planes staged in this slot
+            // (64B swizzle) and stored with one TMA store each: 4 bytes per element leave the SM
+            // instead of 6 (fp32 x + bf16 copy)
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint32_t hw[4], lw[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float a = v[8 * g + 2 * e], b = v[8 * g + 2 * e + 1];
+                hw[e] = pack_bf16x2(a, b);
+                lw[e] = pack_bf16x2(a - __uint_as_float(hw[e] << 16),
+                                    b - __uint_as_float(hw[e] & 0xffff0000u));
+              }
+              const int so = lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4);
+              *reinterpret_cast<uint4*>(bsl + so) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+              *reinterpret_cast<uint4*>(bsl + 2048 + so) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            }
+            fence_proxy_async_smem();
+            if (elect_one()) {
+              tma_store_2d(&tmXB, bsl, col0, row0);
+              tma_store_2d(&tmXLoOut, bsl + 2048, col0, row0);
+              bulk_commit();
+            }
+            __syncwarp();
+          } else {
           // bf16 copy straight from registers: this lane's 32 values are 64 contiguous bytes of
           // its row = two full 32-byte sectors (STG.256): no staging tile.
           if (p.xb_out && row < p.M) {
@@ -720,6 +794,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
             bulk_commit();
           }
           __syncwarp();
+          }
         } else {
           if (j > 0 && p.xb_out) {
             // the previous chunk's stores have read their staging tile
@@ -844,7 +919,7 @@ extern "C" int devit_mlp_fused(const devit_mlp_args* a, void* stream_v) {
                                        MlpCfg<256>::kSmem));
     attr_done[dev & 63] = true;
   }
-  CUtensorMap tY, tW1, tW2, tX, tXB, tWp;
+  CUtensorMap tY, tW1, tW2, tX, tXB, tWp, tXHi, tXLoIn, tXLoOut;
   if (proj) {
     rc = encode_tmap_2d(&tY, a->o, 2, a->proj_k, a->m, a->proj_k, 64, 128, false);
     if (rc) return rc;
@@ -866,6 +941,21 @@ extern "C" int devit_mlp_fused(const devit_mlp_args* a, void* stream_v) {
     rc = encode_tmap_2d_sw64(&tXB, a->xb_out, 2, Dm, a->m, Dm, 32, 32);
     if (rc) return rc;
   }
+  tXHi = tXLoIn = tXLoOut = tXB;
+  if (a->x_lo_in) {
+    DEVIT_REQUIRE(proj && a->xb, "devit_mlp_fused: x_lo_in needs the fused projection (o) and xb "
+                  "(the hi plane)");
+    rc = encode_tmap_2d_sw64(&tXHi, a->xb, 2, Dm, a->m, Dm, 32, 32);
+    if (rc) return rc;
+    rc = encode_tmap_2d_sw64(&tXLoIn, a->x_lo_in, 2, Dm, a->m, Dm, 32, 32);
+    if (rc) return rc;
+  }
+  if (a->x_lo_out) {
+    DEVIT_REQUIRE(proj && a->xb_out, "devit_mlp_fused: x_lo_out needs the fused projection (o) "
+                  "and xb_out (the hi plane)");
+    rc = encode_tmap_2d_sw64(&tXLoOut, a->x_lo_out, 2, Dm, a->m, Dm, 32, 32);
+    if (rc) return rc;
+  }
   MlpParams p;
   p.M = a->m;
   p.F_ld = a->hidden_ld;
@@ -881,6 +971,8 @@ extern "C" int devit_mlp_fused(const devit_mlp_args* a, void* stream_v) {
   p.stats_out = a->stats_out;
   p.bp = a->b_proj;
   p.proj_chunks = proj ? a->proj_k / 64 : 0;
+  p.split_in = a->x_lo_in ? 1 : 0;
+  p.lo_out = static_cast<__nv_bfloat16*>(a->x_lo_out);
   p.trace = g_attn_trace;
   {
     static int stagger = -1;  // DEVIT_MLP_STAGGER=<clocks> (0 = off)
@@ -909,7 +1001,8 @@ extern "C" int devit_mlp_fused(const devit_mlp_args* a, void* stream_v) {
     cfg.numAttrs = pdl_enabled() ? 1 : 0;
     auto kern = Dm == 384 ? (proj ? mlp_fused_kernel<384, true> : mlp_fused_kernel<384, false>)
                           : (proj ? mlp_fused_kernel<256, true> : mlp_fused_kernel<256, false>);
-    DEVIT_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tY, tW1, tW2, tX, tXB, tWp, p));
+    DEVIT_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tY, tW1, tW2, tX, tXB, tWp, tXHi, tXLoIn, tXLoOut,
+                                     p));
   }
   DEVIT_CUDA_OK(cudaGetLastError());
   count_launch();

@@ -233,6 +233,17 @@ typedef struct devit_mlp_args {
   const void* w_proj;
   const float* b_proj;
   int32_t proj_k;
+  /* ---- optional (with `o` only): the residual stream as TWO bf16 planes, x = hi + lo
+   * (hi = bf16(x), lo = bf16(x - hi): 16 mantissa bits, 2^-17 relative), instead of fp32 x plus a
+   * bf16 copy.  An SM stores at most ~32 bytes per clock, so 4 bytes per element instead of 6
+   * shorten the kernel's write-bound final epilogue by a third; hi is at the same time the A
+   * operand of the next layer's LayerNorm-folded QKV GEMM.
+   * x_lo_in  != NULL: the input residual is `xb` (hi plane) + x_lo_in; fp32 `x` is not read.
+   * x_lo_out != NULL: the output is written as `xb_out` (hi plane) + x_lo_out; fp32 `x` is not
+   *                   written (the last layer leaves it NULL so the final norm reads fp32 x).
+   * Planes are bf16 [m, dim], 16-byte aligned; in and out planes may alias (tile-local). */
+  const void* x_lo_in;
+  void* x_lo_out;
 } devit_mlp_args;
 
 int devit_mlp_fused(const devit_mlp_args* args, void* stream);

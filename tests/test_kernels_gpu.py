@@ -166,6 +166,22 @@ def test_proj_mlp_fused(m, f, d, heads):
     yb, st = L.rowstats(y)
     L.mlp_fused(y, yb, st, w1f, c1, c2, w2.bfloat16().contiguous(), b2, eps)
     assert rel(x, y) < 2e-3, rel(x, y)
+    # residual stream as two bf16 planes (x = hi + lo) in and out: same result to 2^-16
+    hi0 = x0.bfloat16()
+    lo0 = (x0 - hi0.float()).bfloat16()
+    hi1 = torch.zeros_like(hi0)
+    lo1 = torch.zeros_like(lo0)
+    so2 = torch.full((4, m, 2), -1.0, device="cuda")
+    xs = torch.full_like(x0, 7.0)  # must stay untouched: fp32 x is neither read nor written
+    L.mlp_fused(xs, hi0, None, w1f, c1, c2, w2.bfloat16().contiguous(), b2, eps, xb_out=hi1,
+                stats_out=so2, o=o, w_proj=wp, b_proj=bp, x_lo_in=lo0, x_lo_out=lo1)
+    torch.cuda.synchronize()
+    assert bool((xs == 7.0).all())
+    got = hi1.float() + lo1.float()
+    # (the 2^-17 input difference flips individual bf16 roundings of Y / H inside the kernel)
+    assert rel(got, x) < 2e-3, rel(got, x)
+    assert rel(hi1.float(), x) < 5e-3              # hi alone is the bf16 copy the QKV GEMM reads
+    assert rel(so2[..., 0].t(), got.view(m, 4, d // 4).sum(-1)) < 1e-3
 
 
 @pytest.mark.parametrize("m", [200, 520, 256 * 160 + 9])

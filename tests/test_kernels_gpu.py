@@ -353,6 +353,29 @@ def test_attention_bf16(batch, tokens, heads):
     assert rel(out, ref) < 1.5e-2, rel(out, ref)
 
 
+@pytest.mark.parametrize("tokens", [198, 256, 150])
+def test_attention_bf16_late_dominant_keys(tokens):
+    """Softmax range handling: keys far down the row (and in the last, partial chunk) beat the
+    first chunk by 72 nats; other rows have their max in chunk 0 and tiny scores elsewhere
+    (underflow side).  (Written for a single-pass softmax variant with an online rescale, measured
+    slower and not kept -- profiles/r2_attn_experiments.txt; the two-pass kernel must pass too.)"""
+    batch, heads = 3, 2
+    qkv = (_mk((batch * tokens, 3 * heads * 64), 17) * 0.25)
+    v = qkv.view(batch, tokens, 3, heads, 64)
+    v[:, :, 0, :, :] *= 0.1                       # small queries ...
+    v[:, 0::2, 0, :, 0] = 24.0                    # ... except a strong component on even rows
+    v[:, :, 1, :, 0] = 0.0
+    v[:, 40, 1, 0, 0] = 24.0                      # head 0: hot key in chunk 1
+    v[:, tokens - 1, 1, 0, 0] = 24.0              # ... and in the last (partial) chunk
+    v[:, 5, 1, 1, 0] = 24.0                       # head 1: hot key inside chunk 0
+    v[:, 100, 1, 1, 0] = -24.0                    # and a strongly negative one later
+    qkv = qkv.bfloat16()
+    out = L.attention(qkv, batch, tokens, heads, 0.125)
+    ref = _attn_ref(qkv.float(), batch, tokens, heads, 0.125)
+    assert torch.isfinite(out.float()).all()
+    assert rel(out, ref) < 1.5e-2, rel(out, ref)
+
+
 @pytest.mark.parametrize("batch,tokens,heads", [(2, 198, 6), (1, 197, 5), (2, 64, 4)])
 def test_attention_fp32(batch, tokens, heads):
     qkv = _mk((batch * tokens, 3 * heads * 64), 7)

@@ -366,6 +366,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--eager-multi", action="store_true",
                     help="N > 1: do not capture the step (NCCL all-gather included) in a CUDA graph")
+    ap.add_argument("--pipeline-depth", type=int, default=0,
+                    help="batches in flight (0 = auto: 2 when the rank runs a single kernel chain)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dense-arm", action="store_true")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
@@ -519,6 +521,48 @@ def main():
     # ---- value: device-resident inputs
     ms_step = timed(step, args.steps)
     value = BATCH / (ms_step / 1e3)
+    one_in_flight = {"value": value, "ms_per_step": ms_step, "launch_mode": launch_mode}
+
+    # ---- a rank with ONE kernel chain (one sub-model per GPU at N >= 4, the single teacher
+    #      model) keeps a second, independent batch in flight on a second stream: consecutive
+    #      batches of an evaluation loop do not depend on each other, and the second chain fills
+    #      the memory-bound phases and partly empty last tile rounds of the first exactly like a
+    #      second sub-model does at N = 1 (parallel.BatchPipeline).  Each slot has its own stream,
+    #      CUDA graph, workspace, output and NCCL communicator.
+    n_chains = 1 if fuse is None else len(plan.subs)
+    depth = args.pipeline_depth if args.pipeline_depth > 0 else (2 if n_chains == 1 else 1)
+    ens_slots = [ens]
+    pipe = None
+    if depth > 1 and graph is not None:
+        for _ in range(depth - 1):
+            if fuse is None:
+                ens_slots.append(parallel.Replica(multi, plan))
+            else:
+                ens_slots.append(parallel.ShardedEnsemble(
+                    multi, fuse, plan, parallel.make_groups(plan) if world > 1 else None,
+                    parallel.make_groups(plan) if world > 1 else None))
+        pipe = parallel.BatchPipeline([(lambda e=e: e(x_dev)) for e in ens_slots])
+        if not all_ranks(all(torch.equal(o, logits) for o in pipe.outs)):
+            raise SystemExit("[bench] a pipelined slot disagrees with the plain step")
+
+        def run_pipe(n):
+            pipe._next = 0
+            pipe.fork()
+            for _ in range(n):
+                pipe.launch()
+            pipe.join()
+
+        run_pipe(args.warmup)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        run_pipe(args.steps)
+        e1.record()
+        barrier()
+        ms_step = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+        value = BATCH / (ms_step / 1e3)
+        launch_mode = f"cuda_graph, {depth} batches in flight (one stream + graph + communicator each)"
 
     # ---- e2e: public API with host buffers; H2D of the step's batch + D2H of its logits inside
     #      the timed region, input copies double-buffered on a copy stream
@@ -532,7 +576,16 @@ def main():
     # the same public call, captured once per input buffer when CUDA graphs are in use (a user
     # serving fixed-shape batches would do the same); eager launches otherwise
     e2e_graphs = None
-    if graph is not None:
+    e2e_pipe = None
+    if pipe is not None:
+        # two input buffers = two slots: buffer b is consumed by slot b (its own stream / graph /
+        # communicator), so the compute of batch i overlaps that of batch i + 1 as in `value`
+        for b in range(2):
+            bufs[b].copy_(x_dev)
+        torch.cuda.synchronize()
+        e2e_pipe = parallel.BatchPipeline([(lambda e=ens_slots[b % depth], b=b: e(bufs[b]))
+                                           for b in range(2)])
+    elif graph is not None:
         ok = True
         try:
             e2e_graphs = []
@@ -554,7 +607,12 @@ def main():
 
     use_stage = world > 1 and fuse is not None and parallel.stage_slice(plan, Bg) is not None
 
+    out_hosts = [out_host, torch.empty_like(out_host).pin_memory()]
+
     def e2e_loop(n):
+        if e2e_pipe is not None:
+            e2e_pipe._next = 0
+            e2e_pipe.fork()
         for i in range(n + 1):
             if i < n:  # prefetch batch i
                 b = i & 1
@@ -565,6 +623,15 @@ def main():
                     else:
                         bufs[b].copy_(x_host, non_blocking=True)
                     ready[b].record(copy_stream)
+            if i > 0 and e2e_pipe is not None:  # compute batch i-1 on slot b's stream
+                b = (i - 1) & 1
+                st = e2e_pipe.streams[b]
+                st.wait_event(ready[b])
+                e2e_pipe.launch()
+                freed[b].record(st)
+                with torch.cuda.stream(st):
+                    out_hosts[b].copy_(e2e_pipe.outs[b], non_blocking=True)
+                continue
             if i > 0:  # compute batch i-1
                 b = (i - 1) & 1
                 main_stream.wait_event(ready[b])
@@ -575,6 +642,8 @@ def main():
                     out = ens(bufs[b])
                 freed[b].record(main_stream)
                 out_host.copy_(out, non_blocking=True)
+        if e2e_pipe is not None:
+            e2e_pipe.join()
         main_stream.synchronize()
 
     # multi-GPU: every model rank of a group needs the same images; rank r uploads rows
@@ -795,13 +864,36 @@ def main():
             for _ in range(3):
                 dstep()
             dms = timed(dstep, args.steps)
+            dmode = "cuda_graph" if gd is not None else "eager"
+            if pipe is not None and gd is not None:  # same batches-in-flight policy as `value`
+                eds = [ed] + [parallel.ShardedEnsemble(md, fd, plan, e.group, None)
+                              for e in ens_slots[1:]]
+                dpipe = parallel.BatchPipeline([(lambda e=e: e(x_dev)) for e in eds])
+
+                def run_dpipe(n):
+                    dpipe._next = 0
+                    dpipe.fork()
+                    for _ in range(n):
+                        dpipe.launch()
+                    dpipe.join()
+
+                run_dpipe(3)
+                torch.cuda.synchronize()
+                t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                barrier()
+                t0.record()
+                run_dpipe(args.steps)
+                t1.record()
+                barrier()
+                dms = max_over_ranks(t0.elapsed_time(t1)) / args.steps
+                dmode = f"cuda_graph, {depth} batches in flight"
             dfl = wd.total_flops_per_image() * BATCH
             dtf = dfl / (dms / 1e3) / 1e12
             dense = {"value": BATCH / (dms / 1e3), "unit": "images/sec", "ms_per_step": dms,
                      "whole_step_tflops": dtf,
                      "frac_of_bf16_burst": dtf / (peaks["bf16_burst"] * world),
                      "flops_per_image": dfl / BATCH,
-                     "launch_mode": "cuda_graph" if gd is not None else "eager"}
+                     "launch_mode": dmode}
         except Exception as e:  # noqa: BLE001
             print(f"[bench] dense arm failed ({type(e).__name__}: {e})", file=sys.stderr)
             torch.cuda.synchronize()
@@ -844,6 +936,8 @@ def main():
         "data": "synthetic",
         "config": wl.config(world, plan),
         "launch_mode": launch_mode,
+        "batches_in_flight": depth if pipe is not None else 1,
+        "one_batch_in_flight": one_in_flight,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "images/sec", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

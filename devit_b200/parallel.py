@@ -163,3 +163,70 @@ class Replica:
     @torch.no_grad()
     def __call__(self, x_group: torch.Tensor) -> torch.Tensor:
         return self.model(x_group)
+
+
+class BatchPipeline:
+    """`depth` copies of one step, each with its own CUDA stream, CUDA graph, workspace and output,
+    replayed round-robin so that `depth` BATCHES are in flight on the GPU at once.
+
+    A rank that owns a single sub-model (one sub-model per GPU on 4 or 8 GPUs), or the single
+    teacher model, runs one kernel chain: every persistent kernel alternates tensor-bound and
+    memory-bound phases and leaves its last round of tiles partly empty (99 pair-tiles on 74
+    cluster slots at 128 images).  Consecutive batches of an evaluation loop are independent, so a
+    second batch on a second stream fills those holes exactly like a second sub-model does at N = 1
+    (measured on one GPU, profiles/r2_time_pipeline.txt: 1 sub-model x 256 images 2.08 -> 1.91 ms per
+    batch, x 128 images 1.28 -> 1.00 ms).  Latency per batch grows, throughput is what is reported.
+
+    `steps`: one zero-argument callable per slot returning the slot's output tensor; across ranks
+    every slot must use its OWN communicator (collectives of different slots run concurrently)."""
+
+    def __init__(self, steps, capture: bool = True):
+        cur = torch.cuda.current_stream()
+        self.steps = list(steps)
+        self.streams = [torch.cuda.Stream() for _ in self.steps]
+        self.graphs, self.outs = [], []
+        for st, fn in zip(self.streams, self.steps):
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                for _ in range(2):  # builds this stream's workspaces outside the capture
+                    out = fn()
+            torch.cuda.synchronize()
+            g = None
+            if capture:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=st):
+                    out = fn()
+                with torch.cuda.stream(st):
+                    g.replay()  # a capture does not execute: fill `out` once
+            self.graphs.append(g)
+            self.outs.append(out)
+        torch.cuda.synchronize()
+        self._next = 0
+
+    @property
+    def depth(self) -> int:
+        return len(self.steps)
+
+    def fork(self):
+        """Order the slots' streams after the work already queued on the current stream."""
+        cur = torch.cuda.current_stream()
+        for st in self.streams:
+            st.wait_stream(cur)
+
+    def launch(self) -> int:
+        """Enqueue the next step on its slot's stream; returns the slot (its result is in
+        `outs[slot]` once that stream has run it; the slot's previous result is overwritten)."""
+        k = self._next % len(self.steps)
+        self._next += 1
+        with torch.cuda.stream(self.streams[k]):
+            if self.graphs[k] is not None:
+                self.graphs[k].replay()
+            else:
+                self.outs[k] = self.steps[k]()
+        return k
+
+    def join(self):
+        """Make the current stream wait for everything the slots have been given."""
+        cur = torch.cuda.current_stream()
+        for st in self.streams:
+            cur.wait_stream(st)

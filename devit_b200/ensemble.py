@@ -67,7 +67,11 @@ _SIDE_STREAMS = {}
 
 
 def _side_streams(device, n):
-    pool = _SIDE_STREAMS.setdefault(str(device), [])
+    """Side streams of the CURRENT stream: every parent stream gets its own set, so two forwards
+    running concurrently on two streams (parallel.BatchPipeline slots) never share a side stream
+    -- and with it a workspace, which packing.workspace keys by stream."""
+    key = (str(device), torch.cuda.current_stream(device).cuda_stream)
+    pool = _SIDE_STREAMS.setdefault(key, [])
     while len(pool) < n:
         pool.append(torch.cuda.Stream(device=device))
     return pool[:n]

@@ -380,3 +380,25 @@ def test_ensmlp_does_not_trust_a_stale_slab():
     ref3[2].zero_()
     want3 = fuse((ref3, [t.clone() for t in dist]))
     assert rel(out3, want3) < 1e-5
+
+
+def test_batch_pipeline_two_batches_in_flight():
+    """parallel.BatchPipeline: two slots (own stream / CUDA graph / workspace / side streams each)
+    replayed round-robin give, slot for slot, exactly the plain forward's logits -- also for a rank
+    that runs two sub-models as concurrent chains inside every slot."""
+    from devit_b200 import parallel
+    mv, fuse = make_ensemble('bf16', True)
+    xs = [synth.images(B, seed=11).cuda(), synth.images(B, seed=12).cuda()]
+    want = [fuse(mv(x)).clone() for x in xs]
+    plan = parallel.shard_plan(1, 0, N_SUB, B)
+    slots = [parallel.ShardedEnsemble(mv, fuse, plan) for _ in xs]
+    pipe = parallel.BatchPipeline([(lambda e=e, x=x: e(x)) for e, x in zip(slots, xs)])
+    assert pipe.depth == 2
+    for rep in range(3):
+        pipe.fork()
+        for _ in range(4):
+            pipe.launch()
+        pipe.join()
+        torch.cuda.synchronize()
+        for k in range(2):
+            assert torch.equal(pipe.outs[k], want[k]), (rep, k)

@@ -1,0 +1,8 @@
+#!/bin/bash
+cd "$(dirname "$0")/.."
+export DEVIT_BENCH_WATCHDOG_S=170
+N=$1; shift
+for c in "$@"; do
+  timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29581 bench.py --gpus $N --config $c --steps 20 --warmup 5 > gpurun_out/bench_r2_v14_${c}_n$N.json 2> gpurun_out/bench_r2_v14_${c}_n$N.err
+  echo "rc=$?" >> gpurun_out/bench_r2_v14_${c}_n$N.err
+done

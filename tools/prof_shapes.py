@@ -58,9 +58,11 @@ if which in ("projmlp", "all"):
         hh = H if F_ == F else 6
         o, w_proj, b_proj = rnd(M, 64 * hh), rnd(D, 64 * hh, scale=.05), rnd(D, dt=torch.float32)
         so = torch.empty(4, M, 2, device=dev)
+        lo = torch.zeros(M, D, device=dev, dtype=torch.bfloat16)
         for _ in range(reps):
-            L.mlp_fused(x, None, None, w1, c11, c21, w2, b2, 1e-6, xb_out=xb, stats_out=so,
-                        o=o, w_proj=w_proj, b_proj=b_proj)
+            # the steady state inside a model: residual stream as hi (xb) + lo planes in and out
+            L.mlp_fused(x, xb, None, w1, c11, c21, w2, b2, 1e-6, xb_out=xb, stats_out=so,
+                        o=o, w_proj=w_proj, b_proj=b_proj, x_lo_in=lo, x_lo_out=lo)
 if which in ("attn", "all"):
     qkv = rnd(M, 192 * H)
     for _ in range(reps):

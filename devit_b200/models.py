@@ -306,6 +306,12 @@ class VisionTransformer(nn.Module):
     def _init_weights(self, m):
         _init_vit_weights(m)
 
+    @torch.jit.ignore()
+    def load_pretrained(self, checkpoint_path, prefix=''):
+        """models/de_vit.py:223-224: Google-Brain Flax .npz checkpoint -> parameters."""
+        from .npz_loader import load_npz
+        load_npz(self, checkpoint_path, prefix)
+
     @torch.jit.ignore
     def no_weight_decay(self):
         return {'pos_embed', 'cls_token', 'dist_token'}
@@ -739,14 +745,18 @@ def dedeit(pretrained=False, pretrained_path=None, **kwargs):
 
 @register_model
 def devit(pretrained=False, pretrained_path=None, **kwargs):
-    """models/de_vit.py:506-513 (npz loading of Google checkpoints is load-time host work that
-    the reference delegates to timm helpers; a torch state_dict path is accepted here)."""
+    """models/de_vit.py:506-513: `pretrained_path` is a Flax .npz archive, read by
+    load_pretrained like the reference does (devit_b200/npz_loader.py); a torch checkpoint
+    (.pth / .pt, optionally wrapped in {'model': ...}) is accepted as well."""
     model = VisionTransformer(patch_size=16, embed_dim=384, depth=12, num_heads=6, mlp_ratio=4,
                               qkv_bias=True, norm_layer=partial(nn.LayerNorm, eps=1e-6), **kwargs)
     model.default_cfg = _cfg()
     if pretrained_path is not None and pretrained:
-        sd = torch.load(pretrained_path)
-        model.load_state_dict(checkpoint_filter_fn(sd, model))
+        if str(pretrained_path).endswith(('.pth', '.pt')):
+            sd = torch.load(pretrained_path)
+            model.load_state_dict(checkpoint_filter_fn(sd, model))
+        else:
+            model.load_pretrained(checkpoint_path=pretrained_path)
     return model
 
 

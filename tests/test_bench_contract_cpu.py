@@ -9,8 +9,11 @@ ROOT = Path(__file__).resolve().parents[1]
 
 
 def test_reference_arm_prints_one_contract_line():
+    import os
+    env = dict(os.environ, DEVIT_REF_BUDGET_S='8')  # a small per-step sample keeps the CPU suite short
     r = subprocess.run([sys.executable, str(ROOT / 'bench.py'), '--impl', 'reference', '--steps', '1',
-                        '--warmup', '1'], capture_output=True, text=True, timeout=600, cwd=ROOT)
+                        '--warmup', '1'], capture_output=True, text=True, timeout=600, cwd=ROOT,
+                       env=env)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.startswith('{')]
     assert len(lines) == 1

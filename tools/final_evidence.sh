@@ -1,5 +1,6 @@
 #!/bin/bash
-# final single-GPU evidence: full GPU test suite, smoke, bench (all configs), reference arm, ncu
+# single-GPU evidence of a round: full GPU test suite, smoke, bench (all configs), reference arm,
+# ncu launch list + full capture of the dominant kernel -> gpurun_out/final_*   (gpurun -- "bash tools/final_evidence.sh")
 cd "$(dirname "$0")/.."
 timeout 1400 python -m pytest tests -m gpu -q > gpurun_out/final_pytest_gpu.txt 2>&1; echo "rc=$?" >> gpurun_out/final_pytest_gpu.txt
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/final_smoke.txt 2>&1; echo "rc=$?" >> gpurun_out/final_smoke.txt

@@ -71,6 +71,7 @@ int main() {
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   const int rows_per_cta = (int)(per_cta / 1536);
+  CK(cudaFuncSetAttribute(k_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 4096 + 1024));
   for (int ctas : {1, 16, 74, 148}) {
     CUtensorMap tm;
     cuuint64_t dims[2] = {384, (cuuint64_t)rows_per_cta * ctas};

@@ -547,7 +547,7 @@ def main():
             raise SystemExit("[bench] a pipelined slot disagrees with the plain step")
 
         def run_pipe(n):
-            pipe._next = 0
+            pipe.reset()
             pipe.fork()
             for _ in range(n):
                 pipe.launch()
@@ -618,7 +618,7 @@ def main():
 
     def e2e_loop(n):
         if e2e_pipe is not None:
-            e2e_pipe._next = 0
+            e2e_pipe.reset()
             e2e_pipe.fork()
         for i in range(n + 1):
             if i < n:  # prefetch batch i
@@ -878,7 +878,7 @@ def main():
                 dpipe = parallel.BatchPipeline([(lambda e=e: e(x_dev)) for e in eds])
 
                 def run_dpipe(n):
-                    dpipe._next = 0
+                    dpipe.reset()
                     dpipe.fork()
                     for _ in range(n):
                         dpipe.launch()

@@ -207,6 +207,10 @@ class BatchPipeline:
     def depth(self) -> int:
         return len(self.steps)
 
+    def reset(self):
+        """Next launch() goes to slot 0 again (callers that pair slots with input buffers)."""
+        self._next = 0
+
     def fork(self):
         """Order the slots' streams after the work already queued on the current stream."""
         cur = torch.cuda.current_stream()

@@ -315,3 +315,55 @@ def test_timm_registration_failures_are_logged_not_swallowed(monkeypatch, caplog
     assert calls == ['my_model']
     registry._ENTRYPOINTS.pop('my_model')
     registry.TIMM_FAILURES.pop('my_model')
+
+
+def test_chain_scheduling_policy(monkeypatch):
+    """ensemble.chain_tasks / batch_chunks / chain_sm_budget: the host-side plan of the concurrent
+    kernel chains (no GPU needed: pure bookkeeping)."""
+    from devit_b200 import ensemble
+    for k in ('DEVIT_CHAINS', 'DEVIT_MIN_CHUNK', 'DEVIT_SM_SHARE', 'DEVIT_SUB_STREAMS'):
+        monkeypatch.delenv(k, raising=False)
+    # default: one chain per local sub-model, no batch chunking
+    assert ensemble.batch_chunks(1, 256) == 1 and ensemble.batch_chunks(4, 256) == 1
+    assert ensemble.chain_tasks([0, 2], 256) == [(0, 0, None), (1, 2, None)]
+    assert ensemble.sub_streams() == 4
+    # asking for ~4 chains on a rank with one sub-model cuts the batch, never below the minimum
+    monkeypatch.setenv('DEVIT_CHAINS', '4')
+    assert ensemble.batch_chunks(1, 256) == 4 and ensemble.batch_chunks(1, 128) == 2
+    assert ensemble.batch_chunks(2, 256) == 2 and ensemble.batch_chunks(4, 256) == 1
+    tasks = ensemble.chain_tasks([3], 250)
+    assert [t[2] for t in tasks] == [(0, 83), (83, 166), (166, 250)]  # covers every image once
+    monkeypatch.setenv('DEVIT_MIN_CHUNK', '200')
+    assert ensemble.batch_chunks(1, 256) == 1
+
+
+def test_collapsed_fusion_head_algebra():
+    """EnsMLP._collapsed pre-multiplies the two Linears of a token kind (no activation between
+    them, models/ensemble_models.py:79-84): W = classifier.weight @ mlp.weight,
+    b = classifier.weight @ mlp.bias + classifier.bias, summed over cls / dist and halved by the
+    GEMM's alpha.  Check the algebra against the two-level evaluation in fp64 on the CPU."""
+    import torch
+    from devit_b200 import ensemble, synth
+    n, D, C = 4, 384, 100
+    fuse = ensemble.EnsMLP(model='dedeit', num_class=C, sub_size=D,
+                           num_classes_list=[25] * n, teacher_size=768)
+    fuse.load_state_dict(synth.ensmlp_state_dict(n, num_class=C))
+    fuse.set_precision('fp32')
+    wcat, bias, wk, bk = fuse._collapsed(torch.device('cpu'))
+    w = (wcat[0] + wcat[1]).double()          # hi + lo planes of the split-tf32 operand
+    assert w.shape == (C, 2 * n * D)
+    g = torch.Generator().manual_seed(3)
+    fc = torch.randn(5, n * D, generator=g, dtype=torch.float64)
+    fd = torch.randn(5, n * D, generator=g, dtype=torch.float64)
+    sd = {k: v.double() for k, v in fuse.state_dict().items()}
+    two_level = 0.5 * (
+        (fc @ sd['cls_mlp.weight'].t() + sd['cls_mlp.bias']) @ sd['cls_classifier.weight'].t()
+        + sd['cls_classifier.bias']
+        + (fd @ sd['dist_mlp.weight'].t() + sd['dist_mlp.bias']) @ sd['dist_classifier.weight'].t()
+        + sd['dist_classifier.bias'])
+    one_gemm = 0.5 * (torch.cat([fc, fd], 1) @ w.t() + bias.double())
+    assert (one_gemm - two_level).abs().max() / two_level.abs().max() < 1e-6
+    # the per-kind pair used when 2 n > 8 K-segments: cls first (bias 0), dist second (whole bias)
+    assert float(bk[0].abs().max()) == 0.0 and torch.equal(bk[1], bias)
+    wc, wd = (wk[0][0] + wk[0][1]).double(), (wk[1][0] + wk[1][1]).double()
+    assert torch.equal(torch.cat([wc, wd], 1), w)

@@ -60,13 +60,13 @@ ProfScope::ProfScope(int tag, cudaStream_t s) : stream(s), on(g_prof_on) {
     return;
   }
   cudaEventRecord(r.a, stream);
+  end_event = r.b;
   std::lock_guard<std::mutex> lk(g_prof_mu);
   g_prof.push_back(r);
 }
 ProfScope::~ProfScope() {
   if (!on) return;
-  std::lock_guard<std::mutex> lk(g_prof_mu);
-  cudaEventRecord(g_prof.back().b, stream);
+  cudaEventRecord(static_cast<cudaEvent_t>(end_event), stream);
 }
 
 struct DevInfo {

@@ -25,6 +25,8 @@ enum ProfTag {
 struct ProfScope {
   cudaStream_t stream;
   bool on;
+  void* end_event = nullptr;  // this scope's own stop event (launches on other threads / streams
+                              // may open scopes in between)
   ProfScope(int tag, cudaStream_t s);
   ~ProfScope();
 };

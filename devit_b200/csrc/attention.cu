@@ -327,7 +327,7 @@ template <int KVP>
 __global__ void __launch_bounds__(kPersistThreads, 1)
 attn_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                     __nv_bfloat16* __restrict__ out, int tokens, int heads, int num_items,
-                    float scale_log2e, int dephase, long long* trace) {
+                    float scale_log2e, int dephase, int poll_ns, long long* trace) {
   using Cfg = AttnPersistCfg<KVP>;
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
@@ -466,7 +466,7 @@ attn_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           }
         }
       }
-      if (!progress) __nanosleep(40);  // leave the issue slots to the softmax warps
+      if (!progress && poll_ns > 0) __nanosleep(poll_ns);  // leave issue slots to the softmax warps
     }
   } else if (warp < 8) {
     // ------------------------------------------------------------ softmax warps
@@ -770,6 +770,7 @@ static int launch_attn_persist(const void* qkv, void* out, int batch, int tokens
   const int items = batch * heads;
   const int grid = items < num_sms() ? items : num_sms();
   static int env_lockstep = kEnvUnread;  // debug: issue both query tiles in lock-step
+  static int env_poll = kEnvUnread;      // control warp's back-off between barrier probes (ns)
   {
     ProfScope ps(kTagAttention, stream);
     cudaLaunchConfig_t cfg = {};
@@ -786,7 +787,7 @@ static int launch_attn_persist(const void* qkv, void* out, int batch, int tokens
                                      static_cast<__nv_bfloat16*>(out), tokens, heads, items,
                                      scale * 1.4426950408889634f,
                                      env_int("DEVIT_ATTN_LOCKSTEP", 0, &env_lockstep) ? 0 : 1,
-                                     g_attn_trace));
+                                     env_int("DEVIT_ATTN_POLL_NS", 40, &env_poll), g_attn_trace));
   }
   DEVIT_CUDA_OK(cudaGetLastError());
   count_launch();

@@ -100,7 +100,9 @@ def run_chains(device, tasks, launch):
     residual read / write) that do not overlap inside one CTA; two unrelated kernels on the two
     halves of the chip fill each other's gaps, and a chain's partly filled last round of tiles no
     longer idles the SMs it does not use.  Measured on the 4-way bs-256 step: 9.93 -> 8.7 ms.
-    Results are bit-identical to the single-chain order (every row's arithmetic is unchanged)."""
+    Results are bit-identical to the single-chain order (every row's arithmetic is unchanged).
+    The SM budget is a process-wide setting of the library: forwards issued from several host
+    threads at once would see each other's budget (a performance matter only, never correctness)."""
     on_cuda = device.type == 'cuda'
     n_st = max(1, min(len(tasks), sub_streams())) if on_cuda and not L.profiling() else 1
     if n_st == 1:

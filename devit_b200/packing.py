@@ -99,13 +99,23 @@ class PackedVit:
         attn, mlp = blk.attn, blk.mlp
         w = L.BlockWeights()
         w.dim, w.num_heads, w.hidden = dim, attn.num_heads, mlp.hidden_features
+        tmp = []  # fp32 device copies only devit_pack_layer reads (it synchronises before returning)
+
+        def t32(t):
+            t = t.detach().to(device=self.device, dtype=torch.float32).contiguous()
+            tmp.append(t)
+            return t.data_ptr()
+
+        # the descriptor keeps pointing at these (LayerNorm parameters, proj / fc2 bias): kept alive
         w.ln1_g, w.ln1_b = f32(blk.norm1.weight), f32(blk.norm1.bias)
-        w.w_qkv = f32(attn.qkv.weight)
-        w.b_qkv = f32(attn.qkv.bias) if attn.qkv.bias is not None else None
-        w.w_proj, w.b_proj = f32(attn.proj.weight), f32(attn.proj.bias)
         w.ln2_g, w.ln2_b = f32(blk.norm2.weight), f32(blk.norm2.bias)
-        w.w_fc1, w.b_fc1 = f32(mlp.fc1.weight), f32(mlp.fc1.bias)
-        w.w_fc2, w.b_fc2 = f32(mlp.fc2.weight), f32(mlp.fc2.bias)
+        w.b_proj, w.b_fc2 = f32(attn.proj.bias), f32(mlp.fc2.bias)
+        # read once by the pack kernels
+        w.w_qkv = t32(attn.qkv.weight)
+        w.b_qkv = t32(attn.qkv.bias) if attn.qkv.bias is not None else None
+        w.w_proj = t32(attn.proj.weight)
+        w.w_fc1, w.b_fc1 = t32(mlp.fc1.weight), t32(mlp.fc1.bias)
+        w.w_fc2 = t32(mlp.fc2.weight)
         hg = attn.gate.detach().float().cpu().contiguous()
         ng = mlp.gate.detach().float().cpu().contiguous()
         if hg.numel() != attn.num_heads or ng.numel() != mlp.hidden_features:

@@ -7,7 +7,7 @@
 //     K-major, 128B swizzle) and streams W1 / W2 in 64-neuron chunks through two 2-slot rings;
 //     each CTA stages HALF of every weight chunk (the pair's MMA reads both halves).
 //   * GEMM1 chunk c: acc1[c&1] (128 x 64 fp32 per CTA, TMEM columns 384 + 64 (c&1)) = Y W1_c^T.
-//   * 8 epilogue warps turn acc1 into H_c = gelu(rstd (acc - mean c1) + c2)  (LayerNorm folded
+//   * 16 epilogue warps turn acc1 into H_c = gelu(rstd (acc - mean c1) + c2)  (LayerNorm folded
 //     into the epilogue, see devit_gemm_args.ln_stats) and write it back INTO TMEM as packed
 //     bf16 pairs over columns they have already consumed.
 //   * GEMM2 chunk c: acc2 (128 x 384 fp32, TMEM columns [0, 384)) += H_c W2_c^T with the A operand
@@ -25,12 +25,16 @@
 // PROJ variant (devit_mlp_args.o != NULL): the attention-output projection and its residual add
 // (models/de_vit.py:81-82, :114) run in the SAME kernel in front of the MLP:
 //     x1 = x + o Wp^T + bp ;  x = x1 + gelu( LN(x1) W1^T + b1 ) W2^T + b2
-// so the residual stream makes ONE fp32 round trip through HBM per layer instead of two and
-// neither x1, its bf16 copy nor its row statistics ever exist in global memory.  Per pair-tile:
+// so the residual stream makes ONE round trip through HBM per layer instead of two and neither
+// x1, its bf16 copy nor its row statistics ever exist in global memory.  Between fused layers the
+// stream travels as two bf16 planes, x = hi + lo (x_lo_in / x_lo_out: an SM stores ~32 B/clk, so
+// 4 bytes per element instead of fp32 + bf16 copy = 6 shorten the write-bound final epilogue; hi
+// is the next QKV GEMM's operand); the first layer reads and the last one writes fp32.
+// Per pair-tile:
 //   * the attention output tile O (128 x 64h bf16 per CTA) is TMA-loaded into the Y buffer and
 //     Wp streams through the W2 ring, one 64-wide head chunk at a time;
-//   * preload: every epilogue warp brings the fp32 residual of its 32 rows x D/4 columns into its
-//     two private 4 KB slots by TMA (requested while the PREVIOUS tile's stores drain; the slots
+//   * preload: every epilogue warp brings the residual (fp32, or hi + lo planes) of its 32 rows x
+//     D/4 columns into its two private 4 KB slots by TMA (requested while the PREVIOUS tile's stores drain; the slots
 //     lie over the weight rings and the staging buffer, never over Y, so the next tile's O is
 //     loaded as soon as the last GEMM1 has retired), adds bp
 //     and writes x + bp INTO acc2 (tcgen05.st), so the HBM-latency-bound part of the residual add
@@ -42,7 +46,8 @@
 //     128B-swizzled layout GEMM1 reads.  The four partial row sums of a row meet in shared memory
 //     (one named barrier), giving the exact LayerNorm statistics of x1;
 //   * the hidden-chunk loop is unchanged (GEMM2 accumulates on top of x1); the final epilogue
-//     adds b2 and has no residual to fetch.
+//     adds b2, has no residual to fetch, and stores hi / lo planes (or fp32 x + a bf16 copy written
+//     straight from registers) through the same two slots.
 #include <cstdlib>
 
 #include "common.cuh"

@@ -574,9 +574,12 @@ def main():
     # ---- e2e: public API with host buffers; H2D of the step's batch + D2H of its logits inside
     #      the timed region, input copies double-buffered on a copy stream
     copy_stream = torch.cuda.Stream()
-    bufs = [torch.empty_like(x_dev), torch.empty_like(x_dev)]
-    ready = [torch.cuda.Event(), torch.cuda.Event()]
-    freed = [torch.cuda.Event(), torch.cuda.Event()]
+    # input buffers: two when the steps run one after the other (copy i+1 under compute i); four
+    # when two batches are in flight, so that the uploads can run ahead of both computing slots
+    nbuf = 4 if pipe is not None else 2
+    bufs = [torch.empty_like(x_dev) for _ in range(nbuf)]
+    ready = [torch.cuda.Event() for _ in range(nbuf)]
+    freed = [torch.cuda.Event() for _ in range(nbuf)]
     out_host = torch.empty(Bg, wl.classes).pin_memory()
     main_stream = torch.cuda.current_stream()
 
@@ -585,13 +588,14 @@ def main():
     e2e_graphs = None
     e2e_pipe = None
     if pipe is not None:
-        # two input buffers = two slots: buffer b is consumed by slot b (its own stream / graph /
-        # communicator), so the compute of batch i overlaps that of batch i + 1 as in `value`
-        for b in range(2):
+        # one slot (CUDA graph) per input buffer on `depth` streams: buffer b is consumed on stream
+        # b % depth with that stream's communicator, so the compute of batch i overlaps that of
+        # batch i + 1 as in `value`, and the uploads fill the other buffers meanwhile
+        for b in range(nbuf):
             bufs[b].copy_(x_dev)
         torch.cuda.synchronize()
         e2e_pipe = parallel.BatchPipeline([(lambda e=ens_slots[b % depth], b=b: e(bufs[b]))
-                                           for b in range(2)])
+                                           for b in range(nbuf)], n_streams=depth)
     elif graph is not None:
         ok = True
         try:
@@ -614,7 +618,7 @@ def main():
 
     use_stage = world > 1 and fuse is not None and parallel.stage_slice(plan, Bg) is not None
 
-    out_hosts = [out_host, torch.empty_like(out_host).pin_memory()]
+    out_hosts = [out_host] + [torch.empty_like(out_host).pin_memory() for _ in range(nbuf - 1)]
 
     def e2e_loop(n):
         if e2e_pipe is not None:
@@ -622,7 +626,7 @@ def main():
             e2e_pipe.fork()
         for i in range(n + 1):
             if i < n:  # prefetch batch i
-                b = i & 1
+                b = i % nbuf
                 with torch.cuda.stream(copy_stream):
                     copy_stream.wait_event(freed[b])
                     if use_stage:
@@ -631,7 +635,7 @@ def main():
                         bufs[b].copy_(x_host, non_blocking=True)
                     ready[b].record(copy_stream)
             if i > 0 and e2e_pipe is not None:  # compute batch i-1 on slot b's stream
-                b = (i - 1) & 1
+                b = (i - 1) % nbuf
                 st = e2e_pipe.streams[b]
                 st.wait_event(ready[b])
                 e2e_pipe.launch()
@@ -640,7 +644,7 @@ def main():
                     out_hosts[b].copy_(e2e_pipe.outs[b], non_blocking=True)
                 continue
             if i > 0:  # compute batch i-1
-                b = (i - 1) & 1
+                b = (i - 1) % nbuf
                 main_stream.wait_event(ready[b])
                 if e2e_graphs is not None:
                     e2e_graphs[b][0].replay()
@@ -657,18 +661,18 @@ def main():
     # [r Bg/G, (r+1) Bg/G) and an NVLink all-gather assembles the batch (1/G of the PCIe bytes per
     # rank).  Checked against the device-resident result before it is timed; any disagreement
     # (on any rank) falls back to every rank copying the whole batch.
-    for b in range(2):
+    for b in range(nbuf):
         freed[b].record(main_stream)
-    e2e_loop(3)
+    e2e_loop(nbuf + 1)
     if use_stage:
         if not all_ranks(torch.equal(out_host.to(dev), logits)):
             if rank == 0:
                 print("[bench] staged input gave different logits; timing full per-rank copies",
                       file=sys.stderr)
             use_stage = False
-            for b in range(2):
+            for b in range(nbuf):
                 freed[b].record(main_stream)
-            e2e_loop(3)
+            e2e_loop(nbuf + 1)
     e2e_ok = all_ranks(torch.equal(out_host.to(dev), logits))
     parity["e2e_equals_resident"] = e2e_ok
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -180,10 +180,16 @@ class BatchPipeline:
     `steps`: one zero-argument callable per slot returning the slot's output tensor; across ranks
     every slot must use its OWN communicator (collectives of different slots run concurrently)."""
 
-    def __init__(self, steps, capture: bool = True):
+    def __init__(self, steps, capture: bool = True, n_streams: int = 0):
+        """n_streams (0 = one per step): slot k runs on stream k % n_streams.  More slots than
+        streams = several input / output buffers per in-flight batch (slots that share a stream
+        never overlap, so they may share a communicator): an input pipeline can then fill the
+        buffers of later slots while the earlier ones compute."""
         cur = torch.cuda.current_stream()
         self.steps = list(steps)
-        self.streams = [torch.cuda.Stream() for _ in self.steps]
+        n_streams = len(self.steps) if n_streams <= 0 else min(n_streams, len(self.steps))
+        pool = [torch.cuda.Stream() for _ in range(n_streams)]
+        self.streams = [pool[k % n_streams] for k in range(len(self.steps))]
         self.graphs, self.outs = [], []
         for st, fn in zip(self.streams, self.steps):
             st.wait_stream(cur)
@@ -214,7 +220,7 @@ class BatchPipeline:
     def fork(self):
         """Order the slots' streams after the work already queued on the current stream."""
         cur = torch.cuda.current_stream()
-        for st in self.streams:
+        for st in set(self.streams):
             st.wait_stream(cur)
 
     def launch(self) -> int:
@@ -232,5 +238,5 @@ class BatchPipeline:
     def join(self):
         """Make the current stream wait for everything the slots have been given."""
         cur = torch.cuda.current_stream()
-        for st in self.streams:
+        for st in set(self.streams):
             cur.wait_stream(st)

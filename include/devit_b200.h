@@ -9,7 +9,8 @@
  * Conventions
  *  - every pointer is a DEVICE pointer unless stated; the caller owns all memory;
  *  - all work is enqueued on `stream` (a cudaStream_t passed as void*), no hidden syncs,
- *    safe to capture in a CUDA graph;
+ *    safe to capture in a CUDA graph (the two entries that do synchronise say so:
+ *    the one-off devit_pack_layer and the measurement hook devit_profile_collect);
  *  - return value 0 = ok, otherwise a DEVIT_ERR_* code; devit_last_error() gives the text;
  *  - there is no CPU fallback: on a device that is not sm_100 every launch returns
  *    DEVIT_ERR_DEVICE.

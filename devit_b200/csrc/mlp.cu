@@ -242,10 +242,10 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
   // with an HBM-bound one (final epilogue + refill: ~0.6 MB per CTA).  Started together, all
   // 148 SMs stream at the same time and compute at the same time; delaying every other cluster
   // by about half a tile lets one half compute while the other half owns the HBM.
-  // Mode 1 (DEVIT_MLP_STAGGER_MODE=1, not yet measured): delay only the clusters that own one
-  // tile fewer than the busiest ones -- they have a whole tile time of slack, so the delay is free
-  // for the kernel's end time (198 pair-tiles over 74 clusters: 24 such clusters; 99 tiles at
-  // N = 8: 49).
+  // Mode 1 (DEVIT_MLP_STAGGER_MODE=1): delay only the clusters that own one tile fewer than the
+  // busiest ones -- they have a whole tile time of slack (198 pair-tiles over 74 clusters: 24 such
+  // clusters; 99 tiles at N = 8: 49).  Measured 104.8 vs 106.4 us at 30 k clocks, inside the
+  // run-to-run spread (profiles/r2_ab_projmlp_sm.txt): mode 0 stays the default.
   const bool delayed = p.stagger_mode == 1
       ? (num_pairs > num_clusters && cluster_id >= num_pairs % num_clusters &&
          num_pairs % num_clusters != 0)

@@ -1,7 +1,8 @@
 #!/bin/bash
-# A/B experiments queued at the end of round 1 (no GPU minutes were left to run them).  One gpurun
-# call, ~1 minute:   gpurun --timeout 300 -- 'bash tools/ab_queue.sh > gpurun_out/ab_queue.txt 2>&1'
-# Results decide two defaults:
+# A/B experiments queued at the end of round 1 and run first thing in round 2
+# (profiles/r2_ab_queue_mlp_stagger.txt).  One gpurun call, ~1 minute:
+#   gpurun --timeout 300 -- 'bash tools/ab_queue.sh > gpurun_out/ab_queue.txt 2>&1'
+# They decided two defaults (both kept: stagger mode 0 at 10 k clocks, token table on):
 #  1. DEVIT_MLP_STAGGER_MODE=1 (delay only the clusters with a tile less) vs the current mode 0,
 #     at the bs-256 shape (198 pair-tiles / 74 clusters) and at the bs-128 shape of the 8-GPU run.
 #  2. DEVIT_TOK_TABLE=1 (periodic-residual patch GEMM, current default) vs 0, whole bench step.

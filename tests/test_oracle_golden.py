@@ -106,3 +106,20 @@ def test_oracle_fp64_noise_floor(sds, x):
         c32, _ = O.forward_features(sds[0], x[:1])
         c64, _ = O.forward_features(O.to_dtype(sds[0], torch.float64), x[:1].double())
     assert rel(c32.numpy(), c64.numpy()) < 2e-5
+
+
+def test_fp32_oracle_noise_floor_against_fp64(sds, x):
+    """the same graph in fp64 is the ground truth that arbitrates fp32
+    disagreements.  The fp32 oracle sits ~1e-6 from it -- two orders of magnitude under the 1e-4
+    bar the fp32/3xTF32 GPU mode is held to -- and picks the same classes."""
+    esd = synth.ensmlp_state_dict(N_SUB)
+    gates = [synth.shrink_gates(s) for s in range(N_SUB)]
+    with torch.no_grad():
+        l32, c32, _ = O.ensemble_logits(sds, esd, x, gates)
+        l64, c64, _ = O.ensemble_logits([O.to_dtype(sd, torch.float64) for sd in sds],
+                                        O.to_dtype(esd, torch.float64), x.double(), gates)
+    assert l64.dtype == torch.float64
+    floor = rel(l32.numpy(), l64.numpy())
+    assert floor < 5e-6, floor
+    assert rel(torch.stack(c32).numpy(), torch.stack(c64).numpy()) < 5e-6
+    assert torch.equal(l32.argmax(-1), l64.argmax(-1))

@@ -100,14 +100,6 @@ def test_keep_mask_edge_cases():
     assert list(O.kept_indices(O.keep_mask(6, 0.49, np.array([5, 0, 3, 1, 4, 2])))) == [1, 2, 4]
 
 
-def test_oracle_fp64_noise_floor(sds, x):
-    """fp32 oracle vs its own fp64 evaluation: the oracle's noise floor is far below 1e-4."""
-    with torch.no_grad():
-        c32, _ = O.forward_features(sds[0], x[:1])
-        c64, _ = O.forward_features(O.to_dtype(sds[0], torch.float64), x[:1].double())
-    assert rel(c32.numpy(), c64.numpy()) < 2e-5
-
-
 def test_fp32_oracle_noise_floor_against_fp64(sds, x):
     """the same graph in fp64 is the ground truth that arbitrates fp32
     disagreements.  The fp32 oracle sits ~1e-6 from it -- two orders of magnitude under the 1e-4
